@@ -1,0 +1,171 @@
+/*
+ * psx.h -- C ABI of the B200-native dense-recall engine ("psx" = photo-search exact scan).
+ *
+ * This is the drop-in boundary below the reference's Python class
+ * `utils/vector_store.py::VectorStore`.  In the reference that class binds the third-party
+ * faiss-cpu SWIG module; each entry point below names the FAISS call (and the reference
+ * file:line that makes it) which it replaces.  Signatures are plain C: pointers, sizes and
+ * integer codes only -- no torch / C++ types.
+ *
+ * Conventions
+ *   - every function returns PSX_OK (0) or a negative psx_status; psx_last_error() gives a
+ *     thread-local human readable message for the last failure on the calling thread;
+ *   - "host" pointers are ordinary CPU memory owned by the caller, "dev" pointers are CUDA
+ *     device memory on the index' device, `stream` is a cudaStream_t passed as void*
+ *     (NULL = the index' own stream);
+ *   - row ids are 0-based insertion order, exactly as FAISS labels (utils/vector_store.py:194-197);
+ *     unfilled result slots are id -1 with score -inf (inner product) / +inf (L2), as FAISS
+ *     leaves them (utils/vector_store.py:195 skips label -1);
+ *   - results are ordered best first; equal scores are ordered by lower id first;
+ *   - a handle may be used from several threads; calls on one handle are serialised internally.
+ *   - there is NO CPU fallback: every compute entry point fails with PSX_ERR_CUDA when no
+ *     sm_100 device is usable.
+ */
+#ifndef PSX_H_
+#define PSX_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PSX_ABI_VERSION 1
+
+typedef enum psx_status {
+    PSX_OK = 0,
+    PSX_ERR_INVALID = -1,   /* bad argument (dimension mismatch, k <= 0, null pointer ...) */
+    PSX_ERR_CUDA = -2,      /* CUDA runtime / driver failure, or no usable device */
+    PSX_ERR_OOM = -3,       /* device or host allocation failed */
+    PSX_ERR_RANGE = -4,     /* row id out of range */
+    PSX_ERR_STATE = -5      /* call not valid in the current state */
+} psx_status;
+
+/* faiss.METRIC_INNER_PRODUCT / faiss.METRIC_L2 as used at utils/vector_store.py:73-81,92-101 */
+#define PSX_METRIC_IP 0
+#define PSX_METRIC_L2 1
+
+/* storage precision of the corpus in HBM; arithmetic is always fp32 accumulate */
+#define PSX_STORE_F32 0
+#define PSX_STORE_BF16 1
+
+/* hard upper bound of k for ONE scan pass; larger k is served by paging inside psx_search */
+#define PSX_K_PASS_MAX 2048
+
+typedef struct psx_index psx_index; /* opaque */
+
+/* ---- EXIF predicate (core/searcher.py:1884-1950 `_check_time_match_v2`) -----------------
+ * One 64-bit attribute word per row:
+ *   bits  0..38  dt      0 = no parseable datetime, else 1 + seconds since 0001-01-01T00:00:00
+ *                         of `time_info.datetime_str or exif_data.datetime`
+ *   bits 39..42  month   time_info.month  (0 = None, 1..12, 15 = not representable)
+ *   bits 43..56  year    time_info.year   (0 = None, 1..16382, 16383 = not representable)
+ *   bits 57..59  period  time_info.time_period code (0 = None, 1..7 = the 7 day parts of
+ *                         core/indexer.py:583-598, in that order)
+ *   bits 60..62  season  time_info.season code (0 = None, 1 春天 2 夏天 3 秋天 4 冬天, 7 = other)
+ *   bit  63      exif    exif_data.datetime is truthy
+ * A row passes iff every active clause holds; a row without `exif` fails any of the
+ * season/period/year/month clauses, a row with dt == 0 fails an active range clause.
+ */
+#define PSX_F_SEASON 0x01u
+#define PSX_F_PERIOD 0x02u
+#define PSX_F_YEAR 0x04u
+#define PSX_F_MONTH 0x08u
+#define PSX_F_NEED_DT 0x10u /* start_date or end_date given (even if unparseable) */
+#define PSX_F_START 0x20u   /* `start` is valid */
+#define PSX_F_END 0x40u     /* `end` is valid   */
+
+typedef struct psx_filter {
+    uint32_t flags;
+    uint32_t season;
+    uint32_t period;
+    uint32_t year;
+    uint32_t month;
+    uint32_t reserved;
+    uint64_t start; /* dt encoding, inclusive */
+    uint64_t end;   /* dt encoding, inclusive */
+} psx_filter;
+
+/* ---- lifecycle ---------------------------------------------------------------------------- */
+
+/* Replaces faiss.IndexFlatIP(d) / faiss.IndexFlatL2(d) (utils/vector_store.py:72-81).
+ * `device` is a CUDA ordinal.  Fails with PSX_ERR_CUDA if the device is absent or not sm_100. */
+int psx_create(int d, int metric, int store_dtype, int device, psx_index** out);
+/* Replaces dropping the faiss index object. */
+int psx_destroy(psx_index* h);
+/* Replaces re-creating the index in VectorStore.clear() (utils/vector_store.py:273-280). */
+int psx_reset(psx_index* h);
+/* Replaces index.ntotal / index.d (utils/vector_store.py:183,188,255-258,271). */
+int64_t psx_ntotal(const psx_index* h);
+int psx_dim(const psx_index* h);
+int psx_metric(const psx_index* h);
+const char* psx_last_error(void);
+int psx_abi_version(void);
+
+/* ---- write side --------------------------------------------------------------------------- */
+
+/* Replaces index.add(np.float32 (n,d)) (utils/vector_store.py:163-164).  `x` is n*d host
+ * floats, row major, ALREADY normalised by the caller when the metric is cosine (the
+ * reference normalises in Python, utils/vector_store.py:83-90, before calling FAISS).
+ * Rows are staged on the host and uploaded lazily by the next search / psx_sync, so
+ * one-vector-at-a-time appends (core/indexer.py:858) do not launch anything. */
+int psx_add(psx_index* h, const float* x, int64_t n);
+/* Bulk ingest of rows already resident on the device (fp32, row major, n*d).  When
+ * `normalize` is non-zero every row is L2-normalised on the device first (zero rows are kept
+ * unchanged, as utils/vector_store.py:88-89).  Runs on `stream`. */
+int psx_add_device(psx_index* h, const float* x_dev, int64_t n, int normalize, void* stream);
+/* Pre-size the HBM arena for `n` rows in total (avoids regrowth copies). */
+int psx_reserve(psx_index* h, int64_t n);
+/* Upload everything staged by psx_add. */
+int psx_sync(psx_index* h);
+/* Attribute words for rows [row0, row0+n) (host pointer).  Rows never given a word hold 0
+ * (no EXIF), i.e. fail every active clause -- the reference's behaviour for photos without
+ * EXIF (core/searcher.py:1903-1927). */
+int psx_set_attrs(psx_index* h, int64_t row0, const uint64_t* attrs, int64_t n);
+int psx_set_attrs_device(psx_index* h, int64_t row0, const uint64_t* attrs_dev, int64_t n, void* stream);
+
+/* ---- read side ---------------------------------------------------------------------------- */
+
+/* Replaces index.search(np.float32 (nq,d), k) -> (D float32 (nq,k), I int64 (nq,k))
+ * (utils/vector_store.py:190-191).  Host buffers; `q` already normalised for cosine.
+ * `filter` may be NULL (no predicate).  Scores are inner products (best = largest) or
+ * squared L2 distances (best = smallest).  Any k >= 1 is accepted. */
+int psx_search(psx_index* h, const float* q, int64_t nq, int64_t k, const psx_filter* filter,
+               float* out_scores, int64_t* out_ids);
+
+/* Same scan with every buffer on the device and no host synchronisation: q_dev (nq*d fp32),
+ * out_scores_dev (nq*k), out_ids_dev (nq*k int64), out_keys_dev (nq*kpad uint64, may be NULL)
+ * with kpad = psx_kpad(k).  `id_base` is added to every row id (row-sharded corpora).
+ * k <= PSX_K_PASS_MAX.  The 64-bit keys are the sortable form of (score, id):
+ *   key = (orderable(score) << 32) | ~(uint32)(id_base + row),  0 = empty slot,
+ * so that a larger key is a better hit and a plain integer sort reproduces the result order;
+ * they are what row shards exchange (psx_merge_keys_device). */
+int psx_search_device(psx_index* h, const float* q_dev, int64_t nq, int64_t k, const psx_filter* filter,
+                      uint32_t id_base, float* out_scores_dev, int64_t* out_ids_dev,
+                      uint64_t* out_keys_dev, void* stream);
+int64_t psx_kpad(int64_t k);
+/* Final merge of `nlists` sorted key lists per query (layout [nq][nlists][kpad], e.g. the
+ * all-gathered per-shard results) into the global top-k.  Pure device work on `stream`. */
+int psx_merge_keys_device(int device, const uint64_t* keys_dev, int64_t nq, int64_t nlists, int64_t k,
+                          int metric, float* out_scores_dev, int64_t* out_ids_dev, void* stream);
+
+/* Replaces index.reconstruct(i) (utils/vector_store.py:207): the stored row as fp32. */
+int psx_reconstruct(psx_index* h, int64_t id, float* out);
+/* Replaces the flat payload of faiss.write_index (utils/vector_store.py:234): rows
+ * [row0,row0+n) as fp32 into a host buffer, in id order. */
+int psx_read_rows(psx_index* h, int64_t row0, int64_t n, float* out);
+/* Device address/stride of the stored rows (after psx_sync), for zero-copy consumers. */
+int psx_storage_device(psx_index* h, const void** rows_dev, int64_t* ld_elems, int* store_dtype);
+
+/* ---- tuning / introspection ---------------------------------------------------------------- */
+
+/* key: "warps" (consumer warps per CTA), "stages" (ring slots per warp), "ctas_per_sm".
+ * Values <= 0 restore the default. */
+int psx_set_tunable(psx_index* h, const char* key, int value);
+/* Number of kernels launched by this library in the calling process so far. */
+int64_t psx_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PSX_H_ */

@@ -1,0 +1,722 @@
+// psx_api.cu -- host side of the C ABI declared in include/psx.h: HBM arena, staged appends,
+// launch configuration, paging for k > PSX_K_PASS_MAX.  No CPU compute path exists here: every
+// score is produced by the kernels in psx_scan.cuh.
+#include <algorithm>
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "psx_aux.cuh"
+#include "psx_scan.cuh"
+
+using namespace psx;
+
+// ------------------------------------------------------------------------------------------
+// error plumbing
+// ------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static std::atomic<long long> g_launches{0};
+
+static int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail(e_ == cudaErrorMemoryAllocation ? PSX_ERR_OOM : PSX_ERR_CUDA, "%s: %s",    \
+                        #call, cudaGetErrorString(e_));                                            \
+    } while (0)
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        ok = cudaSetDevice(dev) == cudaSuccess;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+// ------------------------------------------------------------------------------------------
+// index object
+// ------------------------------------------------------------------------------------------
+struct psx_index {
+    int d = 0, ld = 0, metric = 0, dtype = 0, device = 0;
+    size_t esize = 4, row_bytes = 0;
+    unsigned char* x = nullptr;  // [cap][row_bytes]
+    uint64_t* attrs = nullptr;   // [cap]
+    bool attrs_set = false;
+    long long n = 0, cap = 0;
+    std::vector<float> pending;  // rows staged by psx_add, not yet in HBM
+    long long pending_n = 0;
+
+    cudaStream_t stream = nullptr;
+    cudaEvent_t last_ev = nullptr;   // completion of the last search (scratch reuse across streams)
+    cudaStream_t last_stream = nullptr;
+    int sm_count = 148;
+    int warps = 8, stages = 5, ctas_per_sm = 1;
+
+    uint64_t* lists = nullptr;  // [grid][kpad]
+    size_t lists_cap = 0;
+    unsigned int* counter = nullptr;
+    // device + pinned staging for the host-buffer API
+    float* dq = nullptr;
+    size_t dq_cap = 0;
+    float* dscores = nullptr;
+    long long* dids = nullptr;
+    uint64_t* dkeys = nullptr;
+    size_t dout_cap = 0;
+    float* hq = nullptr;
+    float* hscores = nullptr;
+    long long* hids = nullptr;
+    size_t hq_cap = 0, hout_cap = 0;
+    std::mutex mu;
+};
+
+static int pow2ceil(long long v) {
+    long long p = 1;
+    while (p < v) p <<= 1;
+    return (int)p;
+}
+
+extern "C" int64_t psx_kpad(int64_t k) {
+    if (k < 1) k = 1;
+    if (k > PSX_K_PASS_MAX) k = PSX_K_PASS_MAX;
+    int p = pow2ceil(k);
+    return p < 32 ? 32 : p;
+}
+
+extern "C" const char* psx_last_error(void) { return g_err.c_str(); }
+extern "C" int psx_abi_version(void) { return PSX_ABI_VERSION; }
+extern "C" int64_t psx_launch_count(void) { return g_launches.load(); }
+
+template <typename K>
+static int set_max_smem(K kernel) {
+    CU(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PSX_SMEM_LIMIT));
+    return PSX_OK;
+}
+
+extern "C" int psx_create(int d, int metric, int store_dtype, int device, psx_index** out) {
+    if (!out) return fail(PSX_ERR_INVALID, "out is null");
+    *out = nullptr;
+    if (d <= 0 || d > 32768) return fail(PSX_ERR_INVALID, "dimension %d out of range [1, 32768]", d);
+    if (metric != PSX_METRIC_IP && metric != PSX_METRIC_L2) return fail(PSX_ERR_INVALID, "bad metric %d", metric);
+    if (store_dtype != PSX_STORE_F32 && store_dtype != PSX_STORE_BF16)
+        return fail(PSX_ERR_INVALID, "bad store dtype %d", store_dtype);
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev <= 0)
+        return fail(PSX_ERR_CUDA, "no CUDA device available (%s); this engine has no CPU fallback",
+                    e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) return fail(PSX_ERR_INVALID, "device %d not in [0,%d)", device, ndev);
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(PSX_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major,
+                    prop.minor);
+    DeviceGuard g(device);
+    if (!g.ok) return fail(PSX_ERR_CUDA, "cudaSetDevice(%d) failed", device);
+    psx_index* h = new (std::nothrow) psx_index();
+    if (!h) return fail(PSX_ERR_OOM, "host allocation failed");
+    h->d = d;
+    h->metric = metric;
+    h->dtype = store_dtype;
+    h->device = device;
+    h->esize = store_dtype == PSX_STORE_F32 ? 4 : 2;
+    const int per16 = 16 / (int)h->esize;
+    h->ld = (d + per16 - 1) / per16 * per16;
+    h->row_bytes = (size_t)h->ld * h->esize;
+    h->sm_count = prop.multiProcessorCount;
+    int rc = PSX_OK;
+    auto init = [&]() -> int {
+        CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&h->last_ev, cudaEventDisableTiming));
+        CU(cudaMalloc(&h->counter, sizeof(unsigned int)));
+        CU(cudaMemset(h->counter, 0, sizeof(unsigned int)));
+        int r;
+        if ((r = set_max_smem(scan_topk_kernel<float, PSX_METRIC_IP>))) return r;
+        if ((r = set_max_smem(scan_topk_kernel<float, PSX_METRIC_L2>))) return r;
+        if ((r = set_max_smem(scan_topk_kernel<__nv_bfloat16, PSX_METRIC_IP>))) return r;
+        if ((r = set_max_smem(scan_topk_kernel<__nv_bfloat16, PSX_METRIC_L2>))) return r;
+        if ((r = set_max_smem(merge_keys_kernel))) return r;
+        return PSX_OK;
+    };
+    rc = init();
+    if (rc != PSX_OK) {
+        psx_destroy(h);
+        return rc;
+    }
+    *out = h;
+    return PSX_OK;
+}
+
+static void free_all(psx_index* h) {
+    cudaFree(h->x);
+    cudaFree(h->attrs);
+    cudaFree(h->lists);
+    cudaFree(h->counter);
+    cudaFree(h->dq);
+    cudaFree(h->dscores);
+    cudaFree(h->dids);
+    cudaFree(h->dkeys);
+    cudaFreeHost(h->hq);
+    cudaFreeHost(h->hscores);
+    cudaFreeHost(h->hids);
+    if (h->last_ev) cudaEventDestroy(h->last_ev);
+    if (h->stream) cudaStreamDestroy(h->stream);
+}
+
+extern "C" int psx_destroy(psx_index* h) {
+    if (!h) return PSX_OK;
+    {
+        DeviceGuard g(h->device);
+        cudaDeviceSynchronize();
+        free_all(h);
+    }
+    delete h;
+    return PSX_OK;
+}
+
+extern "C" int64_t psx_ntotal(const psx_index* h) { return h ? h->n + h->pending_n : 0; }
+extern "C" int psx_dim(const psx_index* h) { return h ? h->d : 0; }
+extern "C" int psx_metric(const psx_index* h) { return h ? h->metric : 0; }
+
+extern "C" int psx_reset(psx_index* h) {
+    if (!h) return fail(PSX_ERR_INVALID, "null handle");
+    std::lock_guard<std::mutex> lk(h->mu);
+    DeviceGuard g(h->device);
+    cudaDeviceSynchronize();
+    cudaFree(h->x);
+    cudaFree(h->attrs);
+    h->x = nullptr;
+    h->attrs = nullptr;
+    h->attrs_set = false;
+    h->n = h->cap = 0;
+    h->pending.clear();
+    h->pending.shrink_to_fit();
+    h->pending_n = 0;
+    return PSX_OK;
+}
+
+// grow the arena to hold at least `need` rows (amortised doubling, device-to-device move)
+static int ensure_capacity(psx_index* h, long long need, bool exact) {
+    if (need <= h->cap) return PSX_OK;
+    long long ncap = need;
+    if (!exact) {
+        long long dbl = h->cap * 2;
+        if (dbl > ncap) ncap = dbl;
+        if (ncap < 1024) ncap = 1024;
+    }
+    unsigned char* nx = nullptr;
+    uint64_t* na = nullptr;
+    cudaError_t e = cudaMalloc(&nx, (size_t)ncap * h->row_bytes);
+    if (e != cudaSuccess && !exact && ncap > need) {  // retry without the growth slack
+        cudaGetLastError();
+        ncap = need;
+        e = cudaMalloc(&nx, (size_t)ncap * h->row_bytes);
+    }
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(PSX_ERR_OOM, "cudaMalloc of %lld rows x %zu B failed: %s", ncap, h->row_bytes, cudaGetErrorString(e));
+    }
+    e = cudaMalloc(&na, (size_t)ncap * sizeof(uint64_t));
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        cudaFree(nx);
+        return fail(PSX_ERR_OOM, "cudaMalloc of attribute words failed: %s", cudaGetErrorString(e));
+    }
+    CU(cudaMemsetAsync(na, 0, (size_t)ncap * sizeof(uint64_t), h->stream));
+    if (h->n > 0) {
+        CU(cudaMemcpyAsync(nx, h->x, (size_t)h->n * h->row_bytes, cudaMemcpyDeviceToDevice, h->stream));
+        CU(cudaMemcpyAsync(na, h->attrs, (size_t)h->n * sizeof(uint64_t), cudaMemcpyDeviceToDevice, h->stream));
+    }
+    CU(cudaStreamSynchronize(h->stream));
+    cudaFree(h->x);
+    cudaFree(h->attrs);
+    h->x = nx;
+    h->attrs = na;
+    h->cap = ncap;
+    return PSX_OK;
+}
+
+static int launch_pack(psx_index* h, const float* src_dev, long long row0, long long n, int normalize, cudaStream_t st) {
+    if (n <= 0) return PSX_OK;
+    long long blocks = (n + 7) / 8;  // 8 warps per block
+    if (blocks > (long long)h->sm_count * 16) blocks = (long long)h->sm_count * 16;
+    unsigned char* dst = h->x + (size_t)row0 * h->row_bytes;
+    if (h->dtype == PSX_STORE_F32)
+        pack_rows_kernel<float><<<(unsigned)blocks, 256, 0, st>>>(src_dev, (float*)dst, n, h->d, h->ld, normalize);
+    else
+        pack_rows_kernel<__nv_bfloat16><<<(unsigned)blocks, 256, 0, st>>>(src_dev, (__nv_bfloat16*)dst, n, h->d, h->ld, normalize);
+    g_launches++;
+    CU(cudaGetLastError());
+    return PSX_OK;
+}
+
+// upload rows staged on the host (chunked through a bounded device bounce buffer)
+static int flush_pending(psx_index* h) {
+    if (h->pending_n == 0) return PSX_OK;
+    int rc = ensure_capacity(h, h->n + h->pending_n, false);
+    if (rc) return rc;
+    const long long chunk_rows = std::max<long long>(1, (256ll << 20) / ((long long)h->d * 4));
+    float* bounce = nullptr;
+    const long long brows = std::min(chunk_rows, h->pending_n);
+    CU(cudaMalloc(&bounce, (size_t)brows * h->d * sizeof(float)));
+    long long done = 0;
+    while (done < h->pending_n) {
+        const long long m = std::min(brows, h->pending_n - done);
+        cudaError_t e = cudaMemcpyAsync(bounce, h->pending.data() + (size_t)done * h->d, (size_t)m * h->d * sizeof(float),
+                                        cudaMemcpyHostToDevice, h->stream);
+        if (e == cudaSuccess) {
+            rc = launch_pack(h, bounce, h->n + done, m, 0, h->stream);
+            if (rc == PSX_OK) e = cudaStreamSynchronize(h->stream);
+        }
+        if (e != cudaSuccess || rc != PSX_OK) {
+            cudaFree(bounce);
+            return rc ? rc : fail(PSX_ERR_CUDA, "upload failed: %s", cudaGetErrorString(e));
+        }
+        done += m;
+    }
+    cudaFree(bounce);
+    h->n += h->pending_n;
+    h->pending_n = 0;
+    h->pending.clear();
+    return PSX_OK;
+}
+
+extern "C" int psx_add(psx_index* h, const float* x, int64_t n) {
+    if (!h || (!x && n > 0) || n < 0) return fail(PSX_ERR_INVALID, "bad arguments to psx_add");
+    std::lock_guard<std::mutex> lk(h->mu);
+    if ((unsigned long long)(h->n + h->pending_n + n) >= 0xffffffffull) return fail(PSX_ERR_RANGE, "more than 2^32-1 rows");
+    try {
+        h->pending.insert(h->pending.end(), x, x + (size_t)n * h->d);
+    } catch (const std::bad_alloc&) {
+        return fail(PSX_ERR_OOM, "host staging allocation failed");
+    }
+    h->pending_n += n;
+    // keep the host staging bounded: big batches go to HBM right away
+    if ((size_t)h->pending_n * h->d * sizeof(float) >= (512ull << 20)) {
+        DeviceGuard g(h->device);
+        return flush_pending(h);
+    }
+    return PSX_OK;
+}
+
+extern "C" int psx_sync(psx_index* h) {
+    if (!h) return fail(PSX_ERR_INVALID, "null handle");
+    std::lock_guard<std::mutex> lk(h->mu);
+    DeviceGuard g(h->device);
+    return flush_pending(h);
+}
+
+extern "C" int psx_reserve(psx_index* h, int64_t n) {
+    if (!h || n < 0) return fail(PSX_ERR_INVALID, "bad arguments to psx_reserve");
+    std::lock_guard<std::mutex> lk(h->mu);
+    DeviceGuard g(h->device);
+    return ensure_capacity(h, n, true);
+}
+
+extern "C" int psx_add_device(psx_index* h, const float* x_dev, int64_t n, int normalize, void* stream) {
+    if (!h || (!x_dev && n > 0) || n < 0) return fail(PSX_ERR_INVALID, "bad arguments to psx_add_device");
+    std::lock_guard<std::mutex> lk(h->mu);
+    DeviceGuard g(h->device);
+    int rc = flush_pending(h);
+    if (rc) return rc;
+    if ((unsigned long long)(h->n + n) >= 0xffffffffull) return fail(PSX_ERR_RANGE, "more than 2^32-1 rows");
+    rc = ensure_capacity(h, h->n + n, false);
+    if (rc) return rc;
+    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    rc = launch_pack(h, x_dev, h->n, n, normalize, st);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(st));
+    h->n += n;
+    return PSX_OK;
+}
+
+extern "C" int psx_set_attrs(psx_index* h, int64_t row0, const uint64_t* attrs, int64_t n) {
+    if (!h || !attrs || n < 0 || row0 < 0) return fail(PSX_ERR_INVALID, "bad arguments to psx_set_attrs");
+    std::lock_guard<std::mutex> lk(h->mu);
+    DeviceGuard g(h->device);
+    int rc = flush_pending(h);
+    if (rc) return rc;
+    if (row0 + n > h->n) return fail(PSX_ERR_RANGE, "attribute rows [%lld,%lld) exceed ntotal %lld", (long long)row0,
+                                     (long long)(row0 + n), h->n);
+    if (n == 0) return PSX_OK;
+    CU(cudaMemcpyAsync(h->attrs + row0, attrs, (size_t)n * sizeof(uint64_t), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    h->attrs_set = true;
+    return PSX_OK;
+}
+
+extern "C" int psx_set_attrs_device(psx_index* h, int64_t row0, const uint64_t* attrs_dev, int64_t n, void* stream) {
+    if (!h || !attrs_dev || n < 0 || row0 < 0) return fail(PSX_ERR_INVALID, "bad arguments to psx_set_attrs_device");
+    std::lock_guard<std::mutex> lk(h->mu);
+    DeviceGuard g(h->device);
+    int rc = flush_pending(h);
+    if (rc) return rc;
+    if (row0 + n > h->n) return fail(PSX_ERR_RANGE, "attribute rows exceed ntotal");
+    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    CU(cudaMemcpyAsync(h->attrs + row0, attrs_dev, (size_t)n * sizeof(uint64_t), cudaMemcpyDeviceToDevice, st));
+    CU(cudaStreamSynchronize(st));
+    h->attrs_set = true;
+    return PSX_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// scan launch
+// ------------------------------------------------------------------------------------------
+struct ScanPlan {
+    ScanParams p;
+    int grid, block;
+    size_t smem;
+};
+
+static int plan_scan(psx_index* h, int k, ScanPlan& plan) {
+    ScanParams& p = plan.p;
+    memset(&p, 0, sizeof p);
+    const int W = h->warps;
+    p.n = h->n;
+    p.d = h->d;
+    p.ld = h->ld;
+    p.row_bytes = (int)h->row_bytes;
+    p.k = k;
+    p.kpad = (int)psx_kpad(k);
+    p.metric = h->metric;
+    if (h->row_bytes <= PSX_SLOT_BYTES) {
+        p.rpi = (int)std::min<size_t>(32, PSX_SLOT_BYTES / h->row_bytes);
+        p.cpr = 1;
+    } else {
+        p.rpi = 1;
+        p.cpr = (int)((h->row_bytes + PSX_SLOT_BYTES - 1) / PSX_SLOT_BYTES);
+    }
+    const int burst = W * p.rpi;  // most keys one CTA iteration can append
+    int cap = pow2ceil((long long)k + burst);
+    if (cap - burst - k < std::max(burst, 64)) cap <<= 1;
+    if (cap < 1024) cap = 1024;
+    p.cand_cap = cap;
+    p.high_water = cap - burst;
+    const int qpad = (h->ld + 7) & ~7;
+    auto smem_for = [&](int S) {
+        return (size_t)W * S * PSX_SLOT_BYTES + (size_t)qpad * 4 + (size_t)cap * 8 + (size_t)W * S * 8 + 8 +
+               (size_t)W * S * 4 + 16;
+    };
+    // co-resident CTAs share the SM's 228 KB (1 KB per CTA is reserved by the driver)
+    const size_t limit = h->ctas_per_sm <= 1 ? (size_t)PSX_SMEM_LIMIT : (size_t)(228 * 1024) / h->ctas_per_sm - 1024;
+    int S = h->stages;
+    while (S > 2 && smem_for(S) > limit) --S;
+    // the merge reuses the ring: it must hold at least two lists
+    while ((size_t)W * S * PSX_SLOT_BYTES / 8 < (size_t)2 * p.kpad && smem_for(S + 1) <= PSX_SMEM_LIMIT) ++S;
+    if (smem_for(S) > PSX_SMEM_LIMIT || (size_t)W * S * PSX_SLOT_BYTES / 8 < (size_t)2 * p.kpad)
+        return fail(PSX_ERR_INVALID, "d=%d k=%d does not fit the shared-memory plan", h->d, k);
+    p.stages = S;
+    plan.smem = smem_for(S);
+    const long long num_items = (h->n + p.rpi - 1) / p.rpi;
+    long long grid = (num_items + W - 1) / W;
+    const long long maxgrid = (long long)h->sm_count * h->ctas_per_sm;
+    if (grid > maxgrid) grid = maxgrid;
+    if (grid < 1) grid = 1;
+    plan.grid = (int)grid;
+    plan.block = W * 32;
+    return PSX_OK;
+}
+
+static int launch_scan(psx_index* h, const float* q_dev, int k, const psx_filter* f, uint32_t id_base,
+                       const uint64_t* ceil_ptr, float* out_scores, long long* out_ids, uint64_t* out_keys, cudaStream_t st) {
+    ScanPlan plan;
+    int rc = plan_scan(h, k, plan);
+    if (rc) return rc;
+    ScanParams& p = plan.p;
+    const size_t need_lists = (size_t)plan.grid * p.kpad;
+    if (need_lists > h->lists_cap) {
+        CU(cudaStreamSynchronize(st));
+        cudaFree(h->lists);
+        h->lists = nullptr;
+        h->lists_cap = 0;
+        const size_t want = std::max(need_lists, (size_t)h->sm_count * h->ctas_per_sm * 128);
+        CU(cudaMalloc(&h->lists, want * sizeof(uint64_t)));
+        h->lists_cap = want;
+    }
+    p.x = h->x;
+    p.q = q_dev;
+    p.ceil_ptr = ceil_ptr;
+    p.lists = h->lists;
+    p.counter = h->counter;
+    p.out_scores = out_scores;
+    p.out_ids = out_ids;
+    p.out_keys = out_keys;
+    p.id_base = id_base;
+    p.has_filter = 0;
+    p.attrs = nullptr;
+    if (f && f->flags) {
+        p.has_filter = 1;
+        p.attrs = h->attrs;
+        p.f = *f;
+    }
+    if (h->dtype == PSX_STORE_F32) {
+        if (h->metric == PSX_METRIC_IP)
+            scan_topk_kernel<float, PSX_METRIC_IP><<<plan.grid, plan.block, plan.smem, st>>>(p);
+        else
+            scan_topk_kernel<float, PSX_METRIC_L2><<<plan.grid, plan.block, plan.smem, st>>>(p);
+    } else {
+        if (h->metric == PSX_METRIC_IP)
+            scan_topk_kernel<__nv_bfloat16, PSX_METRIC_IP><<<plan.grid, plan.block, plan.smem, st>>>(p);
+        else
+            scan_topk_kernel<__nv_bfloat16, PSX_METRIC_L2><<<plan.grid, plan.block, plan.smem, st>>>(p);
+    }
+    g_launches++;
+    CU(cudaGetLastError());
+    return PSX_OK;
+}
+
+// scratch is per index: order this search after the previous one if it ran on another stream
+static int enter_stream(psx_index* h, cudaStream_t st) {
+    if (h->last_stream && h->last_stream != st) CU(cudaStreamWaitEvent(st, h->last_ev, 0));
+    return PSX_OK;
+}
+static int leave_stream(psx_index* h, cudaStream_t st) {
+    CU(cudaEventRecord(h->last_ev, st));
+    h->last_stream = st;
+    return PSX_OK;
+}
+
+extern "C" int psx_search_device(psx_index* h, const float* q_dev, int64_t nq, int64_t k, const psx_filter* filter,
+                                 uint32_t id_base, float* out_scores_dev, int64_t* out_ids_dev, uint64_t* out_keys_dev,
+                                 void* stream) {
+    if (!h || !q_dev || nq < 0) return fail(PSX_ERR_INVALID, "bad arguments to psx_search_device");
+    if (k < 1 || k > PSX_K_PASS_MAX) return fail(PSX_ERR_INVALID, "k=%lld not in [1,%d]", (long long)k, PSX_K_PASS_MAX);
+    std::lock_guard<std::mutex> lk(h->mu);
+    DeviceGuard g(h->device);
+    int rc = flush_pending(h);
+    if (rc) return rc;
+    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    if ((rc = enter_stream(h, st))) return rc;
+    const int64_t kpad = psx_kpad(k);
+    for (int64_t qi = 0; qi < nq; ++qi) {
+        rc = launch_scan(h, q_dev + qi * h->d, (int)k, filter, id_base, nullptr,
+                         out_scores_dev ? out_scores_dev + qi * k : nullptr,
+                         out_ids_dev ? (long long*)out_ids_dev + qi * k : nullptr,
+                         out_keys_dev ? out_keys_dev + qi * kpad : nullptr, st);
+        if (rc) return rc;
+    }
+    return leave_stream(h, st);
+}
+
+extern "C" int psx_merge_keys_device(int device, const uint64_t* keys_dev, int64_t nq, int64_t nlists, int64_t k, int metric,
+                                     float* out_scores_dev, int64_t* out_ids_dev, void* stream) {
+    if (!keys_dev || nq < 0 || nlists < 1 || k < 1 || k > PSX_K_PASS_MAX)
+        return fail(PSX_ERR_INVALID, "bad arguments to psx_merge_keys_device");
+    if (nq == 0) return PSX_OK;
+    DeviceGuard g(device);
+    if (!g.ok) return fail(PSX_ERR_CUDA, "cudaSetDevice(%d) failed", device);
+    static std::atomic<bool> attr_done[64];
+    if (device >= 0 && device < 64 && !attr_done[device].load()) {
+        CU(cudaFuncSetAttribute(merge_keys_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PSX_SMEM_LIMIT));
+        attr_done[device].store(true);
+    }
+    const int kpad = (int)psx_kpad(k);
+    int cap_lists = (int)std::min<int64_t>(nlists + 1, (200 * 1024 / 8) / kpad);
+    if (cap_lists < 2) cap_lists = 2;
+    const size_t smem = (size_t)cap_lists * kpad * 8;
+    merge_keys_kernel<<<(unsigned)nq, 256, smem, (cudaStream_t)stream>>>(keys_dev, (int)nlists, (int)k, kpad, cap_lists, metric,
+                                                                       out_scores_dev, (long long*)out_ids_dev);
+    g_launches++;
+    CU(cudaGetLastError());
+    return PSX_OK;
+}
+
+static int ensure_io(psx_index* h, size_t qfloats, size_t outs) {
+    if (qfloats > h->dq_cap) {
+        cudaFree(h->dq);
+        h->dq = nullptr;
+        h->dq_cap = 0;
+        CU(cudaMalloc(&h->dq, qfloats * sizeof(float)));
+        h->dq_cap = qfloats;
+    }
+    if (qfloats > h->hq_cap) {
+        cudaFreeHost(h->hq);
+        h->hq = nullptr;
+        h->hq_cap = 0;
+        CU(cudaMallocHost(&h->hq, qfloats * sizeof(float)));
+        h->hq_cap = qfloats;
+    }
+    if (outs > h->dout_cap) {
+        cudaFree(h->dscores);
+        cudaFree(h->dids);
+        cudaFree(h->dkeys);
+        h->dscores = nullptr;
+        h->dids = nullptr;
+        h->dkeys = nullptr;
+        h->dout_cap = 0;
+        CU(cudaMalloc(&h->dscores, outs * sizeof(float)));
+        CU(cudaMalloc(&h->dids, outs * sizeof(long long)));
+        CU(cudaMalloc(&h->dkeys, outs * sizeof(uint64_t)));
+        h->dout_cap = outs;
+    }
+    if (outs > h->hout_cap) {
+        cudaFreeHost(h->hscores);
+        cudaFreeHost(h->hids);
+        h->hscores = nullptr;
+        h->hids = nullptr;
+        h->hout_cap = 0;
+        CU(cudaMallocHost(&h->hscores, outs * sizeof(float)));
+        CU(cudaMallocHost(&h->hids, outs * sizeof(long long)));
+        h->hout_cap = outs;
+    }
+    return PSX_OK;
+}
+
+extern "C" int psx_search(psx_index* h, const float* q, int64_t nq, int64_t k, const psx_filter* filter, float* out_scores,
+                          int64_t* out_ids) {
+    if (!h || !q || !out_scores || !out_ids || nq < 0) return fail(PSX_ERR_INVALID, "bad arguments to psx_search");
+    if (k < 1) return fail(PSX_ERR_INVALID, "k=%lld must be >= 1", (long long)k);
+    if (nq == 0) return PSX_OK;
+    std::lock_guard<std::mutex> lk(h->mu);
+    DeviceGuard g(h->device);
+    int rc = flush_pending(h);
+    if (rc) return rc;
+    const float empty = h->metric == PSX_METRIC_L2 ? INFINITY : -INFINITY;
+    if (h->n == 0) {
+        for (int64_t i = 0; i < nq * k; ++i) {
+            out_scores[i] = empty;
+            out_ids[i] = -1;
+        }
+        return PSX_OK;
+    }
+    // results beyond ntotal can never be filled: scan for min(k, n) and pad on the host
+    const int64_t kk = std::min<int64_t>(k, h->n);
+    const int64_t pages = (kk + PSX_K_PASS_MAX - 1) / PSX_K_PASS_MAX;
+    // per-query stride of the device outputs
+    const int64_t kslot = pages == 1 ? psx_kpad(kk) : pages * PSX_K_PASS_MAX;
+    // bound the device/pinned staging: process queries in groups
+    const int64_t group = std::max<int64_t>(1, std::min<int64_t>(nq, (8ll << 20) / kslot));
+    if ((rc = ensure_io(h, (size_t)group * h->d, (size_t)group * kslot))) return rc;
+    cudaStream_t st = h->stream;
+    if ((rc = enter_stream(h, st))) return rc;
+    for (int64_t q0 = 0; q0 < nq; q0 += group) {
+        const int64_t gq = std::min(group, nq - q0);
+        memcpy(h->hq, q + q0 * h->d, (size_t)gq * h->d * sizeof(float));
+        CU(cudaMemcpyAsync(h->dq, h->hq, (size_t)gq * h->d * sizeof(float), cudaMemcpyHostToDevice, st));
+        for (int64_t qi = 0; qi < gq; ++qi) {
+            for (int64_t pg = 0; pg < pages; ++pg) {
+                const int kp = (int)std::min<int64_t>(PSX_K_PASS_MAX, kk - pg * PSX_K_PASS_MAX);
+                const size_t off = (size_t)qi * kslot + (size_t)pg * PSX_K_PASS_MAX;
+                // page pg continues strictly below the last key of page pg-1 (a full page)
+                const uint64_t* ceil_ptr = pg ? h->dkeys + off - 1 : nullptr;
+                rc = launch_scan(h, h->dq + qi * h->d, kp, filter, 0, ceil_ptr, h->dscores + off, h->dids + off,
+                                 h->dkeys + off, st);
+                if (rc) return rc;
+            }
+        }
+        CU(cudaMemcpyAsync(h->hscores, h->dscores, (size_t)gq * kslot * sizeof(float), cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(h->hids, h->dids, (size_t)gq * kslot * sizeof(long long), cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        for (int64_t qi = 0; qi < gq; ++qi) {
+            float* os = out_scores + (q0 + qi) * k;
+            int64_t* oi = out_ids + (q0 + qi) * k;
+            memcpy(os, h->hscores + qi * kslot, (size_t)kk * sizeof(float));
+            memcpy(oi, h->hids + qi * kslot, (size_t)kk * sizeof(long long));
+            for (int64_t i = kk; i < k; ++i) {
+                os[i] = empty;
+                oi[i] = -1;
+            }
+        }
+    }
+    return leave_stream(h, st);
+}
+
+// ------------------------------------------------------------------------------------------
+// reading rows back
+// ------------------------------------------------------------------------------------------
+static int read_rows_locked(psx_index* h, long long row0, long long n, float* out) {
+    if (n == 0) return PSX_OK;
+    const long long chunk = std::max<long long>(1, (128ll << 20) / ((long long)h->d * 4));
+    float* tmp = nullptr;
+    const long long trows = std::min(chunk, n);
+    CU(cudaMalloc(&tmp, (size_t)trows * h->d * sizeof(float)));
+    long long done = 0;
+    int rc = PSX_OK;
+    while (done < n && rc == PSX_OK) {
+        const long long m = std::min(trows, n - done);
+        const long long total = m * h->d;
+        unsigned blocks = (unsigned)std::min<long long>((total + 255) / 256, (long long)h->sm_count * 32);
+        const unsigned char* src = h->x + (size_t)(row0 + done) * h->row_bytes;
+        if (h->dtype == PSX_STORE_F32)
+            unpack_rows_kernel<float><<<blocks, 256, 0, h->stream>>>((const float*)src, tmp, m, h->d, h->ld);
+        else
+            unpack_rows_kernel<__nv_bfloat16><<<blocks, 256, 0, h->stream>>>((const __nv_bfloat16*)src, tmp, m, h->d, h->ld);
+        g_launches++;
+        cudaError_t e = cudaGetLastError();
+        if (e == cudaSuccess)
+            e = cudaMemcpyAsync(out + (size_t)done * h->d, tmp, (size_t)total * sizeof(float), cudaMemcpyDeviceToHost, h->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+        if (e != cudaSuccess) rc = fail(PSX_ERR_CUDA, "row read-back failed: %s", cudaGetErrorString(e));
+        done += m;
+    }
+    cudaFree(tmp);
+    return rc;
+}
+
+extern "C" int psx_read_rows(psx_index* h, int64_t row0, int64_t n, float* out) {
+    if (!h || row0 < 0 || n < 0 || (!out && n > 0)) return fail(PSX_ERR_INVALID, "bad arguments to psx_read_rows");
+    std::lock_guard<std::mutex> lk(h->mu);
+    DeviceGuard g(h->device);
+    int rc = flush_pending(h);
+    if (rc) return rc;
+    if (row0 + n > h->n) return fail(PSX_ERR_RANGE, "rows [%lld,%lld) exceed ntotal %lld", (long long)row0, (long long)(row0 + n), h->n);
+    return read_rows_locked(h, row0, n, out);
+}
+
+extern "C" int psx_reconstruct(psx_index* h, int64_t id, float* out) {
+    if (!h || !out) return fail(PSX_ERR_INVALID, "bad arguments to psx_reconstruct");
+    std::lock_guard<std::mutex> lk(h->mu);
+    if (id < 0 || id >= h->n + h->pending_n) return fail(PSX_ERR_RANGE, "id %lld not in [0,%lld)", (long long)id, h->n + h->pending_n);
+    if (id >= h->n && h->dtype == PSX_STORE_F32) {  // still staged on the host, stored precision == fp32
+        memcpy(out, h->pending.data() + (size_t)(id - h->n) * h->d, (size_t)h->d * sizeof(float));
+        return PSX_OK;
+    }
+    DeviceGuard g(h->device);
+    int rc = flush_pending(h);
+    if (rc) return rc;
+    return read_rows_locked(h, id, 1, out);
+}
+
+extern "C" int psx_storage_device(psx_index* h, const void** rows_dev, int64_t* ld_elems, int* store_dtype) {
+    if (!h) return fail(PSX_ERR_INVALID, "null handle");
+    std::lock_guard<std::mutex> lk(h->mu);
+    DeviceGuard g(h->device);
+    int rc = flush_pending(h);
+    if (rc) return rc;
+    if (rows_dev) *rows_dev = h->x;
+    if (ld_elems) *ld_elems = h->ld;
+    if (store_dtype) *store_dtype = h->dtype;
+    return PSX_OK;
+}
+
+extern "C" int psx_set_tunable(psx_index* h, const char* key, int value) {
+    if (!h || !key) return fail(PSX_ERR_INVALID, "bad arguments to psx_set_tunable");
+    std::lock_guard<std::mutex> lk(h->mu);
+    if (!strcmp(key, "warps")) {
+        h->warps = value <= 0 ? 8 : std::min(value, PSX_MAX_WARPS);
+    } else if (!strcmp(key, "stages")) {
+        h->stages = value <= 0 ? 5 : std::max(2, std::min(value, 12));
+    } else if (!strcmp(key, "ctas_per_sm")) {
+        h->ctas_per_sm = value <= 0 ? 1 : std::min(value, 8);
+    } else {
+        return fail(PSX_ERR_INVALID, "unknown tunable '%s'", key);
+    }
+    return PSX_OK;
+}

@@ -1,0 +1,173 @@
+// psx_common.cuh -- shared device helpers: sortable (score,id) keys, mbarrier / bulk-copy PTX,
+// block-wide bitonic primitives.  sm_100a only.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+#include "../../include/psx.h"
+
+#define PSX_SLOT_BYTES 4096      // one ring slot = one bulk copy of at most this many bytes
+#define PSX_MAX_WARPS 16
+#define PSX_MAX_THREADS (PSX_MAX_WARPS * 32)
+#define PSX_SMEM_LIMIT (227 * 1024)
+
+namespace psx {
+
+// ---------------------------------------------------------------------------------------
+// sortable keys.  A hit is (score fp32, row id u32); "better" = higher score, then lower id.
+// key = orderable(score) << 32 | ~id  makes "better" == "larger unsigned 64-bit integer", so the
+// per-CTA selection, the cross-CTA merge and the cross-GPU merge are all plain integer
+// compare-exchange networks and ties resolve identically everywhere.  key 0 = empty slot
+// (the smallest key of a real hit is 0x007FFFFF'xxxxxxxx, the image of -inf).
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t f32_to_ord(float s) {
+    uint32_t u = __float_as_uint(s);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float ord_to_f32(uint32_t o) {
+    uint32_t u = (o & 0x80000000u) ? (o & 0x7fffffffu) : ~o;
+    return __uint_as_float(u);
+}
+__device__ __forceinline__ uint64_t make_key(float score, uint32_t id) {
+    if (score != score) score = -INFINITY;  // NaN rows sort last
+    score += 0.0f;                          // -0.0 -> +0.0 so that equal floats give equal keys
+    return ((uint64_t)f32_to_ord(score) << 32) | (uint32_t)(~id);
+}
+__device__ __forceinline__ float key_score(uint64_t key) { return ord_to_f32((uint32_t)(key >> 32)); }
+__device__ __forceinline__ uint32_t key_id(uint64_t key) { return ~(uint32_t)key; }
+
+// ---------------------------------------------------------------------------------------
+// mbarrier + bulk async copy (TMA 1-D, SASS: UBLKCP / SYNCS)
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// Spin on the phase with the given parity.  try_wait suspends in hardware between polls; the
+// poll bound turns a protocol bug into a trap instead of a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok = 0;
+    for (uint32_t spin = 0; !ok; ++spin) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (spin > (1u << 26)) __trap();
+    }
+}
+// global -> shared bulk copy, completion signalled on `bar` (bytes: multiple of 16, both
+// addresses 16-byte aligned).
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+
+__device__ __forceinline__ uint64_t ld_cg_u64(const uint64_t* p) {
+    uint64_t v;
+    asm volatile("ld.global.cg.u64 %0, [%1];" : "=l"(v) : "l"(p));
+    return v;
+}
+
+// ---------------------------------------------------------------------------------------
+// block-wide sorting networks over 64-bit keys in shared memory (descending)
+// ---------------------------------------------------------------------------------------
+// Full bitonic sort of buf[0..n), n a power of two.  All threads of the block must call.
+__device__ __forceinline__ void block_bitonic_sort_desc(uint64_t* buf, int n) {
+    const int tid = threadIdx.x, nt = blockDim.x;
+    for (int size = 2; size <= n; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int t = tid; t < (n >> 1); t += nt) {
+                const int i = ((t & ~(stride - 1)) << 1) | (t & (stride - 1));
+                const int j = i | stride;
+                const bool desc = (i & size) == 0;
+                const uint64_t a = buf[i], b = buf[j];
+                if ((a < b) == desc) {
+                    buf[i] = b;
+                    buf[j] = a;
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// Merge `L` descending lists of `kp` keys each (kp a power of two >= 2, padded with 0) living in
+// global memory at src[l*kp + i] into the `kp` best keys, descending, left in buf[0..kp).
+// `buf` is shared memory with room for cap_lists*kp keys (cap_lists >= 2).  Uses only
+// compare-exchange of whole keys, so the result is the exact (score desc, id asc) order.
+__device__ __forceinline__ void block_merge_lists(const uint64_t* __restrict__ src, int L, int kp, uint64_t* buf,
+                                                  int cap_lists) {
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int half = kp >> 1;
+    bool have_acc = false;
+    int pos = 0;
+    while (pos < L) {
+        const int base = have_acc ? 1 : 0;
+        int nb = cap_lists - base;
+        if (nb > L - pos) nb = L - pos;
+        for (int idx = tid; idx < nb * kp; idx += nt) buf[base * kp + idx] = ld_cg_u64(src + (size_t)pos * kp + idx);
+        __syncthreads();
+        const int m = base + nb;
+        for (int stride = 1; stride < m; stride <<= 1) {
+            // pairs (a = p*2*stride, b = a + stride) with b < m
+            const int npairs = (m - stride + 2 * stride - 1) / (2 * stride);
+            // half-cleaner across the pair: the kp largest of A u B, as a bitonic sequence in A
+            for (int w = tid; w < npairs * kp; w += nt) {
+                const int p = w / kp, i = w - p * kp;
+                uint64_t* A = buf + (size_t)(p * 2 * stride) * kp;
+                const uint64_t* B = A + (size_t)stride * kp;
+                const uint64_t x = A[i], y = B[kp - 1 - i];
+                A[i] = x > y ? x : y;
+            }
+            __syncthreads();
+            for (int j = half; j >= 1; j >>= 1) {
+                for (int w = tid; w < npairs * half; w += nt) {
+                    const int p = w / half, t = w - p * half;
+                    uint64_t* A = buf + (size_t)(p * 2 * stride) * kp;
+                    const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                    const uint64_t a = A[i], b = A[i | j];
+                    if (a < b) {
+                        A[i] = b;
+                        A[i | j] = a;
+                    }
+                }
+                __syncthreads();
+            }
+        }
+        have_acc = true;
+        pos += nb;
+    }
+}
+
+// Decode the first k keys of a sorted list into FAISS-shaped outputs.
+__device__ __forceinline__ void block_emit_results(const uint64_t* sorted, int k, int kp, int metric, float* out_scores,
+                                                   long long* out_ids, uint64_t* out_keys) {
+    for (int i = threadIdx.x; i < kp; i += blockDim.x) {
+        const uint64_t key = i < k ? sorted[i] : 0ull;
+        if (out_keys) out_keys[i] = key;
+        if (i < k) {
+            float s = key ? key_score(key) : -INFINITY;
+            if (metric == PSX_METRIC_L2) s = -s;
+            if (out_scores) out_scores[i] = s;
+            if (out_ids) out_ids[i] = key ? (long long)key_id(key) : -1ll;
+        }
+    }
+}
+
+}  // namespace psx

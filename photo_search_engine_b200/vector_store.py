@@ -1,0 +1,366 @@
+"""Drop-in ``VectorStore`` whose arithmetic runs on a B200.
+
+Surface contract: the constructor keywords, public attributes, method
+names, return shapes and exception types of the reference class
+``utils/vector_store.py::VectorStore`` (a FAISS CPU ``IndexFlatIP`` / ``IndexFlatL2`` wrapper),
+so ``main.py:59-68``, ``core/searcher.py`` and ``core/indexer.py`` run unchanged once
+``utils/vector_store.py`` re-exports this class.  Below the class nothing is
+shared with the reference: rows live in HBM behind ``libpsx.so`` (include/psx.h, ctypes) and a
+search is one launch of the TMA-fed streaming scan with the EXIF predicate and the top-k
+selection fused in.  There is no CPU fallback; importing this module without the native
+library raises ``ImportError`` exactly as the reference does without faiss
+(utils/vector_store.py:9-12).
+
+Additive, optional surface (defaults reproduce the reference):
+
+* keyword-only ctor arguments ``device`` / ``store_dtype`` (env ``PSX_DEVICE`` /
+  ``PSX_STORE_DTYPE``);
+* ``search(..., constraints=None)``: fused pre-filter with the semantics of
+  ``Searcher._check_time_match_v2`` (core/searcher.py:1884-1950);
+* ``search_batch`` / ``add_batch``: arrays in, arrays out, no per-hit Python objects.
+"""
+from __future__ import annotations
+
+import json
+import os
+from typing import Any, Callable, Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _native, faiss_io
+from .exif_attrs import attr_words, build_filter
+
+_native.load_library()
+
+_METRICS = ("l2", "cosine")
+_INDEX_TYPES = ("flat", "hnsw")
+_DTYPES = {"fp32": "fp32", "float32": "fp32", "bf16": "bf16", "bfloat16": "bf16"}
+
+# messages are part of the observable behaviour (they surface in HTTP 500 bodies, api/routes.py:196-207)
+_E_METRIC = "metric仅支持l2或cosine"
+_E_INDEX_TYPE = "index_type仅支持flat或hnsw"
+_E_EMPTY_VECTOR = "向量不能为空"
+_E_DIM = "向量维度不匹配: {} != {}"
+_E_NO_INDEX = "索引未初始化"
+_E_META_MISSING = "索引元信息缺失，请重新构建索引"
+_E_META_BROKEN = "索引元信息损坏，请重新构建索引"
+_E_TYPE_MISMATCH = "索引类型与配置不一致，请重新构建索引"
+_E_METRIC_MISMATCH = "索引度量与配置不一致，请重新构建索引"
+_E_COUNT_MISMATCH = "索引与元数据数量不一致，请重新构建索引"
+
+
+def _native_index(dimension: int, metric: int, store_dtype: int, device: int):
+    return _native.NativeIndex(dimension, metric, store_dtype, device)
+
+
+def _unit_rows(rows: np.ndarray) -> np.ndarray:
+    """Row-wise L2 normalisation in fp32; zero rows stay as they are."""
+    norms = np.linalg.norm(rows, axis=1, keepdims=True).astype(np.float32)
+    norms[norms == 0] = 1.0
+    return (rows / norms).astype(np.float32)
+
+
+class VectorStore:
+    """Vector storage and exact retrieval on the GPU.
+
+    Attributes mirrored from the reference: ``dimension``, ``index_path``, ``metadata_path``,
+    ``meta_path``, ``metric``, ``index_type``, ``hnsw_*``, ``metadata`` (the very dict objects
+    handed to ``add_item``, in insertion order) and ``index`` (the backend handle or ``None``).
+    """
+
+    # tests replace this with an oracle-backed fake to exercise the host logic without a GPU
+    _index_factory: Callable[[int, int, int, int], Any] = staticmethod(_native_index)
+
+    def __init__(
+        self,
+        dimension: Optional[int],
+        index_path: str,
+        metadata_path: str,
+        metric: str = "cosine",
+        index_type: str = "flat",
+        hnsw_m: int = 32,
+        hnsw_ef_construction: int = 200,
+        hnsw_ef_search: int = 96,
+        *,
+        device: Optional[int] = None,
+        store_dtype: Optional[str] = None,
+    ) -> None:
+        # argument handling of utils/vector_store.py:44-62
+        metric_name = metric.lower().strip() if metric else "l2"
+        if metric_name not in _METRICS:
+            raise ValueError(_E_METRIC)
+        type_name = (index_type or "flat").strip().lower()
+        if type_name not in _INDEX_TYPES:
+            raise ValueError(_E_INDEX_TYPE)
+        dtype_name = _DTYPES.get((store_dtype or os.environ.get("PSX_STORE_DTYPE", "fp32")).strip().lower())
+        if dtype_name is None:
+            raise ValueError("store_dtype仅支持fp32或bf16")
+
+        self.dimension = dimension
+        self.index_path = index_path
+        self.metadata_path = metadata_path
+        self.meta_path = index_path + ".meta.json"
+        self.metric = metric_name
+        self.index_type = type_name
+        self.hnsw_m = max(4, int(hnsw_m))
+        self.hnsw_ef_construction = max(8, int(hnsw_ef_construction))
+        self.hnsw_ef_search = max(8, int(hnsw_ef_search))
+        self.device = int(os.environ.get("PSX_DEVICE", "0")) if device is None else int(device)
+        self.store_dtype = dtype_name
+
+        self._normalize = metric_name == "cosine"
+        self.metadata: List[Dict] = []
+        self._embeddings: List[Optional[List[float]]] = []
+        self._path_to_index: Dict[str, int] = {}
+        self._attrs_built = 0  # rows whose attribute word is already on the device
+        self.index = self._create_index(dimension) if dimension else None
+
+    # ------------------------------------------------------------------------------------
+    # helpers
+    # ------------------------------------------------------------------------------------
+    @property
+    def _metric_code(self) -> int:
+        return _native.METRIC_IP if self._normalize else _native.METRIC_L2
+
+    def _create_index(self, dimension: int):
+        """Backend for ``dimension`` (utils/vector_store.py:72-81); ``hnsw`` is served exactly."""
+        dtype = _native.STORE_BF16 if self.store_dtype == "bf16" else _native.STORE_F32
+        return type(self)._index_factory(int(dimension), self._metric_code, dtype, self.device)
+
+    def _require_dimension(self, vector: Sequence[float]) -> None:
+        if len(vector) != self.dimension:
+            raise ValueError(_E_DIM.format(len(vector), self.dimension))
+
+    def _normalize_vector(self, vector: Sequence[float]):
+        """utils/vector_store.py:83-90 -- the same numpy operations in the same order, so the
+        stored bits equal what the reference hands to FAISS."""
+        if self._normalize:
+            as_f32 = np.array(vector, dtype="float32")
+            length = np.linalg.norm(as_f32)
+            if length != 0:
+                return (as_f32 / length).astype("float32").tolist()
+        return vector
+
+    def _remember_path(self, metadata: Dict, row: int) -> None:
+        photo_path = metadata.get("photo_path")
+        if isinstance(photo_path, str) and photo_path:
+            self._path_to_index[photo_path] = row  # the last duplicate wins, as in the reference
+
+    def _filter_for(self, constraints: Optional[Dict[str, Any]]):
+        """-> (psx_filter | None, never_matches)."""
+        if not constraints:
+            return None, False
+        flt, never = build_filter(constraints)
+        if flt is not None and not never:
+            self._upload_attrs()
+        return flt, never
+
+    def _upload_attrs(self) -> None:
+        """Lazy EXIF sidecar: pack and upload attribute words for rows that lack one."""
+        total = len(self.metadata)
+        if self.index is None or self._attrs_built >= total:
+            return
+        self.index.set_attrs(self._attrs_built, attr_words(self.metadata[self._attrs_built : total]))
+        self._attrs_built = total
+
+    def _run_search(self, queries: np.ndarray, k: int, flt) -> Tuple[np.ndarray, np.ndarray]:
+        if flt is None:
+            return self.index.search(queries, k)
+        return self.index.search(queries, k, flt)
+
+    # ------------------------------------------------------------------------------------
+    # write side
+    # ------------------------------------------------------------------------------------
+    def add_item(self, embedding: List[float], metadata: Dict) -> None:
+        """Append one vector with its metadata record (utils/vector_store.py:143-169).
+
+        Raises ``ValueError`` for a ``None`` embedding or a dimension mismatch.  The first call
+        on a store created with ``dimension=None`` fixes the dimension.
+        """
+        if embedding is None:
+            raise ValueError(_E_EMPTY_VECTOR)
+        if self.index is None:
+            self.dimension = len(embedding)
+            self.index = self._create_index(self.dimension)
+        self._require_dimension(embedding)
+
+        stored = self._normalize_vector(embedding)
+        self.index.add(np.array([stored], dtype="float32"))
+        row = len(self.metadata)
+        self.metadata.append(metadata)
+        # Normalised rows are bit-identical to what sits in HBM, so they are re-read on demand
+        # instead of holding a Python list per row; raw (l2) inputs are kept like the reference.
+        self._embeddings.append(None if self._normalize else stored)
+        self._remember_path(metadata, row)
+
+    def add_batch(self, embeddings: np.ndarray, metadatas: Sequence[Dict]) -> None:
+        """Array form of ``add_item``: float32 ``[n, d]`` plus one metadata dict per row."""
+        rows = np.ascontiguousarray(embeddings, dtype=np.float32)
+        if rows.ndim != 2 or len(metadatas) != rows.shape[0]:
+            raise ValueError("embeddings 与 metadatas 数量不一致")
+        if self.index is None:
+            self.dimension = int(rows.shape[1])
+            self.index = self._create_index(self.dimension)
+        if rows.shape[1] != self.dimension:
+            raise ValueError(_E_DIM.format(rows.shape[1], self.dimension))
+        self.index.add(_unit_rows(rows) if self._normalize else rows)
+        first = len(self.metadata)
+        self.metadata.extend(metadatas)
+        self._embeddings.extend([None] * len(metadatas))
+        for offset, metadata in enumerate(metadatas):
+            self._remember_path(metadata, first + offset)
+
+    # ------------------------------------------------------------------------------------
+    # read side
+    # ------------------------------------------------------------------------------------
+    def search(self, query_embedding: List[float], top_k: int, constraints: Optional[Dict[str, Any]] = None) -> List[Dict]:
+        """Top-k retrieval (utils/vector_store.py:172-198).
+
+        Returns ``[{"metadata": <the stored dict>, "distance": float}, ...]`` best first -- inner
+        product for cosine (higher is better), squared L2 for l2 -- with ``k = min(top_k,
+        ntotal)``; ``[]`` on an empty store.  ``constraints`` (not part of the reference
+        signature) limits the scan to rows passing the EXIF predicate.
+        """
+        if self.index is None or self.index.ntotal == 0:
+            return []
+        self._require_dimension(query_embedding)
+        k = min(int(top_k), self.index.ntotal)
+        if k <= 0:
+            return []
+        flt, never = self._filter_for(constraints)
+        if never:
+            return []
+        query = np.array([self._normalize_vector(query_embedding)], dtype="float32")
+        distances, labels = self._run_search(query, k, flt)
+        records = self.metadata
+        return [
+            {"metadata": records[label], "distance": float(distance)}
+            for distance, label in zip(distances[0].tolist(), labels[0].tolist())
+            if label != -1
+        ]
+
+    def search_batch(self, queries: np.ndarray, top_k: int, constraints: Optional[Dict[str, Any]] = None,
+                     normalize: Optional[bool] = None) -> Tuple[np.ndarray, np.ndarray]:
+        """FAISS-shaped batch search: ``(scores float32 [nq,k], ids int64 [nq,k])``, unfilled
+        slots ``(-inf | +inf, -1)``."""
+        batch = np.ascontiguousarray(queries, dtype=np.float32)
+        if batch.ndim == 1:
+            batch = batch[None, :]
+        k = max(int(top_k), 0)
+        blank = (np.full((batch.shape[0], k), np.inf if self.metric == "l2" else -np.inf, np.float32),
+                 np.full((batch.shape[0], k), -1, np.int64))
+        if self.index is None or self.index.ntotal == 0 or k == 0:
+            return blank
+        if batch.shape[1] != self.dimension:
+            raise ValueError(_E_DIM.format(batch.shape[1], self.dimension))
+        flt, never = self._filter_for(constraints)
+        if never:
+            return blank
+        if self._normalize if normalize is None else normalize:
+            batch = _unit_rows(batch)
+        return self._run_search(batch, k, flt)
+
+    def get_embedding_by_photo_path(self, photo_path: str) -> Optional[List[float]]:
+        """Stored (normalised) vector of a photo as a fresh list, or ``None``
+        (utils/vector_store.py:200-212; the cache miss path is ``index.reconstruct``)."""
+        row = self._path_to_index.get(photo_path)
+        if row is None or row >= len(self._embeddings):
+            return None
+        kept = self._embeddings[row]
+        if kept is not None:
+            return list(kept)
+        if self.index is None:
+            return None
+        return self.index.reconstruct(row).astype("float32").tolist()
+
+    def has_photo_path(self, photo_path: str) -> bool:
+        return photo_path in self._path_to_index
+
+    def get_total_items(self) -> int:
+        """Number of stored vectors (utils/vector_store.py:262-271)."""
+        return 0 if self.index is None else int(self.index.ntotal)
+
+    # ------------------------------------------------------------------------------------
+    # persistence: <index_path> (FAISS flat container) + <index_path>.meta.json + metadata.json
+    # ------------------------------------------------------------------------------------
+    def save(self) -> None:
+        """Write the three files the reference writes (utils/vector_store.py:217-237, :104-114).
+        ``ValueError`` if nothing was ever indexed."""
+        if self.index is None:
+            raise ValueError(_E_NO_INDEX)
+        for target in (self.index_path, self.metadata_path):
+            folder = os.path.dirname(target)
+            if folder:
+                os.makedirs(folder, exist_ok=True)
+        faiss_io.write_flat_index(self.index_path, int(self.dimension), self._metric_code, self.index.ntotal,
+                                  self.index.read_rows)
+        settings = dict(
+            index_type=self.index_type,
+            metric=self.metric,
+            dimension=self.dimension,
+            hnsw_m=self.hnsw_m,
+            hnsw_ef_construction=self.hnsw_ef_construction,
+            hnsw_ef_search=self.hnsw_ef_search,
+        )
+        for target, payload in ((self.meta_path, settings), (self.metadata_path, self.metadata)):
+            with open(target, "w", encoding="utf-8") as handle:
+                json.dump(payload, handle, ensure_ascii=False, indent=2)
+
+    def _read_settings(self) -> Dict[str, Any]:
+        """``.meta.json`` checks of utils/vector_store.py:116-140."""
+        if not os.path.exists(self.meta_path):
+            raise ValueError(_E_META_MISSING)
+        with open(self.meta_path, "r", encoding="utf-8") as handle:
+            settings = json.load(handle)
+        if not isinstance(settings, dict):
+            raise ValueError(_E_META_BROKEN)
+        if str(settings.get("index_type") or "").strip().lower() != self.index_type:
+            raise ValueError(_E_TYPE_MISMATCH)
+        if str(settings.get("metric") or "").strip().lower() != self.metric:
+            raise ValueError(_E_METRIC_MISMATCH)
+        return settings
+
+    def load(self) -> bool:
+        """Load index + metadata (utils/vector_store.py:239-260): ``False`` when either file is
+        absent, ``ValueError`` for missing/corrupt ``.meta.json``, a type/metric mismatch or a
+        row-count mismatch.  ``IxFI`` / ``IxF2`` files and FAISS ``IHNf`` containers are read;
+        the whole matrix is uploaded to HBM."""
+        if not (os.path.exists(self.index_path) and os.path.exists(self.metadata_path)):
+            return False
+        info, blocks = faiss_io.open_index(self.index_path)
+        self._read_settings()
+        if info["metric"] != self._metric_code:
+            raise ValueError(_E_METRIC_MISMATCH)
+        with open(self.metadata_path, "r", encoding="utf-8") as handle:
+            records = json.load(handle)
+        if info["ntotal"] != len(records):
+            raise ValueError(_E_COUNT_MISMATCH)
+
+        if self.index is not None and hasattr(self.index, "close"):
+            self.index.close()
+        self.dimension = int(info["d"])
+        self.index = self._create_index(self.dimension)
+        if hasattr(self.index, "reserve"):
+            self.index.reserve(info["ntotal"])
+        for block in blocks:
+            self.index.add(block)
+        self.metadata = records
+        self._embeddings = [None] * info["ntotal"]
+        self._attrs_built = 0
+        self._path_to_index = {}
+        for row, metadata in enumerate(records):
+            self._remember_path(metadata, row)
+        return True
+
+    def clear(self) -> None:
+        """Drop all vectors and metadata, keep the dimension (utils/vector_store.py:273-280)."""
+        if self.index is not None and hasattr(self.index, "reset"):
+            self.index.reset()
+        elif self.dimension:
+            self.index = self._create_index(self.dimension)
+        else:
+            self.index = None
+        self.metadata = []
+        self._embeddings = []
+        self._path_to_index = {}
+        self._attrs_built = 0

@@ -1,0 +1,296 @@
+"""Host logic of the drop-in ``VectorStore`` (no GPU: oracle-backed fake backend).
+
+The first block restates the reference's own ``tests/test_vector_store.py`` case by case;
+the rest covers persistence compatibility, the EXIF sidecar and the additive batch API.
+"""
+from __future__ import annotations
+
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import flat_ip as O
+from tests.conftest import GOLDEN
+
+DIMS = (8, 768, 4096)
+
+
+@pytest.fixture()
+def VS(fake_backend):
+    from photo_search_engine_b200.vector_store import VectorStore
+
+    return VectorStore
+
+
+def _paths(tmp_path):
+    return str(tmp_path / "index.bin"), str(tmp_path / "metadata.json")
+
+
+# ---- reference tests/test_vector_store.py, restated ----------------------------------------
+@pytest.mark.parametrize("d", DIMS)
+def test_init(VS, tmp_path, d):
+    ip, mp = _paths(tmp_path)
+    s = VS(dimension=d, index_path=ip, metadata_path=mp)
+    assert (s.dimension, s.index_path, s.metadata_path, s.get_total_items()) == (d, ip, mp, 0)
+    assert s.meta_path == ip + ".meta.json"
+
+
+@pytest.mark.parametrize("d", DIMS)
+def test_add_and_search_item(VS, tmp_path, d):
+    s = VS(d, *_paths(tmp_path))
+    s.add_item([0.1] * d, {"id": 1, "photo": "test1.jpg"})
+    s.add_item([0.5] * d, {"id": 2, "photo": "test2.jpg"})
+    r = s.search([0.1] * d, top_k=1)
+    assert len(r) == 1 and r[0]["metadata"]["id"] == 1 and r[0]["distance"] >= 0.0
+
+
+@pytest.mark.parametrize("index_type", ["flat", "hnsw"])
+def test_save_and_load(VS, tmp_path, index_type):
+    ip, mp = _paths(tmp_path)
+    kw = dict(index_type=index_type, hnsw_m=16, hnsw_ef_construction=80, hnsw_ef_search=48)
+    s = VS(16, ip, mp, **kw)
+    s.add_item([0.1] * 16, {"photo_path": "/a.jpg", "id": 1})
+    s.add_item([0.2] * 16, {"photo_path": "/b.jpg", "id": 2})
+    s.save()
+    assert os.path.exists(ip) and os.path.exists(mp) and os.path.exists(ip + ".meta.json")
+    t = VS(16, ip, mp, **kw)
+    assert t.load() is True
+    assert t.get_total_items() == 2 and t.has_photo_path("/b.jpg")
+    meta = json.load(open(ip + ".meta.json"))
+    assert meta == {"index_type": index_type, "metric": "cosine", "dimension": 16, "hnsw_m": 16,
+                    "hnsw_ef_construction": 80, "hnsw_ef_search": 48}
+
+
+def test_load_nonexistent(VS, tmp_path):
+    assert VS(8, str(tmp_path / "no.bin"), str(tmp_path / "no.json")).load() is False
+
+
+def test_load_metadata_mismatch(VS, tmp_path):
+    ip, mp = _paths(tmp_path)
+    s = VS(8, ip, mp)
+    s.add_item([0.1] * 8, {"id": 1})
+    s.save()
+    open(mp, "w").write("[]")
+    with pytest.raises(ValueError):
+        VS(8, ip, mp).load()
+
+
+def test_dimension_mismatch(VS, tmp_path):
+    s = VS(8, *_paths(tmp_path))
+    s.add_item([0.1] * 8, {"id": 1})
+    with pytest.raises(ValueError):
+        s.add_item([0.1] * 9, {"id": 2})
+    with pytest.raises(ValueError):
+        s.search([0.1] * 9, 1)
+    with pytest.raises(ValueError):
+        s.add_item(None, {})
+
+
+def test_search_empty_and_top_k_limit(VS, tmp_path):
+    s = VS(8, *_paths(tmp_path))
+    assert s.search([0.1] * 8, top_k=10) == []
+    for i in range(10):
+        s.add_item([i * 0.1] * 8, {"id": i})
+    assert len(s.search([0.1] * 8, top_k=5)) == 5
+    assert len(s.search([0.1] * 8, top_k=50)) == 10  # k = min(top_k, ntotal)
+
+
+@pytest.mark.parametrize("d", DIMS)
+def test_get_embedding_by_photo_path(VS, tmp_path, d):
+    s = VS(d, *_paths(tmp_path))
+    s.add_item([0.1] * d, {"photo_path": "/a.jpg"})
+    s.add_item([0.2] * d, {"photo_path": "/b.jpg"})
+    e = s.get_embedding_by_photo_path("/b.jpg")
+    assert len(e) == d and abs(e[0] - 1.0 / d**0.5) < 5e-7
+    assert s.get_embedding_by_photo_path("/missing.jpg") is None
+    e[0] = 123.0  # a fresh list every time
+    assert s.get_embedding_by_photo_path("/b.jpg")[0] != 123.0
+
+
+# ---- constructor contract (main.py:59-68, utils/vector_store.py:44-56) -------------------------
+def test_constructor_contract(VS, tmp_path):
+    ip, mp = _paths(tmp_path)
+    with pytest.raises(ValueError):
+        VS(8, ip, mp, metric="dot")
+    with pytest.raises(ValueError):
+        VS(8, ip, mp, index_type="ivf")
+    s = VS(None, ip, mp, metric=" COSINE ", index_type=None, hnsw_m=1, hnsw_ef_construction=1, hnsw_ef_search=1)
+    assert (s.metric, s.index_type, s.hnsw_m, s.hnsw_ef_construction, s.hnsw_ef_search) == ("cosine", "flat", 4, 8, 8)
+    assert s.index is None and s.get_total_items() == 0 and s.search([1.0], 3) == []
+    with pytest.raises(ValueError):
+        s.save()
+    s.add_item([3.0, 4.0], {"photo_path": "p"})  # lazy dimension
+    assert s.dimension == 2 and s.get_embedding_by_photo_path("p") == pytest.approx([0.6, 0.8])
+    assert VS(4, ip, mp, metric=None).metric == "l2"
+
+
+def test_metadata_objects_are_shared(VS, tmp_path):
+    s = VS(4, *_paths(tmp_path))
+    record = {"photo_path": "a", "x": 1}
+    s.add_item([1, 0, 0, 0], record)
+    assert s.metadata[0] is record and s.search([1, 0, 0, 0], 1)[0]["metadata"] is record
+
+
+def test_duplicate_path_last_wins_and_clear(VS, tmp_path):
+    s = VS(4, *_paths(tmp_path))
+    s.add_item([1, 0, 0, 0], {"photo_path": "dup"})
+    s.add_item([0, 1, 0, 0], {"photo_path": "dup"})
+    assert s.get_embedding_by_photo_path("dup") == [0.0, 1.0, 0.0, 0.0]
+    s.clear()
+    assert s.get_total_items() == 0 and s.metadata == [] and not s.has_photo_path("dup") and s.dimension == 4
+    s.add_item([0, 0, 1, 0], {"photo_path": "z"})
+    assert s.get_total_items() == 1
+
+
+def test_l2_metric(VS, tmp_path):
+    s = VS(3, *_paths(tmp_path), metric="l2")
+    s.add_item([0.0, 0.0, 0.0], {"photo_path": "o"})
+    s.add_item([3.0, 4.0, 0.0], {"photo_path": "far"})
+    r = s.search([0.0, 0.0, 0.0], 2)
+    assert [h["metadata"]["photo_path"] for h in r] == ["o", "far"] and [h["distance"] for h in r] == [0.0, 25.0]
+    assert s.get_embedding_by_photo_path("far") == [3.0, 4.0, 0.0]  # not normalised for l2
+
+
+# ---- persistence compatibility ----------------------------------------------------------------
+def test_save_is_byte_identical_to_faiss_fixture(VS, tmp_path):
+    ip, mp = _paths(tmp_path)
+    s = VS(8, ip, mp)
+    s.add_item([11.0 + i for i in range(8)], {"photo_path": "x"})
+    s.save()
+    assert open(ip, "rb").read() == open(os.path.join(GOLDEN, "build_smoke.idx"), "rb").read()
+    assert open(ip + ".meta.json").read() == open(os.path.join(GOLDEN, "build_smoke.idx.meta.json")).read()
+    # and the oracle's reader (independent restatement of the format) accepts it
+    ix, info = O.read_index(ip)
+    assert info["ntotal"] == 1
+
+
+def test_loads_faiss_hnsw_container(VS, tmp_path):
+    ip, mp = _paths(tmp_path)
+    with open(ip, "wb") as f:
+        f.write(open(os.path.join(GOLDEN, "real77_hnsw_header.bin"), "rb").read())
+        f.write(open(os.path.join(GOLDEN, "real77.index"), "rb").read())
+    json.dump({"index_type": "hnsw", "metric": "cosine", "dimension": 4096, "hnsw_m": 48,
+               "hnsw_ef_construction": 320, "hnsw_ef_search": 192}, open(ip + ".meta.json", "w"))
+    meta = json.load(open(os.path.join(GOLDEN, "real77_time.json"), encoding="utf-8"))
+    for i, m in enumerate(meta):
+        m["photo_path"] = f"/p/{i}.jpg"
+    json.dump(meta, open(mp, "w"))
+    s = VS(4096, ip, mp, index_type="hnsw", hnsw_m=48, hnsw_ef_construction=320, hnsw_ef_search=192)
+    assert s.load() and s.get_total_items() == 77
+    gold = json.load(open(os.path.join(GOLDEN, "real77_topk.json")))
+    q = s.get_embedding_by_photo_path("/p/5.jpg")
+    hits = s.search(q, 10)
+    assert [s.metadata.index(h["metadata"]) for h in hits] == gold["ids"][5]
+    # config/type mismatches are ValueErrors (utils/vector_store.py:125-140)
+    with pytest.raises(ValueError):
+        VS(4096, ip, mp, index_type="flat").load()
+    with pytest.raises(ValueError):
+        VS(4096, ip, mp, index_type="hnsw", metric="l2").load()
+    os.remove(ip + ".meta.json")
+    with pytest.raises(ValueError):
+        VS(4096, ip, mp, index_type="hnsw").load()
+
+
+def test_corrupt_meta_json(VS, tmp_path):
+    ip, mp = _paths(tmp_path)
+    s = VS(4, ip, mp)
+    s.add_item([1, 2, 3, 4], {})
+    s.save()
+    open(ip + ".meta.json", "w").write("[1, 2]")
+    with pytest.raises(ValueError):
+        VS(4, ip, mp).load()
+
+
+# ---- EXIF sidecar ---------------------------------------------------------------------------------
+def _real_meta():
+    return json.load(open(os.path.join(GOLDEN, "real77_time.json"), encoding="utf-8"))
+
+
+def test_attr_words_reproduce_reference_predicate():
+    """Packed word + psx_filter == Searcher._check_time_match_v2 on the reference's real metadata
+    and on adversarial records."""
+    from photo_search_engine_b200.exif_attrs import attr_words, build_filter
+    from tests._fake_backend import attr_pass_np
+
+    meta = _real_meta()
+    meta += [
+        {},
+        {"exif_data": None, "time_info": None},
+        {"exif_data": {"datetime": "2024:02:29 23:59:59"}, "time_info": {"season": "冬天", "year": 2024, "month": 2}},
+        {"exif_data": {"datetime": ""}, "time_info": {"season": "夏天", "time_period": "下午", "year": 2023, "month": 7,
+                                                     "datetime_str": "2023-07-01T14:00:00"}},
+        {"exif_data": {"datetime": "garbage"}, "time_info": {"season": "夏天", "year": 2023, "month": 7}},
+        {"exif_data": {"datetime": "2023-12-31T23:59:59"}, "time_info": O.time_info_from_exif("2023-12-31T23:59:59")},
+        {"exif_data": {"datetime": "2024-01-01T00:00:00"}, "time_info": O.time_info_from_exif("2024-01-01T00:00:00")},
+        {"exif_data": {"datetime": "0001-01-01T00:00:00"}, "time_info": O.time_info_from_exif("0001-01-01T00:00:00")},
+        {"exif_data": {"datetime": "9999-12-31T23:59:59"}, "time_info": O.time_info_from_exif("9999-12-31T23:59:59")},
+    ]
+    words = attr_words(meta)
+    cases = [
+        {"season": "夏天"}, {"season": "春天"}, {"time_period": "下午"}, {"time_period": "夜晚", "season": "冬天"},
+        {"year": 2023}, {"year": 2024, "month": 2}, {"month": 12},
+        {"start_date": "2023-01-01", "end_date": "2023-12-31"}, {"start_date": "2024-01-01"},
+        {"end_date": "2023-12-31"}, {"end_date": "2023-12-31T23:59:58"}, {"start_date": "2023/07/01 14:00:00"},
+        {"start_date": "not a date"}, {"start_date": "20230101", "end_date": "20231231", "season": "夏天"},
+        {"start_date": "0001-01-01", "end_date": "9999-12-31"},
+        {"season": None, "year": 0, "start_date": None},
+    ]
+    for c in cases:
+        want = np.array([O.check_time_match_v2(m, c) for m in meta])
+        flt, never = build_filter(c)
+        if flt is None:
+            assert want.all(), c
+            continue
+        got = np.zeros(len(meta), bool) if never else attr_pass_np(words, flt)
+        assert got.tolist() == want.tolist(), c
+    # unrepresentable constraints match nothing, as `!=` does in the reference
+    for c in ({"season": "雨季"}, {"year": "2023"}, {"month": 13}):
+        flt, never = build_filter(c)
+        assert never and not any(O.check_time_match_v2(m, c) for m in meta)
+
+
+def test_filtered_search_equals_reference_post_filter_superset(VS, tmp_path):
+    ix, _ = O.read_index(os.path.join(GOLDEN, "real77.index"))
+    x = ix._matrix()
+    meta = _real_meta()
+    s = VS(4096, *_paths(tmp_path))
+    for i, m in enumerate(meta):
+        m["photo_path"] = f"/p/{i}.jpg"
+        s.add_item(x[i].tolist(), m)
+    gold = json.load(open(os.path.join(GOLDEN, "real77_topk.json")))
+    for case in gold["predicates"]:
+        for qi in range(4):
+            hits = s.search(x[qi].tolist(), 10, constraints=case["constraints"])
+            got = [int(h["metadata"]["photo_path"].split("/")[-1][:-4]) for h in hits]
+            assert got == [i for i in case["ids"][qi] if i != -1]
+            # identical to filtering the reference's full ranking afterwards
+            full = s.search(x[qi].tolist(), 77)
+            post = [h for h in full if O.check_time_match_v2(h["metadata"], case["constraints"])][:10]
+            assert [h["metadata"] for h in hits] == [h["metadata"] for h in post]
+    assert s.search(x[0].tolist(), 5, constraints={"season": "雨季"}) == []
+    # rows appended later get their word lazily
+    s.add_item(x[0].tolist(), {"photo_path": "/late.jpg", "exif_data": {"datetime": "2030-07-01T10:00:00"},
+                               "time_info": O.time_info_from_exif("2030-07-01T10:00:00")})
+    hits = s.search(x[0].tolist(), 3, constraints={"year": 2030})
+    assert [h["metadata"]["photo_path"] for h in hits] == ["/late.jpg"]
+
+
+# ---- batch API ---------------------------------------------------------------------------------------
+def test_batch_api(VS, tmp_path):
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal((300, 32)).astype(np.float32)
+    s = VS(32, *_paths(tmp_path))
+    s.add_batch(x, [{"photo_path": f"{i}"} for i in range(300)])
+    t = VS(32, str(tmp_path / "b"), str(tmp_path / "c"))
+    for i in range(300):
+        t.add_item(x[i].tolist(), {"photo_path": f"{i}"})
+    q = rng.standard_normal((5, 32)).astype(np.float32)
+    D, I = s.search_batch(q, 7)
+    for qi in range(5):
+        single = t.search(q[qi].tolist(), 7)
+        assert [int(h["metadata"]["photo_path"]) for h in single] == I[qi].tolist()
+        assert np.allclose([h["distance"] for h in single], D[qi], rtol=1e-6, atol=1e-7)
+    D, I = s.search_batch(q, 400)
+    assert D.shape == (5, 400) and (I[:, 300:] == -1).all() and np.isinf(D[:, 300:]).all()

@@ -1,0 +1,114 @@
+"""Pin the oracle: golden vectors / fixtures the reference itself ships."""
+from __future__ import annotations
+
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import flat_ip as O
+from tests.conftest import GOLDEN, REFERENCE
+
+
+def _fake_embedding(text: str, d: int = 8):
+    # tests/helpers.py:6-15 FakeEmbeddingService, restated
+    seed = float(sum(ord(c) for c in text) % 13)
+    return [seed + float(i) for i in range(d)]
+
+
+def test_flat_file_reproduced_byte_for_byte(tmp_path):
+    """add_item + save of the row the reference indexed == the FAISS-written fixture bytes."""
+    want = open(os.path.join(GOLDEN, "build_smoke.idx"), "rb").read()
+    store = O.OracleVectorStore(8, str(tmp_path / "idx"), str(tmp_path / "meta.json"))
+    store.add_item(_fake_embedding("photo 图片 32x24"), {"photo_path": "x"})
+    store.save()
+    assert open(tmp_path / "idx", "rb").read() == want
+    assert json.load(open(tmp_path / "idx.meta.json")) == json.load(open(os.path.join(GOLDEN, "build_smoke.idx.meta.json")))
+
+
+def test_flat_file_round_trip():
+    index, info = O.read_index(os.path.join(GOLDEN, "build_smoke.idx"))
+    assert (info["d"], info["ntotal"], info["metric"]) == (8, 1, 0)
+    row = index.reconstruct(0)
+    want = np.array(O.normalize_vector(_fake_embedding("photo 图片 32x24")), np.float32)
+    assert np.array_equal(row, want)
+
+
+def test_ihnf_container_parsed(tmp_path):
+    """FAISS IHNf container (graph header + nested flat block) -> the 77x4096 real rows."""
+    gold = json.load(open(os.path.join(GOLDEN, "real77_topk.json")))
+    path = tmp_path / "photo_search.index"
+    with open(path, "wb") as f:
+        f.write(open(os.path.join(GOLDEN, "real77_hnsw_header.bin"), "rb").read())
+        f.write(open(os.path.join(GOLDEN, "real77.index"), "rb").read())
+    index, info = O.read_index(str(path))
+    assert info["fourcc"] == "IHNf" and info["d"] == 4096 and info["ntotal"] == 77
+    for key, val in gold["ihnf"].items():
+        assert info[key] == val
+    flat, _ = O.read_index(os.path.join(GOLDEN, "real77.index"))
+    assert np.array_equal(flat._matrix(), index._matrix())
+    norms = np.linalg.norm(index._matrix(), axis=1)
+    assert np.all(np.abs(norms - 1) < 1e-6)
+
+
+@pytest.mark.skipif(not os.path.isdir(REFERENCE), reason="reference checkout not present")
+def test_fixtures_match_reference_checkout():
+    assert open(os.path.join(GOLDEN, "build_smoke.idx"), "rb").read() == open(
+        os.path.join(REFERENCE, "pytest-tmp", "build-smoke", "data", "idx"), "rb").read()
+    raw = open(os.path.join(REFERENCE, "data", "photo_search.index"), "rb").read()
+    assert raw[30865:] == open(os.path.join(GOLDEN, "real77.index"), "rb").read()
+
+
+def test_real77_known_answers():
+    gold = json.load(open(os.path.join(GOLDEN, "real77_topk.json")))
+    index, _ = O.read_index(os.path.join(GOLDEN, "real77.index"))
+    x = index._matrix()
+    D, I = index.search(x, gold["k"])
+    assert I.tolist() == gold["ids"]
+    assert np.allclose(D, np.array(gold["scores"], np.float32), rtol=1e-6, atol=1e-7)
+    assert I[:, 0].tolist() == list(range(77))  # every row is its own best hit
+    # float64 ground truth agrees within the north-star tolerance
+    D64 = np.sort(x.astype(np.float64) @ x.astype(np.float64).T, axis=1)[:, ::-1][:, : gold["k"]]
+    assert np.allclose(D, D64, rtol=1e-5, atol=1e-6)
+
+
+def test_real77_predicate_known_answers():
+    gold = json.load(open(os.path.join(GOLDEN, "real77_topk.json")))
+    meta = json.load(open(os.path.join(GOLDEN, "real77_time.json"), encoding="utf-8"))
+    index, _ = O.read_index(os.path.join(GOLDEN, "real77.index"))
+    x = index._matrix()
+    for case in gold["predicates"]:
+        mask = np.array([O.check_time_match_v2(m, case["constraints"]) for m in meta])
+        assert np.nonzero(mask)[0].tolist() == case["pass_rows"]
+        _, I = index.search(x[:4], 10, mask=mask)
+        assert I.tolist() == case["ids"]
+
+
+def test_reference_tie_and_normalisation_semantics(tmp_path):
+    """tests/test_vector_store.py:35-51 and :163-175 of the reference, on the oracle."""
+    for d in (8, 768, 1024, 4096):
+        s = O.OracleVectorStore(d, str(tmp_path / "i"), str(tmp_path / "m"))
+        s.add_item([0.1] * d, {"id": 1})
+        s.add_item([0.5] * d, {"id": 2, "photo_path": "/b.jpg"})
+        hit = s.search([0.1] * d, 1)
+        assert len(hit) == 1 and hit[0]["metadata"]["id"] == 1 and hit[0]["distance"] >= 0.0
+        assert abs(s.get_embedding_by_photo_path("/b.jpg")[0] - 1 / d**0.5) < 5e-7
+
+
+def test_l2_and_unfilled_slots():
+    ix = O.OracleIndexFlat(4, O.METRIC_L2)
+    ix.add(np.array([[0, 0, 0, 0], [1, 0, 0, 0], [0, 2, 0, 0]], np.float32))
+    D, I = ix.search(np.array([[0, 0, 0, 0]], np.float32), 5)
+    assert I[0].tolist() == [0, 1, 2, -1, -1]
+    assert D[0, :3].tolist() == [0.0, 1.0, 4.0] and np.isinf(D[0, 3])
+
+
+def test_call_site_arithmetic():
+    # core/searcher.py:605-625 pins from tests/test_searcher.py:33-46
+    assert O.distance_to_score(1.0) > 0.9 and O.distance_to_score(-1.0) < 0.1
+    assert O.distance_to_score(0.0, "l2") == 1.0
+    # core/searcher.py:771-820: the k the kernel has to serve
+    assert O.calculate_candidate_k(10_000_000, 12, False) == 500
+    assert O.calculate_candidate_k(10_000_000, 50, True, 3) == 1333
+    assert O.calculate_candidate_k(40, 12, False) == 40
