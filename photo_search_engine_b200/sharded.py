@@ -1,0 +1,121 @@
+"""Row-sharded exact search across the GPUs of one box: one process per GPU
+(``torch.distributed``), each rank scans its contiguous row range with the single-GPU kernel,
+the per-rank k best travel as 64-bit keys in ONE all-gather (k * 8 bytes per rank per query --
+latency-bound over NVLink), and every rank runs the same integer merge, so all ranks return the
+identical global top-k.  SURVEY.md section 8(e); there is nothing to compare with in the
+reference, which is single-process.
+
+Rows are partitioned contiguously: rank r owns ``[bounds[r], bounds[r+1])``; ids reported are
+global (``id_base`` is added inside the kernel), so the result equals the single-GPU result bit
+for bit -- the per-row reduction tree does not depend on where a row is scanned.
+"""
+from __future__ import annotations
+
+from typing import Callable, List, Optional, Tuple
+
+import numpy as np
+
+from . import _native
+
+
+def shard_bounds(n_total: int, world_size: int) -> List[int]:
+    """Contiguous row ranges, ceil(n/world) rows per rank (the last ranks may be short/empty)."""
+    per = -(-int(n_total) // int(world_size)) if n_total > 0 else 0
+    return [min(r * per, n_total) for r in range(world_size + 1)]
+
+
+class ShardedIndex:
+    """One rank's handle on a row-sharded corpus.
+
+    ``local`` is this rank's single-GPU index (``_native.NativeIndex``) holding rows
+    ``[row0, row0 + local.ntotal)`` of the global corpus.  ``group`` is a ``torch.distributed``
+    process group (NCCL on the GPU box; the gloo tests inject ``local_search`` / ``merge``).
+    """
+
+    def __init__(self, local, row0: int, k_max: int = 128, group=None,
+                 local_search: Optional[Callable] = None, merge: Optional[Callable] = None) -> None:
+        import torch
+        import torch.distributed as dist
+
+        self.torch, self.dist = torch, dist
+        self.local = local
+        self.row0 = int(row0)
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self._local_search = local_search
+        self._merge = merge
+        self.device = torch.device("cuda", local.device) if local_search is None else torch.device("cpu")
+        self._bufs = {}
+
+    # -- buffers are cached per (nq, k): the steady-state query allocates nothing ----------------
+    def _buffers(self, nq: int, k: int):
+        key = (nq, k)
+        if key not in self._bufs:
+            t = self.torch
+            kp = _native.kpad(k)
+            d = self.local.d
+            pin = self.device.type == "cuda"
+            self._bufs[key] = dict(
+                kp=kp,
+                q=t.empty((nq, d), dtype=t.float32, device=self.device),
+                q_host=t.empty((nq, d), dtype=t.float32, pin_memory=pin),
+                mine=t.zeros((nq, kp), dtype=t.int64, device=self.device),
+                gathered=t.zeros((self.world * nq, kp), dtype=t.int64, device=self.device),
+                lists=t.zeros((nq, self.world, kp), dtype=t.int64, device=self.device),
+                scores=t.empty((nq, k), dtype=t.float32, device=self.device),
+                ids=t.empty((nq, k), dtype=t.int64, device=self.device),
+                scores_host=t.empty((nq, k), dtype=t.float32, pin_memory=pin),
+                ids_host=t.empty((nq, k), dtype=t.int64, pin_memory=pin),
+            )
+        return self._bufs[key]
+
+    def search_device(self, q_dev, k: int, flt=None):
+        """``q_dev``: float32 ``[nq, d]`` tensor on this rank's device (same on every rank).
+        Returns device tensors ``(scores [nq,k], ids [nq,k])`` -- identical on every rank.
+        Everything is enqueued on the current torch stream; no host synchronisation."""
+        t = self.torch
+        nq = int(q_dev.shape[0])
+        b = self._buffers(nq, k)
+        if self._local_search is not None:  # CPU test path: keys from the injected scanner
+            b["mine"].copy_(self._local_search(q_dev, k, self.row0, flt))
+        else:
+            stream = t.cuda.current_stream(self.device).cuda_stream
+            self.local.search_device(q_dev.data_ptr(), nq, k, 0, 0, b["mine"].data_ptr(), flt=flt,
+                                     id_base=self.row0, stream=stream)
+        if self.world > 1:
+            self.dist.all_gather_into_tensor(b["gathered"], b["mine"], group=self.group)
+            if nq == 1:
+                lists = b["gathered"].view(1, self.world, b["kp"])
+            else:
+                lists = b["lists"]
+                lists.copy_(b["gathered"].view(self.world, nq, b["kp"]).permute(1, 0, 2))
+        else:
+            lists = b["mine"].view(nq, 1, b["kp"])
+        if self._merge is not None:
+            s, i = self._merge(lists, k)
+            b["scores"].copy_(s)
+            b["ids"].copy_(i)
+        else:
+            stream = t.cuda.current_stream(self.device).cuda_stream
+            _native.merge_keys_device(self.local.device, lists.data_ptr(), nq, self.world, k, self.local.metric,
+                                      b["scores"].data_ptr(), b["ids"].data_ptr(), stream)
+        return b["scores"], b["ids"]
+
+    def search(self, q: np.ndarray, k: int, flt=None) -> Tuple[np.ndarray, np.ndarray]:
+        """Host in, host out (the call a user makes): pinned H2D of the query, sharded search,
+        D2H of the merged result.  Collective: every rank must call it with the same query."""
+        t = self.torch
+        q = np.ascontiguousarray(q, np.float32)
+        if q.ndim == 1:
+            q = q[None]
+        nq = q.shape[0]
+        b = self._buffers(nq, k)
+        b["q_host"].copy_(t.from_numpy(q))
+        b["q"].copy_(b["q_host"], non_blocking=True)
+        s, i = self.search_device(b["q"], k, flt)
+        b["scores_host"].copy_(s, non_blocking=True)
+        b["ids_host"].copy_(i, non_blocking=True)
+        if self.device.type == "cuda":
+            t.cuda.current_stream(self.device).synchronize()
+        return b["scores_host"].numpy().copy(), b["ids_host"].numpy().copy()

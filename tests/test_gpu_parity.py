@@ -1,0 +1,449 @@
+"""Parity tests proper: the CUDA path, called through the C ABI (ctypes -> libpsx.so), against the
+CPU oracle on the same seeded inputs.
+
+Tolerance (north star): ids identical except where the oracle's own scores tie within
+``1e-5 * |score| + 1e-6``; fp32 scores within the same bound.  Exact duplicates must come back in
+ascending id order (bit-equal scores, deterministic tie rule).
+"""
+from __future__ import annotations
+
+import json
+import os
+import threading
+
+import numpy as np
+import pytest
+
+from oracle import flat_ip as O
+from tests.conftest import GOLDEN, has_gpu
+
+pytestmark = pytest.mark.gpu
+
+RTOL, ATOL = 1e-5, 1e-6
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _need_gpu():
+    if not has_gpu():
+        pytest.skip("no GPU")
+
+
+def N():
+    from photo_search_engine_b200 import _native
+
+    return _native
+
+
+def unit_rows(rng, n, d):
+    x = rng.standard_normal((n, d)).astype(np.float32)
+    x /= np.linalg.norm(x, axis=1, keepdims=True)
+    return x.astype(np.float32)
+
+
+def check_against_oracle(D, I, oracle: O.OracleIndexFlat, q, k, mask=None, stored=None):
+    """Apply the tolerance rule query by query.  ``stored`` (optional) = the rows as the device
+    holds them (bf16 storage)."""
+    ip = oracle.metric_type == O.METRIC_INNER_PRODUCT
+    Dw, Iw = oracle.search(q, k, mask=mask)
+    for qi in range(q.shape[0]):
+        s = oracle.scores(q[qi])  # larger is better, fp32
+        want_ids, got_ids = Iw[qi], I[qi]
+        nvalid = int((want_ids >= 0).sum())
+        assert int((got_ids >= 0).sum()) == nvalid, "number of filled slots differs"
+        assert (got_ids[nvalid:] == -1).all()
+        if nvalid == 0:
+            continue
+        got_s = D[qi, :nvalid] if ip else -D[qi, :nvalid]
+        tol = RTOL * np.abs(s[want_ids[:nvalid]]) + ATOL
+        # scores position by position
+        assert np.all(np.abs(got_s - s[want_ids[:nvalid]]) <= tol), "score out of tolerance"
+        # scores reported for the returned ids are the oracle's scores of those ids
+        assert np.all(np.abs(got_s - s[got_ids[:nvalid]]) <= tol), "reported score does not belong to reported id"
+        assert len(set(got_ids[:nvalid].tolist())) == nvalid, "duplicate ids"
+        if mask is not None:
+            assert mask[got_ids[:nvalid]].all(), "a filtered-out row was returned"
+        diff = got_ids[:nvalid] != want_ids[:nvalid]
+        if diff.any():  # only near-ties may swap
+            assert np.all(np.abs(s[got_ids[:nvalid][diff]] - s[want_ids[:nvalid][diff]]) <= tol[diff]), "ids differ beyond ties"
+        # descending order of what we returned
+        assert np.all(np.diff(got_s) <= 0), "result not sorted"
+
+
+def make_index(x, metric=0, dtype=0, chunk=None):
+    ix = N().NativeIndex(x.shape[1], metric, dtype, 0)
+    if chunk is None:
+        ix.add(x)
+    else:
+        for s in range(0, x.shape[0], chunk):
+            ix.add(x[s : s + chunk])
+    return ix
+
+
+def make_oracle(x, metric=0):
+    o = O.OracleIndexFlat(x.shape[1], metric)
+    o.add(x)
+    return o
+
+
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize(
+    "n,d,ks",
+    [
+        (1, 8, [1, 5]),
+        (2, 8, [1, 2]),
+        (31, 8, [7, 31]),
+        (33, 12, [33]),
+        (1000, 8, [50]),
+        (777, 100, [1, 100, 777]),
+        (5000, 768, [50, 500]),
+        (20000, 1024, [50, 100, 1333]),
+        (3000, 4096, [100, 2048]),
+        (257, 4100, [10]),
+        (4097, 20, [2048]),
+    ],
+)
+def test_fp32_ip_shapes(n, d, ks):
+    rng = np.random.default_rng(n * 131 + d)
+    x = unit_rows(rng, n, d)
+    q = np.concatenate([unit_rows(rng, 2, d), x[:1] + 0.05 * unit_rows(rng, 1, d)]).astype(np.float32)
+    ix, oracle = make_index(x), make_oracle(x)
+    assert ix.ntotal == n
+    for k in ks:
+        D, I = ix.search(q, k)
+        assert D.shape == (3, k) and I.dtype == np.int64
+        check_against_oracle(D, I, oracle, q, k)
+    ix.close()
+
+
+def test_reference_tie_cases():
+    """tests/test_vector_store.py:35-51 / :150-161 / tests/test_searcher.py:323-350 of the reference."""
+    for d in (8, 768, 1024, 4096):
+        a = np.array(O.normalize_vector([0.1] * d), np.float32)
+        b = np.array(O.normalize_vector([0.5] * d), np.float32)
+        ix = make_index(np.stack([a, b]))
+        D, I = ix.search(a[None], 1)
+        want = 0 if np.array_equal(a, b) else int(np.argmax([a @ a, b @ a]))
+        assert I[0, 0] == want == 0
+        ix.close()
+    d = 8
+    rows = [O.normalize_vector([i * 0.1] * d) for i in range(10)]  # row 0 is the zero vector, rows 1.. collapse
+    x = np.array(rows, np.float32)
+    ix, oracle = make_index(x), make_oracle(x)
+    q = np.array([O.normalize_vector([0.1] * d)], np.float32)
+    D, I = ix.search(q, 5)
+    check_against_oracle(D, I, oracle, q, 5)
+    Dw, Iw = oracle.search(q, 10)
+    D, I = ix.search(q, 10)
+    assert I[0, -1] == 0 and D[0, -1] == 0.0  # the zero vector scores 0 and ranks last
+    # bit-identical rows come back in ascending id order
+    groups = {}
+    for i in range(1, 10):
+        groups.setdefault(x[i].tobytes(), []).append(i)
+    pos = {int(r): p for p, r in enumerate(I[0])}
+    for ids in groups.values():
+        assert [pos[i] for i in ids] == sorted(pos[i] for i in ids)
+    ix.close()
+
+
+def test_exact_duplicates_order_by_id():
+    rng = np.random.default_rng(5)
+    base = unit_rows(rng, 50, 1024)
+    x = np.concatenate([base, base[::-1], base]).astype(np.float32)  # every row three times
+    ix = make_index(x)
+    q = base[7:8]
+    D, I = ix.search(q, 9)
+    assert I[0, :3].tolist() == [7, 92, 107] and D[0, 0] == D[0, 1] == D[0, 2]
+    for j in range(0, 9, 3):
+        assert D[0, j] == D[0, j + 1] == D[0, j + 2] and I[0, j] < I[0, j + 1] < I[0, j + 2]
+    ix.close()
+
+
+def test_l2_metric():
+    rng = np.random.default_rng(11)
+    x = rng.standard_normal((4000, 96)).astype(np.float32)
+    q = rng.standard_normal((3, 96)).astype(np.float32)
+    ix, oracle = make_index(x, metric=1), make_oracle(x, metric=1)
+    for k in (1, 64, 300):
+        D, I = ix.search(q, k)
+        check_against_oracle(D, I, oracle, q, k)
+        assert (D >= 0).all()
+    D, I = ix.search(x[10:11], 1)
+    assert I[0, 0] == 10 and D[0, 0] == 0.0
+    D, I = ix.search(q, 4100)
+    assert (I[:, 4000:] == -1).all() and np.isposinf(D[:, 4000:]).all()
+    ix.close()
+
+
+def _bf16_round(x):
+    u = x.view(np.uint32).astype(np.uint64)
+    r = ((u + 0x7FFF + ((u >> 16) & 1)) >> 16) << 16
+    return r.astype(np.uint32).view(np.float32).reshape(x.shape)
+
+
+@pytest.mark.parametrize("n,d", [(3000, 768), (2000, 1024), (500, 72), (300, 4104)])
+def test_bf16_storage(n, d):
+    """bf16 rows, fp32 query and accumulate: exact against the oracle run on the rounded rows,
+    and recall against the fp32 rows is reported by bench/DESIGN (north star >= 0.999)."""
+    rng = np.random.default_rng(d)
+    x = unit_rows(rng, n, d)
+    q = unit_rows(rng, 3, d)
+    ix = make_index(x, dtype=1)
+    xr = _bf16_round(x)
+    assert np.array_equal(ix.reconstruct(5), xr[5])
+    assert np.array_equal(ix.read_rows(0, n), xr)
+    oracle = make_oracle(xr)
+    for k in (10, 100):
+        D, I = ix.search(q, k)
+        check_against_oracle(D, I, oracle, q, k)
+    ix.close()
+
+
+def test_k_beyond_one_pass_and_beyond_n():
+    rng = np.random.default_rng(3)
+    x = unit_rows(rng, 9000, 64)
+    x[100] = x[200]  # a tie straddling pages is still ordered by id
+    q = unit_rows(rng, 2, 64)
+    ix, oracle = make_index(x), make_oracle(x)
+    for k in (2049, 5000, 9000, 9500):
+        D, I = ix.search(q, k)
+        check_against_oracle(D, I, oracle, q, k)
+        kk = min(k, 9000)
+        assert sorted(I[0, :kk].tolist()) == sorted(set(I[0, :kk].tolist()))
+    D, I = ix.search(q, 9000)
+    assert sorted(I[0].tolist()) == list(range(9000))  # a full ranking is a permutation
+    ix.close()
+
+
+def test_incremental_add_reset_reconstruct():
+    rng = np.random.default_rng(8)
+    x = unit_rows(rng, 2500, 40)
+    ix = N().NativeIndex(40)
+    D, I = ix.search(x[:1], 3)
+    assert (I == -1).all() and np.isneginf(D).all()
+    oracle = O.OracleIndexFlat(40)
+    done = 0
+    for step in (1, 1, 30, 468, 2000):
+        ix.add(x[done : done + step])
+        oracle.add(x[done : done + step])
+        done += step
+        assert ix.ntotal == done
+        assert np.array_equal(ix.reconstruct(done - 1), x[done - 1])  # may still be staged on the host
+        D, I = ix.search(x[:2], 5)
+        check_against_oracle(D, I, oracle, x[:2], 5)
+    assert np.array_equal(ix.read_rows(7, 100), x[7:107])
+    with pytest.raises(ValueError):
+        ix.reconstruct(2500)
+    with pytest.raises(ValueError):
+        ix.search(np.zeros((1, 41), np.float32), 3)
+    with pytest.raises(ValueError):
+        ix.search(x[:1], 0)
+    ix.reset()
+    assert ix.ntotal == 0
+    ix.add(x[:10])
+    D, I = ix.search(x[3:4], 1)
+    assert I[0, 0] == 3
+    ix.close()
+
+
+def _random_meta(rng, n):
+    meta = []
+    for i in range(n):
+        if rng.random() < 0.2:
+            meta.append({"exif_data": {}, "time_info": O.time_info_from_exif(None)})
+            continue
+        t = f"{int(rng.integers(2015, 2026)):04d}-{int(rng.integers(1, 13)):02d}-{int(rng.integers(1, 29)):02d}T" \
+            f"{int(rng.integers(0, 24)):02d}:{int(rng.integers(0, 60)):02d}:{int(rng.integers(0, 60)):02d}"
+        meta.append({"exif_data": {"datetime": t}, "time_info": O.time_info_from_exif(t)})
+    return meta
+
+
+@pytest.mark.parametrize("n,d", [(6000, 1024), (5000, 8), (3000, 4096), (4000, 200)])
+def test_fused_predicate(n, d):
+    """Scan restricted by the packed EXIF word == oracle restricted to rows passing the restated
+    ``_check_time_match_v2`` (core/searcher.py:1884-1950)."""
+    from photo_search_engine_b200.exif_attrs import attr_words, build_filter
+
+    rng = np.random.default_rng(n + d)
+    x = unit_rows(rng, n, d)
+    q = unit_rows(rng, 2, d)
+    meta = _random_meta(rng, n)
+    ix, oracle = make_index(x), make_oracle(x)
+    ix.set_attrs(0, attr_words(meta))
+    cases = [
+        {"season": "夏天"},
+        {"start_date": "2020-01-01", "end_date": "2020-12-31"},
+        {"season": "冬天", "time_period": "上午"},
+        {"year": 2021, "month": 2},
+        {"start_date": "2015-01-01", "end_date": "2025-12-31"},  # every EXIF-bearing row
+        {"year": 1999},  # nothing
+        {"start_date": "2024-06-30T12:00:00"},
+    ]
+    for c in cases:
+        mask = np.array([O.check_time_match_v2(m, c) for m in meta])
+        flt, never = build_filter(c)
+        assert flt is not None and not never
+        for k in (1, 100, 700):
+            D, I = ix.search(q, k, flt)
+            check_against_oracle(D, I, oracle, q, k, mask=mask)
+    # rows without an attribute word behave like photos without EXIF
+    ix.add(x[:50])
+    oracle.add(x[:50])
+    mask = np.concatenate([np.array([O.check_time_match_v2(m, cases[0]) for m in meta]), np.zeros(50, bool)])
+    D, I = ix.search(q, 100, build_filter(cases[0])[0])
+    check_against_oracle(D, I, oracle, q, 100, mask=mask)
+    ix.close()
+
+
+def test_real77_known_answers_on_gpu():
+    gold = json.load(open(os.path.join(GOLDEN, "real77_topk.json")))
+    oracle, _ = O.read_index(os.path.join(GOLDEN, "real77.index"))
+    x = oracle._matrix()
+    ix = make_index(x)
+    D, I = ix.search(x, gold["k"])
+    # the near-duplicate pair may swap within tolerance; everything else is identical to the gold ids
+    check_against_oracle(D, I, oracle, x, gold["k"])
+    same = (I == np.array(gold["ids"])).mean()
+    assert same > 0.99
+    assert np.allclose(D, np.array(gold["scores"], np.float32), rtol=RTOL, atol=ATOL)
+    from photo_search_engine_b200.exif_attrs import attr_words, build_filter
+
+    meta = json.load(open(os.path.join(GOLDEN, "real77_time.json"), encoding="utf-8"))
+    ix.set_attrs(0, attr_words(meta))
+    for case in gold["predicates"]:
+        flt, never = build_filter(case["constraints"])
+        D, I = ix.search(x[:4], 10, flt)
+        assert I.tolist() == case["ids"]
+    ix.close()
+
+
+def test_determinism_and_tunables():
+    rng = np.random.default_rng(21)
+    x = unit_rows(rng, 30000, 1024)
+    q = unit_rows(rng, 1, 1024)
+    ix = make_index(x)
+    D0, I0 = ix.search(q, 100)
+    for key, val in (("warps", 4), ("stages", 2), ("warps", 16), ("stages", 3), ("ctas_per_sm", 2), ("warps", 8)):
+        ix.set_tunable(key, val)
+        D, I = ix.search(q, 100)
+        # same reduction tree per row -> bit-identical scores whatever the launch geometry
+        assert np.array_equal(I, I0) and np.array_equal(D, D0), (key, val)
+    ix.close()
+
+
+def test_concurrent_searches_one_handle():
+    rng = np.random.default_rng(4)
+    x = unit_rows(rng, 20000, 256)
+    q = unit_rows(rng, 8, 256)
+    ix, oracle = make_index(x), make_oracle(x)
+    Dw, Iw = ix.search(q, 20)
+    errors = []
+
+    def worker(j):
+        try:
+            for _ in range(20):
+                D, I = ix.search(q[j : j + 1], 20)
+                assert np.array_equal(I[0], Iw[j]) and np.array_equal(D[0], Dw[j])
+        except Exception as exc:  # pragma: no cover
+            errors.append(exc)
+
+    threads = [threading.Thread(target=worker, args=(j,)) for j in range(8)]
+    [t.start() for t in threads]
+    [t.join() for t in threads]
+    assert not errors
+    check_against_oracle(Dw, Iw, oracle, q, 20)
+    ix.close()
+
+
+def test_device_api_and_shard_merge():
+    """psx_search_device + psx_merge_keys_device: row shards with an id base, all lists gathered,
+    one merge -> bit-identical to the single-index result (what the multi-GPU path relies on)."""
+    import torch
+
+    n, d, k, nq = 30000, 512, 100, 3
+    rng = np.random.default_rng(17)
+    x = unit_rows(rng, n, d)
+    x[12345] = x[77]  # tie across shards
+    q = unit_rows(rng, nq, d)
+    q[0] = x[77]
+    whole = make_index(x)
+    Dw, Iw = whole.search(q, k)
+    bounds = [0, 9000, 9001, 21000, n]
+    kp = N().kpad(k)
+    qd = torch.from_numpy(q).cuda()
+    keys = torch.zeros((nq, len(bounds) - 1, kp), dtype=torch.int64, device="cuda")
+    stream = torch.cuda.current_stream().cuda_stream
+    shards = []
+    for si in range(len(bounds) - 1):
+        sh = make_index(x[bounds[si] : bounds[si + 1]])
+        shards.append(sh)
+        tmp = torch.empty((nq, kp), dtype=torch.int64, device="cuda")
+        sc = torch.empty((nq, k), dtype=torch.float32, device="cuda")
+        ids = torch.empty((nq, k), dtype=torch.int64, device="cuda")
+        sh.search_device(qd.data_ptr(), nq, k, sc.data_ptr(), ids.data_ptr(), tmp.data_ptr(), id_base=bounds[si], stream=stream)
+        keys[:, si, :] = tmp
+        torch.cuda.synchronize()
+        # per-shard outputs are already global ids
+        valid = ids[ids >= 0]
+        assert int(valid.min()) >= bounds[si] and int(valid.max()) < bounds[si + 1]
+    out_s = torch.empty((nq, k), dtype=torch.float32, device="cuda")
+    out_i = torch.empty((nq, k), dtype=torch.int64, device="cuda")
+    N().merge_keys_device(0, keys.data_ptr(), nq, len(bounds) - 1, k, 0, out_s.data_ptr(), out_i.data_ptr(), stream)
+    torch.cuda.synchronize()
+    assert np.array_equal(out_i.cpu().numpy(), Iw) and np.array_equal(out_s.cpu().numpy(), Dw)
+    assert Iw[0, 0] == 77 and Iw[0, 1] == 12345
+    for sh in shards:
+        sh.close()
+    whole.close()
+
+
+def test_full_size_properties_1m_x_1024():
+    """BASELINE config 2 size, generated on the device.  Checked through size-independent
+    properties: planted neighbours are found at the right ranks, results equal a torch fp32
+    reference (matmul + topk, TF32 off) under the tolerance rule, the filtered scan returns only
+    passing rows and equals the reference restricted to them."""
+    import torch
+
+    torch.backends.cuda.matmul.allow_tf32 = False
+    n, d, k = 1_000_000, 1024, 100
+    g = torch.Generator(device="cuda").manual_seed(20261018)
+    x = torch.randn((n, d), generator=g, device="cuda", dtype=torch.float32)
+    x /= x.norm(dim=1, keepdim=True)
+    q = torch.randn((4, d), generator=g, device="cuda", dtype=torch.float32)
+    q[1] = x[123456] + 0.2 * q[1] / q[1].norm()
+    q[2] = x[999999]
+    q /= q.norm(dim=1, keepdim=True)
+    x[500000] = x[999999]  # exact duplicate: lower id first
+    ix = N().NativeIndex(d)
+    ix.add_device(x.data_ptr(), n)
+    assert ix.ntotal == n
+    # attribute words: dt = 1 + row, so a [start, end] window selects a row range
+    words = torch.arange(n, device="cuda", dtype=torch.int64) + 1
+    ix.set_attrs_device(0, words.data_ptr(), n)
+    D, I = ix.search(q.cpu().numpy(), k)
+    ref = x @ q.t()
+    rs, ri = torch.topk(ref, k, dim=0)
+    rs, ri = rs.t().cpu().numpy(), ri.t().cpu().numpy()
+    s_all = ref.t().cpu().numpy()
+    for qi in range(4):
+        tol = RTOL * np.abs(rs[qi]) + ATOL
+        assert np.all(np.abs(D[qi] - rs[qi]) <= tol)
+        diff = I[qi] != ri[qi]
+        assert np.all(np.abs(s_all[qi][I[qi][diff]] - s_all[qi][ri[qi][diff]]) <= tol[diff])
+        assert np.all(np.diff(D[qi]) <= 0) and len(set(I[qi].tolist())) == k
+    assert I[1, 0] == 123456
+    assert I[2, 0] == 500000 and I[2, 1] == 999999 and D[2, 0] == D[2, 1]
+    # fused predicate: rows [250000, 750000) pass
+    from photo_search_engine_b200._native import F_END, F_NEED_DT, F_START, PsxFilter
+
+    flt = PsxFilter(flags=F_NEED_DT | F_START | F_END, start=250001, end=750000)
+    Df, If = ix.search(q.cpu().numpy(), k, flt)
+    assert ((If >= 250000) & (If < 750000)).all()
+    rs2, ri2 = torch.topk(ref[250000:750000], k, dim=0)
+    ri2 = ri2.t().cpu().numpy() + 250000
+    rs2 = rs2.t().cpu().numpy()
+    for qi in range(4):
+        tol = RTOL * np.abs(rs2[qi]) + ATOL
+        assert np.all(np.abs(Df[qi] - rs2[qi]) <= tol)
+        diff = If[qi] != ri2[qi]
+        assert np.all(np.abs(s_all[qi][If[qi][diff]] - s_all[qi][ri2[qi][diff]]) <= tol[diff])
+    ix.close()

@@ -1,0 +1,114 @@
+"""N>1 host logic on CPU: world_size-2 (and 3) ``gloo`` groups drive ``ShardedIndex`` with an
+oracle-backed local scanner and a numpy key merge.  Checks the row partition, the id bases, the
+key encoding and the all-gather/merge plumbing: every rank must return the single-index result."""
+from __future__ import annotations
+
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port() -> int:
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank: int, world: int, port: int, out_dir: str) -> None:
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+
+    from oracle import flat_ip as O
+    from photo_search_engine_b200 import _native, keys
+    from photo_search_engine_b200.sharded import ShardedIndex, shard_bounds
+
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    n, d, k, nq = 1003, 24, 17, 3
+    rng = np.random.default_rng(99)
+    x = rng.standard_normal((n, d)).astype(np.float32)
+    x /= np.linalg.norm(x, axis=1, keepdims=True)
+    x[700] = x[3]  # an exact tie living on different ranks
+    q = rng.standard_normal((nq, d)).astype(np.float32)
+    q[0] = x[3]
+    bounds = shard_bounds(n, world)
+    lo, hi = bounds[rank], bounds[rank + 1]
+    whole = O.OracleIndexFlat(d)
+    whole.add(x)
+    # one global score table: BLAS results depend on where a row sits in the matrix, the GPU
+    # kernel's do not -- this test is about the plumbing, so both sides read the same scores
+    table = np.stack([whole.scores(q[j]) for j in range(nq)])
+
+    class Local:
+        device, metric, d = 0, 0, 24
+
+    local = Local()
+    kp = _native.kpad(k)
+
+    def local_search(q_dev, kk, row0, flt):
+        D = np.full((nq, kk), -np.inf, np.float32)
+        I = np.full((nq, kk), -1, np.int64)
+        for j in range(nq):
+            s_sel, i_sel = O._topk_desc(table[j, lo:hi], kk)
+            D[j, : len(s_sel)], I[j, : len(i_sel)] = s_sel, i_sel
+        gids = np.where(I >= 0, I + row0, -1)
+        out = np.zeros((q_dev.shape[0], kp), np.uint64)
+        out[:, :kk] = keys.encode(D, gids)
+        return torch.from_numpy(out.view(np.int64))
+
+    def merge(lists, kk):
+        flat = lists.numpy().view(np.uint64).reshape(lists.shape[0], -1)
+        rows_s, rows_i = [], []
+        for row in flat:
+            order = np.sort(row)[::-1][:kk]
+            s, i = keys.decode(order)
+            rows_s.append(s)
+            rows_i.append(i)
+        return torch.from_numpy(np.stack(rows_s)), torch.from_numpy(np.stack(rows_i))
+
+    sh = ShardedIndex(local, lo, local_search=local_search, merge=merge)
+    S, I = sh.search(q, k)
+    Dw = np.stack([O._topk_desc(table[j], k)[0] for j in range(nq)])
+    Iw = np.stack([O._topk_desc(table[j], k)[1] for j in range(nq)])
+    ok = np.array_equal(I, Iw) and np.allclose(S, Dw, rtol=0, atol=0) and I[0, 0] == 3 and I[0, 1] == 700
+    np.save(os.path.join(out_dir, f"ids_{rank}.npy"), I)
+    with open(os.path.join(out_dir, f"ok_{rank}"), "w") as f:
+        f.write("1" if ok else "0")
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_search_over_gloo(tmp_path, world):
+    import torch.multiprocessing as mp
+
+    port = _free_port()
+    mp.spawn(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    results = [np.load(tmp_path / f"ids_{r}.npy") for r in range(world)]
+    for r in range(world):
+        assert open(tmp_path / f"ok_{r}").read() == "1"
+        assert np.array_equal(results[r], results[0])  # identical on every rank
+
+
+def test_shard_bounds_and_keys():
+    from photo_search_engine_b200 import keys
+    from photo_search_engine_b200.sharded import shard_bounds
+
+    assert shard_bounds(10, 4) == [0, 3, 6, 9, 10]
+    assert shard_bounds(2, 4) == [0, 1, 2, 2, 2]
+    assert shard_bounds(0, 2) == [0, 0, 0]
+    assert shard_bounds(10_000_000, 8)[-1] == 10_000_000
+    s = np.array([1.0, 1.0, 0.5, 0.0, -0.0, -0.25, -np.inf, np.nan, 3.0], np.float32)
+    i = np.array([7, 3, 1, 9, 2, 4, 5, 6, -1])
+    k = keys.encode(s, i)
+    order = np.argsort(k)[::-1]
+    # higher score first, then lower id; -0.0 == +0.0; NaN sorts as -inf; id -1 is the empty key
+    assert i[order].tolist() == [3, 7, 1, 2, 9, 4, 5, 6, -1]
+    ds, di = keys.decode(k)
+    assert di.tolist() == i.tolist()
+    assert np.array_equal(ds[:6], np.array([1, 1, 0.5, 0, 0, -0.25], np.float32)) and k[-1] == 0

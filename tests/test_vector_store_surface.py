@@ -1,4 +1,5 @@
-"""Host logic of the drop-in ``VectorStore`` (no GPU: oracle-backed fake backend).
+"""Surface + host logic of the drop-in ``VectorStore``: every case runs over the oracle-backed
+fake backend (CPU suite) and, under ``-m gpu``, over the real CUDA backend.
 
 The first block restates the reference's own ``tests/test_vector_store.py`` case by case;
 the rest covers persistence compatibility, the EXIF sidecar and the additive batch API.
@@ -12,15 +13,23 @@ import numpy as np
 import pytest
 
 from oracle import flat_ip as O
-from tests.conftest import GOLDEN
+from tests.conftest import GOLDEN, has_gpu
 
 DIMS = (8, 768, 4096)
 
 
-@pytest.fixture()
-def VS(fake_backend):
+@pytest.fixture(params=["fake", pytest.param("gpu", marks=pytest.mark.gpu)])
+def VS(request, monkeypatch):
+    """The drop-in class over the oracle-backed fake (CPU suite) or the real CUDA backend
+    (``-m gpu``): the same cases must hold for both."""
     from photo_search_engine_b200.vector_store import VectorStore
 
+    if request.param == "fake":
+        from tests._fake_backend import FakeIndex
+
+        monkeypatch.setattr(VectorStore, "_index_factory", staticmethod(FakeIndex))
+    elif not has_gpu():
+        pytest.skip("no GPU")
     return VectorStore
 
 
