@@ -11,8 +11,9 @@
  *   - every function returns PSX_OK (0) or a negative psx_status; psx_last_error() gives a
  *     thread-local human readable message for the last failure on the calling thread;
  *   - "host" pointers are ordinary CPU memory owned by the caller, "dev" pointers are CUDA
- *     device memory on the index' device, `stream` is a cudaStream_t passed as void*
- *     (NULL = the index' own stream);
+ *     device memory on the index' device, `stream` is a cudaStream_t passed as void* and is
+ *     used literally (NULL = the CUDA default stream, exactly as in the runtime API); the
+ *     host-buffer entry points run on a private non-blocking stream of the index;
  *   - row ids are 0-based insertion order, exactly as FAISS labels (utils/vector_store.py:194-197);
  *     unfilled result slots are id -1 with score -inf (inner product) / +inf (L2), as FAISS
  *     leaves them (utils/vector_store.py:195 skips label -1);

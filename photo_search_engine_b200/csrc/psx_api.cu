@@ -67,8 +67,9 @@ struct psx_index {
     cudaStream_t stream = nullptr;
     cudaEvent_t last_ev = nullptr;   // completion of the last search (scratch reuse across streams)
     cudaStream_t last_stream = nullptr;
+    bool has_last = false;
     int sm_count = 148;
-    int warps = 8, stages = 5, ctas_per_sm = 1;
+    int warps = 16, stages = 2, ctas_per_sm = 1;
 
     uint64_t* lists = nullptr;  // [grid][kpad]
     size_t lists_cap = 0;
@@ -339,7 +340,7 @@ extern "C" int psx_add_device(psx_index* h, const float* x_dev, int64_t n, int n
     if ((unsigned long long)(h->n + n) >= 0xffffffffull) return fail(PSX_ERR_RANGE, "more than 2^32-1 rows");
     rc = ensure_capacity(h, h->n + n, false);
     if (rc) return rc;
-    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    cudaStream_t st = (cudaStream_t)stream;
     rc = launch_pack(h, x_dev, h->n, n, normalize, st);
     if (rc) return rc;
     CU(cudaStreamSynchronize(st));
@@ -369,7 +370,7 @@ extern "C" int psx_set_attrs_device(psx_index* h, int64_t row0, const uint64_t* 
     int rc = flush_pending(h);
     if (rc) return rc;
     if (row0 + n > h->n) return fail(PSX_ERR_RANGE, "attribute rows exceed ntotal");
-    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    cudaStream_t st = (cudaStream_t)stream;
     CU(cudaMemcpyAsync(h->attrs + row0, attrs_dev, (size_t)n * sizeof(uint64_t), cudaMemcpyDeviceToDevice, st));
     CU(cudaStreamSynchronize(st));
     h->attrs_set = true;
@@ -403,7 +404,9 @@ static int plan_scan(psx_index* h, int k, ScanPlan& plan) {
         p.rpi = 1;
         p.cpr = (int)((h->row_bytes + PSX_SLOT_BYTES - 1) / PSX_SLOT_BYTES);
     }
-    const int burst = W * p.rpi;  // most keys one CTA iteration can append
+    // CTA-wide overflow checks are spaced so that a few hundred appends fit between two of them
+    p.sync_every = std::max(1, std::min(8, 256 / (W * p.rpi)));
+    const int burst = W * p.rpi * p.sync_every;  // most keys a CTA can append between two checks
     int cap = pow2ceil((long long)k + burst);
     if (cap - burst - k < std::max(burst, 64)) cap <<= 1;
     if (cap < 1024) cap = 1024;
@@ -484,12 +487,13 @@ static int launch_scan(psx_index* h, const float* q_dev, int k, const psx_filter
 
 // scratch is per index: order this search after the previous one if it ran on another stream
 static int enter_stream(psx_index* h, cudaStream_t st) {
-    if (h->last_stream && h->last_stream != st) CU(cudaStreamWaitEvent(st, h->last_ev, 0));
+    if (h->has_last && h->last_stream != st) CU(cudaStreamWaitEvent(st, h->last_ev, 0));
     return PSX_OK;
 }
 static int leave_stream(psx_index* h, cudaStream_t st) {
     CU(cudaEventRecord(h->last_ev, st));
     h->last_stream = st;
+    h->has_last = true;
     return PSX_OK;
 }
 
@@ -502,7 +506,7 @@ extern "C" int psx_search_device(psx_index* h, const float* q_dev, int64_t nq, i
     DeviceGuard g(h->device);
     int rc = flush_pending(h);
     if (rc) return rc;
-    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    cudaStream_t st = (cudaStream_t)stream;
     if ((rc = enter_stream(h, st))) return rc;
     const int64_t kpad = psx_kpad(k);
     for (int64_t qi = 0; qi < nq; ++qi) {
@@ -710,9 +714,9 @@ extern "C" int psx_set_tunable(psx_index* h, const char* key, int value) {
     if (!h || !key) return fail(PSX_ERR_INVALID, "bad arguments to psx_set_tunable");
     std::lock_guard<std::mutex> lk(h->mu);
     if (!strcmp(key, "warps")) {
-        h->warps = value <= 0 ? 8 : std::min(value, PSX_MAX_WARPS);
+        h->warps = value <= 0 ? 16 : std::min(value, PSX_MAX_WARPS);
     } else if (!strcmp(key, "stages")) {
-        h->stages = value <= 0 ? 5 : std::max(2, std::min(value, 12));
+        h->stages = value <= 0 ? 2 : std::max(2, std::min(value, 12));
     } else if (!strcmp(key, "ctas_per_sm")) {
         h->ctas_per_sm = value <= 0 ? 1 : std::min(value, 8);
     } else {

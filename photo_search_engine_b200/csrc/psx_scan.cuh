@@ -43,6 +43,7 @@ struct ScanParams {
     int cpr;        // chunks (slots) per row, > 1 only when rpi == 1
     int stages;
     int cand_cap, high_water;
+    int sync_every; // CTA-wide overflow check every this many iterations (>= 1)
     int metric;
     int has_filter;
     uint32_t id_base;
@@ -199,9 +200,13 @@ __global__ void __launch_bounds__(PSX_MAX_THREADS, 1) scan_topk_kernel(const Sca
             if (lane < rpi && row < p.n) attr_pf = __ldg(p.attrs + row);
         }
     };
-    auto issue = [&](int L) {
-        const int item_no = cpr == 1 ? L : L / cpr;
-        const int c = cpr == 1 ? 0 : L - item_no * cpr;
+    int p_item = 0, p_chunk = 0;  // next load to issue = chunk p_chunk of this warp's item p_item
+    auto issue = [&](int slot) {
+        const int item_no = p_item, c = p_chunk;
+        if (++p_chunk == cpr) {
+            p_chunk = 0;
+            ++p_item;
+        }
         const long long row0 = ((long long)item_no * Wt + gw) * rpi;
         const long long left = p.n - row0;
         const int rows = left < rpi ? (int)left : rpi;
@@ -216,7 +221,6 @@ __global__ void __launch_bounds__(PSX_MAX_THREADS, 1) scan_topk_kernel(const Sca
             }
         }
         const uint32_t mask = issue_mask;
-        const int slot = L % S;
         const uint32_t bar = bar_base + slot * 8;
         const uint32_t dst = ring_base + (uint32_t)slot * PSX_SLOT_BYTES;
         const unsigned char* src = p.x + (size_t)row0 * row_bytes;
@@ -244,10 +248,22 @@ __global__ void __launch_bounds__(PSX_MAX_THREADS, 1) scan_topk_kernel(const Sca
     };
 
     prefetch_attr(0);
-    {
-        const int pre = total_loads < S ? total_loads : S;
-        for (int L = 0; L < pre; ++L) issue(L);
-    }
+    int issued = total_loads < S ? total_loads : S;
+    for (int L = 0; L < issued; ++L) issue(L);
+    // consumer state: slot and phase parity of the next load to consume
+    int c_slot = 0;
+    uint32_t c_phase = 0;
+    auto advance = [&]() {  // slot just drained -> refill it with the next load, step the ring
+        __syncwarp();
+        if (issued < total_loads) {
+            issue(c_slot);
+            ++issued;
+        }
+        if (++c_slot == S) {
+            c_slot = 0;
+            c_phase ^= 1u;
+        }
+    };
 
     const float4* q4 = reinterpret_cast<const float4*>(sq);
     const int pieces_per_row = row_bytes >> 4;
@@ -255,17 +271,17 @@ __global__ void __launch_bounds__(PSX_MAX_THREADS, 1) scan_topk_kernel(const Sca
     (void)QP;
 
     // ---- main stream -----------------------------------------------------------------------
+    uint64_t tau = 0ull;
+    int over = 0, since_sync = 0;
     for (int it = 0; it < iters; ++it) {
-        const uint64_t tau = *s_tau;
         float myscore = 0.0f;
         uint32_t item_mask = 0;
         long long row0 = 0;
         if (it < my_items) {
             row0 = ((long long)it * Wt + gw) * rpi;
             if (cpr == 1) {
-                const int L = it;
-                const int slot = L % S;
-                mbar_wait(bar_base + slot * 8, (uint32_t)(L / S) & 1u);
+                const int slot = c_slot;
+                mbar_wait(bar_base + slot * 8, c_phase);
                 item_mask = my_masks[slot];
                 const uint4* xs = reinterpret_cast<const uint4*>(ring + ((size_t)(warp * S + slot)) * PSX_SLOT_BYTES);
                 uint32_t m = item_mask;
@@ -279,14 +295,12 @@ __global__ void __launch_bounds__(PSX_MAX_THREADS, 1) scan_topk_kernel(const Sca
                     const float s = warp_sum((a[0] + a[1]) + (a[2] + a[3]));
                     if (lane == r) myscore = s;
                 }
-                __syncwarp();
-                if (L + S < total_loads) issue(L + S);
+                advance();
             } else {
                 float a[4] = {0.f, 0.f, 0.f, 0.f};
                 for (int c = 0; c < cpr; ++c) {
-                    const int L = it * cpr + c;
-                    const int slot = L % S;
-                    mbar_wait(bar_base + slot * 8, (uint32_t)(L / S) & 1u);
+                    const int slot = c_slot;
+                    mbar_wait(bar_base + slot * 8, c_phase);
                     item_mask = my_masks[slot];
                     if (item_mask) {
                         const uint4* xs =
@@ -297,8 +311,7 @@ __global__ void __launch_bounds__(PSX_MAX_THREADS, 1) scan_topk_kernel(const Sca
 #pragma unroll 4
                         for (int pc = lane; pc < np; pc += 32) piece_fma<T, METRIC>(xs[pc], q4, piece0 + pc, a);
                     }
-                    __syncwarp();
-                    if (L + S < total_loads) issue(L + S);
+                    advance();
                 }
                 const float s = warp_sum((a[0] + a[1]) + (a[2] + a[3]));
                 if (lane == 0) myscore = s;
@@ -313,15 +326,21 @@ __global__ void __launch_bounds__(PSX_MAX_THREADS, 1) scan_topk_kernel(const Sca
             want = key > tau && key < ceil_key;
         }
         const uint32_t bal = __ballot_sync(0xffffffffu, want);
-        int pos_end = 0;
         if (bal) {
             int base = 0;
             if (lane == 0) base = atomicAdd(s_count, __popc(bal));
             base = __shfl_sync(0xffffffffu, base, 0);
             if (want) cand[base + __popc(bal & ((1u << lane) - 1u))] = key;
-            pos_end = base + __popc(bal);
+            over |= base + __popc(bal) > p.high_water;
         }
-        if (__syncthreads_or(pos_end > p.high_water)) compact_candidates(cand, s_count, s_tau, p.k);
+        // Warps run free between checks (they overlap each other's latencies); the buffer has
+        // room for sync_every iterations of appends above the high-water mark.
+        if (++since_sync == p.sync_every || it + 1 == iters) {
+            since_sync = 0;
+            if (__syncthreads_or(over)) compact_candidates(cand, s_count, s_tau, p.k);
+            over = 0;
+            tau = *s_tau;
+        }
     }
 
     // ---- publish this CTA's k best -------------------------------------------------------------
@@ -353,7 +372,7 @@ __global__ void __launch_bounds__(PSX_MAX_THREADS, 1) scan_topk_kernel(const Sca
 __global__ void __launch_bounds__(256, 1)
 merge_keys_kernel(const uint64_t* __restrict__ keys, int nlists, int k, int kpad, int cap_lists, int metric,
                   float* out_scores, long long* out_ids) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
     uint64_t* buf = reinterpret_cast<uint64_t*>(smem_raw);
     const size_t qi = blockIdx.x;
     block_merge_lists(keys + qi * (size_t)nlists * kpad, nlists, kpad, buf, cap_lists);
