@@ -301,34 +301,38 @@ def run_ours(args):
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_qps = args.steps / float(te[0])
 
-    # ---- CPU baseline beside it (rank 0, N=1 only): a bounded sample of the same rows ---------------
+    # ---- parity spot check at every N: the sharded GPU result, restricted by a fused row-range
+    # predicate to the first `sample_rows` rows, must equal the CPU oracle on those rows ----------
     cpu = None
     parity = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline and args.store == "fp32":
-        from oracle import c_oracle
-
-        cores = c_oracle.max_threads()
-        sample_rows = min(rows, 1 << 20)
-        x_host = index.read_rows(0, sample_rows)
-        times_all = cpu_time_queries(x_host, queries_host, k, cores, 12.0, 40)
-        times_one = cpu_time_queries(x_host, queries_host, k, 1, 8.0, 8)
-        scale = rows / sample_rows
-        med_all, med_one = statistics.median(times_all), statistics.median(times_one)
-        cpu = {"value": 1.0 / (med_all * scale), "unit": "queries/s", "cores": cores, "kind": "port",
-               "sample": (f"first {sample_rows} of {rows} rows (same bits as the GPU corpus), {len(times_all)} queries, median, "
-                          f"time scaled linearly x{scale:.2f}; oracle/flat_scan.c = FAISS IndexFlatIP small-batch path restated "
-                          f"(FAISS is not installable here), rows split over {cores} threads"),
-               "single_thread_value": 1.0 / (med_one * scale),
-               "single_thread_note": "what FAISS does for nq=1 (it parallelises over queries only)"}
-        # parity spot check on the sample: GPU (restricted by a row-range predicate) vs the C oracle
-        words = torch.arange(rows, device=device, dtype=torch.int64) + 1
-        index.set_attrs_device(0, words.data_ptr(), rows)
+    sample_rows = min(rows, 1 << 20, bounds[1])
+    if args.store == "fp32" and not args.no_cpu_baseline:
+        words = torch.arange(lo, hi, device=device, dtype=torch.int64) + 1  # dt = 1 + global row
+        index.set_attrs_device(0, words.data_ptr(), hi - lo, stream=torch.cuda.current_stream().cuda_stream)
+        del words
         flt = _native.PsxFilter(flags=_native.F_NEED_DT | _native.F_END, end=sample_rows)
-        Dg, Ig = index.search(queries_host[:4], k, flt)
-        Dc, Ic = c_oracle.search(x_host, queries_host[:4], k, nthreads=cores)
-        parity = {"ids_equal_frac": float((Ig == Ic).mean()),
-                  "max_rel_score_err": float(np.max(np.abs(Dg - Dc) / np.maximum(np.abs(Dc), 1e-6)))}
-        del x_host
+        Dg, Ig = sharded.search(queries_host[:4], k, flt)
+        if rank == 0:
+            from oracle import c_oracle
+
+            cores = c_oracle.max_threads()
+            x_host = index.read_rows(0, sample_rows)
+            Dc, Ic = c_oracle.search(x_host, queries_host[:4], k, nthreads=cores)
+            parity = {"rows": sample_rows, "queries": 4, "ids_equal_frac": float((Ig == Ic).mean()),
+                      "max_rel_score_err": float(np.max(np.abs(Dg - Dc) / np.maximum(np.abs(Dc), 1e-6)))}
+            # ---- CPU baseline beside it (rank 0, N=1 only): a bounded sample of the same rows -------
+            if world == 1:
+                times_all = cpu_time_queries(x_host, queries_host, k, cores, 12.0, 40)
+                times_one = cpu_time_queries(x_host, queries_host, k, 1, 8.0, 8)
+                scale = rows / sample_rows
+                med_all, med_one = statistics.median(times_all), statistics.median(times_one)
+                cpu = {"value": 1.0 / (med_all * scale), "unit": "queries/s", "cores": cores, "kind": "port",
+                       "sample": (f"first {sample_rows} of {rows} rows (same bits as the GPU corpus), {len(times_all)} queries, "
+                                  f"median, time scaled linearly x{scale:.2f}; oracle/flat_scan.c = FAISS IndexFlatIP small-batch "
+                                  f"path restated (FAISS is not installable here), rows split over {cores} threads"),
+                       "single_thread_value": 1.0 / (med_one * scale),
+                       "single_thread_note": "what FAISS does for nq=1 (it parallelises over queries only)"}
+            del x_host
 
     # ---- secondary configurations (not bench lines: context for the judge) -------------------------
     extras = {}

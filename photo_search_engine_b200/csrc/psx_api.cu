@@ -148,13 +148,7 @@ extern "C" int psx_create(int d, int metric, int store_dtype, int device, psx_in
         CU(cudaEventCreateWithFlags(&h->last_ev, cudaEventDisableTiming));
         CU(cudaMalloc(&h->counter, sizeof(unsigned int)));
         CU(cudaMemset(h->counter, 0, sizeof(unsigned int)));
-        int r;
-        if ((r = set_max_smem(scan_topk_kernel<float, PSX_METRIC_IP>))) return r;
-        if ((r = set_max_smem(scan_topk_kernel<float, PSX_METRIC_L2>))) return r;
-        if ((r = set_max_smem(scan_topk_kernel<__nv_bfloat16, PSX_METRIC_IP>))) return r;
-        if ((r = set_max_smem(scan_topk_kernel<__nv_bfloat16, PSX_METRIC_L2>))) return r;
-        if ((r = set_max_smem(merge_keys_kernel))) return r;
-        return PSX_OK;
+        return set_max_smem(merge_keys_kernel);
     };
     rc = init();
     if (rc != PSX_OK) {
@@ -398,15 +392,16 @@ static int plan_scan(psx_index* h, int k, ScanPlan& plan) {
     p.kpad = (int)psx_kpad(k);
     p.metric = h->metric;
     if (h->row_bytes <= PSX_SLOT_BYTES) {
-        p.rpi = (int)std::min<size_t>(32, PSX_SLOT_BYTES / h->row_bytes);
+        p.rps = (int)std::min<size_t>(32, PSX_SLOT_BYTES / h->row_bytes);
         p.cpr = 1;
     } else {
-        p.rpi = 1;
+        p.rps = 1;
         p.cpr = (int)((h->row_bytes + PSX_SLOT_BYTES - 1) / PSX_SLOT_BYTES);
     }
+    p.gsize = p.rps * (32 / p.rps);
     // CTA-wide overflow checks are spaced so that a few hundred appends fit between two of them
-    p.sync_every = std::max(1, std::min(8, 256 / (W * p.rpi)));
-    const int burst = W * p.rpi * p.sync_every;  // most keys a CTA can append between two checks
+    p.sync_every = std::max(1, std::min(8, 256 / (W * p.rps)));
+    const int burst = W * p.rps * p.sync_every;  // most keys a CTA can append between two checks
     int cap = pow2ceil((long long)k + burst);
     if (cap - burst - k < std::max(burst, 64)) cap <<= 1;
     if (cap < 1024) cap = 1024;
@@ -415,7 +410,7 @@ static int plan_scan(psx_index* h, int k, ScanPlan& plan) {
     const int qpad = (h->ld + 7) & ~7;
     auto smem_for = [&](int S) {
         return (size_t)W * S * PSX_SLOT_BYTES + (size_t)qpad * 4 + (size_t)cap * 8 + (size_t)W * S * 8 + 8 +
-               (size_t)W * S * 4 + 16;
+               (size_t)W * S * 8 + 16;
     };
     // co-resident CTAs share the SM's 228 KB (1 KB per CTA is reserved by the driver)
     const size_t limit = h->ctas_per_sm <= 1 ? (size_t)PSX_SMEM_LIMIT : (size_t)(228 * 1024) / h->ctas_per_sm - 1024;
@@ -427,14 +422,50 @@ static int plan_scan(psx_index* h, int k, ScanPlan& plan) {
         return fail(PSX_ERR_INVALID, "d=%d k=%d does not fit the shared-memory plan", h->d, k);
     p.stages = S;
     plan.smem = smem_for(S);
-    const long long num_items = (h->n + p.rpi - 1) / p.rpi;
-    long long grid = (num_items + W - 1) / W;
+    const long long num_groups = (h->n + p.gsize - 1) / p.gsize;
+    long long grid = (num_groups + W - 1) / W;
     const long long maxgrid = (long long)h->sm_count * h->ctas_per_sm;
     if (grid > maxgrid) grid = maxgrid;
     if (grid < 1) grid = 1;
     plan.grid = (int)grid;
     plan.block = W * 32;
     return PSX_OK;
+}
+
+template <typename T, int METRIC, int PPL, bool QREG>
+static int launch_one(int device, const ScanPlan& plan, cudaStream_t st) {
+    static std::atomic<bool> ready[64];
+    if (device >= 0 && device < 64 && !ready[device].load()) {
+        CU(cudaFuncSetAttribute(scan_topk_kernel<T, METRIC, PPL, QREG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                PSX_SMEM_LIMIT));
+        ready[device].store(true);
+    }
+    scan_topk_kernel<T, METRIC, PPL, QREG><<<plan.grid, plan.block, plan.smem, st>>>(plan.p);
+    return PSX_OK;
+}
+template <typename T, int METRIC>
+static int launch_by_shape(int device, int ppl, bool qreg, const ScanPlan& plan, cudaStream_t st) {
+    if (qreg) {
+        switch (ppl) {
+            case 1: return launch_one<T, METRIC, 1, true>(device, plan, st);
+            case 2: return launch_one<T, METRIC, 2, true>(device, plan, st);
+            case 3: return launch_one<T, METRIC, 3, true>(device, plan, st);
+            case 4: return launch_one<T, METRIC, 4, true>(device, plan, st);
+            case 6: return launch_one<T, METRIC, 6, true>(device, plan, st);
+            case 8: return launch_one<T, METRIC, 8, true>(device, plan, st);
+            default: break;
+        }
+    } else if (ppl == 8) {
+        return launch_one<T, METRIC, 8, false>(device, plan, st);
+    }
+    return launch_one<T, METRIC, 0, false>(device, plan, st);
+}
+static int launch_scan_variant(int device, int dtype, int metric, int ppl, bool qreg, const ScanPlan& plan, cudaStream_t st) {
+    if (dtype == PSX_STORE_F32)
+        return metric == PSX_METRIC_IP ? launch_by_shape<float, PSX_METRIC_IP>(device, ppl, qreg, plan, st)
+                                       : launch_by_shape<float, PSX_METRIC_L2>(device, ppl, qreg, plan, st);
+    return metric == PSX_METRIC_IP ? launch_by_shape<__nv_bfloat16, PSX_METRIC_IP>(device, ppl, qreg, plan, st)
+                                   : launch_by_shape<__nv_bfloat16, PSX_METRIC_L2>(device, ppl, qreg, plan, st);
 }
 
 static int launch_scan(psx_index* h, const float* q_dev, int k, const psx_filter* f, uint32_t id_base,
@@ -469,17 +500,18 @@ static int launch_scan(psx_index* h, const float* q_dev, int k, const psx_filter
         p.attrs = h->attrs;
         p.f = *f;
     }
-    if (h->dtype == PSX_STORE_F32) {
-        if (h->metric == PSX_METRIC_IP)
-            scan_topk_kernel<float, PSX_METRIC_IP><<<plan.grid, plan.block, plan.smem, st>>>(p);
-        else
-            scan_topk_kernel<float, PSX_METRIC_L2><<<plan.grid, plan.block, plan.smem, st>>>(p);
-    } else {
-        if (h->metric == PSX_METRIC_IP)
-            scan_topk_kernel<__nv_bfloat16, PSX_METRIC_IP><<<plan.grid, plan.block, plan.smem, st>>>(p);
-        else
-            scan_topk_kernel<__nv_bfloat16, PSX_METRIC_L2><<<plan.grid, plan.block, plan.smem, st>>>(p);
+    const int ppr = (int)(h->row_bytes >> 4);  // 16-byte pieces per row
+    int ppl = 0;
+    bool qreg = false;
+    if (p.cpr == 1 && ppr % 32 == 0) {
+        ppl = ppr / 32;
+        qreg = true;
+        if (ppl == 5 || ppl == 7) ppl = 0, qreg = false;
+    } else if (p.cpr > 1 && h->row_bytes % PSX_SLOT_BYTES == 0) {
+        ppl = 8;
     }
+    rc = launch_scan_variant(h->device, h->dtype, h->metric, ppl, qreg, plan, st);
+    if (rc) return rc;
     g_launches++;
     CU(cudaGetLastError());
     return PSX_OK;

@@ -1,12 +1,15 @@
 // psx_scan.cuh -- K1 (streaming exact scan + per-CTA top-k) and K2 (cross-CTA merge), fused in
 // one launch.  Replaces FAISS IndexFlat::search for small nq (utils/vector_store.py:191).
 //
-// Data movement.  Every consumer warp owns a private ring of `stages` shared-memory slots of
-// PSX_SLOT_BYTES.  Lane 0 arms the slot's mbarrier with the byte count and issues one
-// cp.async.bulk (TMA 1-D) per slot -- or, when the EXIF predicate rejects some rows of a
-// multi-row slot, one bulk copy per surviving row -- so rejected rows never leave HBM.  The
-// warp then waits on the mbarrier, reads the slot with conflict-free 128-bit LDS, and refills
-// the slot it just drained.  With W warps x S stages x 4 KB per SM, ~24 MB is in flight
+// Data movement.  Rows are dealt to warps in groups of up to 32 consecutive rows.  Every warp owns
+// a private ring of `stages` shared-memory slots of PSX_SLOT_BYTES; a slot receives one window
+// (as many consecutive rows as fit, or one 4 KB chunk of a longer row).  For each group the 32
+// lanes evaluate the EXIF predicate on the packed attribute words (one coalesced load, prefetched
+// two groups ahead) and ballot; windows with no passing row are skipped without touching the
+// ring, partially passing windows get one bulk copy per surviving row -- rejected rows never
+// leave HBM.  Lane 0 arms the slot's mbarrier with the byte count and issues cp.async.bulk
+// (TMA 1-D); the warp waits on the mbarrier, reads the slot with conflict-free 128-bit LDS and
+// refills the slot it just drained.  With W warps x S stages x 4 KB per SM, ~19 MB is in flight
 // chip-wide, several times bandwidth x latency.
 //
 // Arithmetic.  fp32 FMA; every row uses the same reduction tree (4 lane-local accumulators
@@ -39,11 +42,12 @@ struct ScanParams {
     int ld;         // elements per stored row (zero padded, row_bytes % 16 == 0)
     int row_bytes;
     int k, kpad;
-    int rpi;        // rows per item   (item = what one warp consumes between two CTA barriers)
-    int cpr;        // chunks (slots) per row, > 1 only when rpi == 1
+    int rps;        // rows per slot (window), <= 32
+    int gsize;      // rows per group = rps * (32 / rps): one predicate ballot per group
+    int cpr;        // chunks (slots) per row, > 1 only when rps == 1
     int stages;
     int cand_cap, high_water;
-    int sync_every; // CTA-wide overflow check every this many iterations (>= 1)
+    int sync_every; // CTA-wide overflow check every this many slots per warp (>= 1)
     int metric;
     int has_filter;
     uint32_t id_base;
@@ -129,11 +133,11 @@ __device__ __forceinline__ float warp_sum(float v) {
 }
 
 // Sort the candidate buffer, keep the k best, raise tau.  Block-wide.
-__device__ __forceinline__ void compact_candidates(uint64_t* cand, int* s_count, uint64_t* s_tau, int k) {
+__device__ __forceinline__ void compact_candidates(uint64_t* cand, int* s_count, uint64_t* s_tau, int* s_over, int k) {
     const int n = *s_count;
     int np = 2;
     while (np < n) np <<= 1;
-    __syncthreads();  // everyone has read n
+    __syncthreads();  // everyone has read n (and s_over)
     for (int i = n + threadIdx.x; i < np; i += blockDim.x) cand[i] = 0ull;
     __syncthreads();
     block_bitonic_sort_desc(cand, np);
@@ -142,11 +146,57 @@ __device__ __forceinline__ void compact_candidates(uint64_t* cand, int* s_count,
             *s_tau = cand[k - 1];
             *s_count = k;
         }
+        *s_over = 0;
     }
     __syncthreads();
 }
 
-template <typename T, int METRIC>
+// One stored row (or one chunk of a long row) against the query.
+//   PPL > 0 : the row/chunk is exactly PPL*32 16-byte pieces, fully unrolled;
+//             QREG: the query lives in registers (rows that fit one slot), else in shared memory.
+//   PPL == 0: generic strided loop, query in shared memory.
+template <typename T, int METRIC, int PPL, bool QREG>
+struct RowDot {
+    static constexpr int QF4 = (sizeof(T) == 4 ? 1 : 2) * (PPL > 0 ? PPL : 1);
+    float4 qreg[QREG ? QF4 : 1];
+
+    __device__ __forceinline__ void load_query(const float4* __restrict__ q4, int lane) {
+        if constexpr (QREG) {
+#pragma unroll
+            for (int t = 0; t < PPL; ++t) {
+                if constexpr (sizeof(T) == 4) {
+                    qreg[t] = q4[lane + 32 * t];
+                } else {
+                    qreg[2 * t] = q4[2 * (lane + 32 * t)];
+                    qreg[2 * t + 1] = q4[2 * (lane + 32 * t) + 1];
+                }
+            }
+        }
+    }
+    // xs: first piece of the row/chunk in shared memory; piece0: index of that piece in the row;
+    // npieces: pieces in this row/chunk (ignored when PPL > 0)
+    __device__ __forceinline__ void accumulate(const uint4* __restrict__ xs, const float4* __restrict__ q4, int piece0,
+                                               int npieces, int lane, float (&a)[4]) const {
+        if constexpr (PPL > 0) {
+            uint4 v[PPL];
+#pragma unroll
+            for (int t = 0; t < PPL; ++t) v[t] = xs[lane + 32 * t];
+#pragma unroll
+            for (int t = 0; t < PPL; ++t) {
+                if constexpr (QREG) {
+                    piece_fma<T, METRIC>(v[t], qreg, t, a);
+                } else {
+                    piece_fma<T, METRIC>(v[t], q4, piece0 + lane + 32 * t, a);
+                }
+            }
+        } else {
+#pragma unroll 4
+            for (int pc = lane; pc < npieces; pc += 32) piece_fma<T, METRIC>(xs[pc], q4, piece0 + pc, a);
+        }
+    }
+};
+
+template <typename T, int METRIC, int PPL, bool QREG>
 __global__ void __launch_bounds__(PSX_MAX_THREADS, 1) scan_topk_kernel(const ScanParams p) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     const int W = blockDim.x >> 5;
@@ -161,8 +211,10 @@ __global__ void __launch_bounds__(PSX_MAX_THREADS, 1) scan_topk_kernel(const Sca
     uint64_t* bars = cand + p.cand_cap;
     uint64_t* s_tau = bars + W * S;
     uint32_t* masks = reinterpret_cast<uint32_t*>(s_tau + 1);
-    int* s_count = reinterpret_cast<int*>(masks + W * S);
+    uint32_t* row0s = masks + W * S;
+    int* s_count = reinterpret_cast<int*>(row0s + W * S);
     int* s_flag = s_count + 1;
+    int* s_over = s_count + 2;
 
     // ---- prologue ------------------------------------------------------------------------
     for (int i = threadIdx.x; i < qpad; i += blockDim.x) sq[i] = i < p.d ? p.q[i] : 0.0f;
@@ -170,6 +222,7 @@ __global__ void __launch_bounds__(PSX_MAX_THREADS, 1) scan_topk_kernel(const Sca
         *s_tau = 0ull;
         *s_count = 0;
         *s_flag = 0;
+        *s_over = 0;
     }
     if (lane == 0) {
         for (int s = 0; s < S; ++s) mbar_init(smem_u32(bars + warp * S + s), 1);
@@ -178,173 +231,184 @@ __global__ void __launch_bounds__(PSX_MAX_THREADS, 1) scan_topk_kernel(const Sca
     __syncthreads();
 
     const uint64_t ceil_key = p.ceil_ptr ? *p.ceil_ptr : ~0ull;
-    const int rpi = p.rpi, cpr = p.cpr, row_bytes = p.row_bytes;
-    const long long num_items = (p.n + rpi - 1) / rpi;
+    const int R = p.rps, G = p.gsize, cpr = p.cpr, row_bytes = p.row_bytes;
+    const uint32_t rmask = R >= 32 ? 0xffffffffu : ((1u << R) - 1u);
+    const long long num_groups = (p.n + G - 1) / G;
     const long long Wt = (long long)gridDim.x * W;
     const long long gw = (long long)blockIdx.x * W + warp;
-    const int iters = (int)((num_items + Wt - 1) / Wt);
-    const int my_items = num_items > gw ? (int)((num_items - gw + Wt - 1) / Wt) : 0;
-    const int total_loads = my_items * cpr;
 
     const uint32_t ring_base = smem_u32(ring) + (uint32_t)(warp * S) * PSX_SLOT_BYTES;
     const uint32_t bar_base = smem_u32(bars + warp * S);
     uint32_t* my_masks = masks + warp * S;
+    uint32_t* my_row0s = row0s + warp * S;
+    const float4* q4 = reinterpret_cast<const float4*>(sq);
+    RowDot<T, METRIC, PPL, QREG> dot;
+    dot.load_query(q4, lane);
 
-    // producer state: attribute word of the next item to be issued (prefetched one item ahead)
-    uint64_t attr_pf = 0;
-    uint32_t issue_mask = 0;
-    auto prefetch_attr = [&](int item_no) {
-        attr_pf = 0;
-        if (p.has_filter && item_no < my_items) {
-            const long long row = ((long long)item_no * Wt + gw) * rpi + lane;
-            if (lane < rpi && row < p.n) attr_pf = __ldg(p.attrs + row);
-        }
+    // ---- producer: walks this warp's row groups, skips windows the predicate empties -----------
+    long long g_next = gw;   // next group to open
+    long long g_row0 = 0;    // first row of the open group
+    uint32_t g_mask = 0;     // rows of the open group still to be streamed (bit i = row g_row0 + i)
+    uint32_t cur_mask = 0;   // window being streamed (bit r = row cur_row0 + r)
+    long long cur_row0 = 0;
+    int p_chunk = 0;         // long rows: next chunk of the current row
+    bool p_exhausted = false;
+    int in_flight = 0;
+    uint64_t attr_a = 0, attr_b = 0;  // attribute words of the next two groups (prefetched)
+    auto load_attr = [&](long long g) -> uint64_t {
+        const long long row = g * G + lane;
+        return (p.has_filter && g < num_groups && lane < G && row < p.n) ? __ldg(p.attrs + row) : 0ull;
     };
-    int p_item = 0, p_chunk = 0;  // next load to issue = chunk p_chunk of this warp's item p_item
-    auto issue = [&](int slot) {
-        const int item_no = p_item, c = p_chunk;
-        if (++p_chunk == cpr) {
-            p_chunk = 0;
-            ++p_item;
+    attr_a = load_attr(g_next);
+    attr_b = load_attr(g_next + Wt);
+    auto open_group = [&]() -> bool {
+        if (g_next >= num_groups) {
+            p_exhausted = true;
+            return false;
         }
-        const long long row0 = ((long long)item_no * Wt + gw) * rpi;
-        const long long left = p.n - row0;
-        const int rows = left < rpi ? (int)left : rpi;
-        const uint32_t full = rows >= 32 ? 0xffffffffu : ((1u << rows) - 1u);
-        if (c == 0) {
-            if (p.has_filter) {
-                const bool ok = lane < rows && attr_pass(attr_pf, p.f);
-                issue_mask = __ballot_sync(0xffffffffu, ok);
-                prefetch_attr(item_no + 1);
-            } else {
-                issue_mask = full;
+        g_row0 = g_next * G;
+        const long long left = p.n - g_row0;
+        const int rows = left < G ? (int)left : G;
+        if (p.has_filter) {
+            g_mask = __ballot_sync(0xffffffffu, lane < rows && attr_pass(attr_a, p.f));
+            attr_a = attr_b;
+            attr_b = load_attr(g_next + 2 * Wt);
+        } else {
+            g_mask = rows >= 32 ? 0xffffffffu : ((1u << rows) - 1u);
+        }
+        g_next += Wt;
+        return true;
+    };
+    // Fill `slot` with the next window (or the next chunk of a long row).  false = stream exhausted.
+    auto produce = [&](int slot) -> bool {
+        if (p_chunk == 0) {
+            while (g_mask == 0) {
+                if (!open_group()) return false;
             }
+            const int b = __ffs(g_mask) - 1;
+            const int w = R == 1 ? b : b / R;
+            cur_mask = (g_mask >> (w * R)) & rmask;
+            g_mask &= ~(rmask << (w * R));
+            cur_row0 = g_row0 + (long long)w * R;
         }
-        const uint32_t mask = issue_mask;
+        const uint32_t mask = cur_mask;
         const uint32_t bar = bar_base + slot * 8;
         const uint32_t dst = ring_base + (uint32_t)slot * PSX_SLOT_BYTES;
-        const unsigned char* src = p.x + (size_t)row0 * row_bytes;
-        if (lane == 0) my_masks[slot] = mask;
-        if (mask == 0) {
-            if (lane == 0) mbar_arrive(bar);
-        } else if (cpr > 1) {
-            const int off = c * PSX_SLOT_BYTES;
+        const unsigned char* src = p.x + (size_t)cur_row0 * row_bytes;
+        if (lane == 0) {
+            my_masks[slot] = mask;
+            my_row0s[slot] = (uint32_t)cur_row0;
+        }
+        if (cpr > 1) {
+            const int off = p_chunk * PSX_SLOT_BYTES;
             const int bytes = row_bytes - off < PSX_SLOT_BYTES ? row_bytes - off : PSX_SLOT_BYTES;
             if (lane == 0) {
                 mbar_arrive_expect_tx(bar, bytes);
                 bulk_g2s(dst, src + off, bytes, bar);
             }
-        } else if (mask == full) {
-            if (lane == 0) {
-                mbar_arrive_expect_tx(bar, rows * row_bytes);
-                bulk_g2s(dst, src, rows * row_bytes, bar);
-            }
+            if (++p_chunk == cpr) p_chunk = 0;
         } else {
-            if (lane == 0) mbar_arrive_expect_tx(bar, __popc(mask) * row_bytes);
-            __syncwarp();
-            if ((mask >> lane) & 1u) bulk_g2s(dst + lane * row_bytes, src + (size_t)lane * row_bytes, row_bytes, bar);
+            const int hi = 32 - __clz(mask);  // rows [0, hi) of the window, all passing <=> one copy
+            if (mask == (hi >= 32 ? 0xffffffffu : ((1u << hi) - 1u))) {
+                if (lane == 0) {
+                    mbar_arrive_expect_tx(bar, hi * row_bytes);
+                    bulk_g2s(dst, src, hi * row_bytes, bar);
+                }
+            } else {
+                if (lane == 0) mbar_arrive_expect_tx(bar, __popc(mask) * row_bytes);
+                __syncwarp();
+                if ((mask >> lane) & 1u) bulk_g2s(dst + lane * row_bytes, src + (size_t)lane * row_bytes, row_bytes, bar);
+            }
         }
         __syncwarp();
+        return true;
     };
+    for (int s = 0; s < S; ++s) {
+        if (!produce(s)) break;
+        ++in_flight;
+    }
 
-    prefetch_attr(0);
-    int issued = total_loads < S ? total_loads : S;
-    for (int L = 0; L < issued; ++L) issue(L);
-    // consumer state: slot and phase parity of the next load to consume
+    // ---- consumer ------------------------------------------------------------------------------
     int c_slot = 0;
     uint32_t c_phase = 0;
-    auto advance = [&]() {  // slot just drained -> refill it with the next load, step the ring
+    auto advance = [&]() {  // slot drained -> refill it with the next window, step the ring
         __syncwarp();
-        if (issued < total_loads) {
-            issue(c_slot);
-            ++issued;
-        }
+        --in_flight;
+        if (!p_exhausted && produce(c_slot)) ++in_flight;
         if (++c_slot == S) {
             c_slot = 0;
             c_phase ^= 1u;
         }
     };
-
-    const float4* q4 = reinterpret_cast<const float4*>(sq);
     const int pieces_per_row = row_bytes >> 4;
-    constexpr int QP = sizeof(T) == 4 ? 1 : 2;  // float4 of q per 16-byte piece (documented only)
-    (void)QP;
-
-    // ---- main stream -----------------------------------------------------------------------
+    constexpr int SLOT_PIECES = PSX_SLOT_BYTES >> 4;
     uint64_t tau = 0ull;
-    int over = 0, since_sync = 0;
-    for (int it = 0; it < iters; ++it) {
-        float myscore = 0.0f;
-        uint32_t item_mask = 0;
-        long long row0 = 0;
-        if (it < my_items) {
-            row0 = ((long long)it * Wt + gw) * rpi;
+    int over = 0;
+    float a[4] = {0.f, 0.f, 0.f, 0.f};  // long rows: carried across the chunks of a row
+    int c_chunk = 0;
+    for (;;) {
+        for (int m = 0; m < p.sync_every && in_flight > 0; ++m) {
+            const int slot = c_slot;
+            mbar_wait(bar_base + slot * 8, c_phase);
+            const uint32_t mask = my_masks[slot];
+            const uint32_t row0 = my_row0s[slot];
+            const uint4* xs = reinterpret_cast<const uint4*>(ring + ((size_t)(warp * S + slot)) * PSX_SLOT_BYTES);
+            float myscore = 0.0f;
+            bool row_done = true;
             if (cpr == 1) {
-                const int slot = c_slot;
-                mbar_wait(bar_base + slot * 8, c_phase);
-                item_mask = my_masks[slot];
-                const uint4* xs = reinterpret_cast<const uint4*>(ring + ((size_t)(warp * S + slot)) * PSX_SLOT_BYTES);
-                uint32_t m = item_mask;
-                while (m) {
-                    const int r = __ffs(m) - 1;
-                    m &= m - 1;
-                    const uint4* xr = xs + (size_t)r * pieces_per_row;
-                    float a[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll 4
-                    for (int pc = lane; pc < pieces_per_row; pc += 32) piece_fma<T, METRIC>(xr[pc], q4, pc, a);
-                    const float s = warp_sum((a[0] + a[1]) + (a[2] + a[3]));
+                uint32_t mm = mask;
+                while (mm) {
+                    const int r = __ffs(mm) - 1;
+                    mm &= mm - 1;
+                    float b[4] = {0.f, 0.f, 0.f, 0.f};
+                    dot.accumulate(xs + (size_t)r * pieces_per_row, q4, 0, pieces_per_row, lane, b);
+                    const float s = warp_sum((b[0] + b[1]) + (b[2] + b[3]));
                     if (lane == r) myscore = s;
                 }
-                advance();
             } else {
-                float a[4] = {0.f, 0.f, 0.f, 0.f};
-                for (int c = 0; c < cpr; ++c) {
-                    const int slot = c_slot;
-                    mbar_wait(bar_base + slot * 8, c_phase);
-                    item_mask = my_masks[slot];
-                    if (item_mask) {
-                        const uint4* xs =
-                            reinterpret_cast<const uint4*>(ring + ((size_t)(warp * S + slot)) * PSX_SLOT_BYTES);
-                        const int piece0 = c * (PSX_SLOT_BYTES >> 4);
-                        int np = pieces_per_row - piece0;
-                        if (np > (PSX_SLOT_BYTES >> 4)) np = PSX_SLOT_BYTES >> 4;
-#pragma unroll 4
-                        for (int pc = lane; pc < np; pc += 32) piece_fma<T, METRIC>(xs[pc], q4, piece0 + pc, a);
-                    }
-                    advance();
+                const int piece0 = c_chunk * SLOT_PIECES;
+                int np = pieces_per_row - piece0;
+                if (np > SLOT_PIECES) np = SLOT_PIECES;
+                dot.accumulate(xs, q4, piece0, np, lane, a);
+                if (++c_chunk == cpr) {
+                    c_chunk = 0;
+                    myscore = warp_sum((a[0] + a[1]) + (a[2] + a[3]));
+                    a[0] = a[1] = a[2] = a[3] = 0.f;
+                } else {
+                    row_done = false;
                 }
-                const float s = warp_sum((a[0] + a[1]) + (a[2] + a[3]));
-                if (lane == 0) myscore = s;
+            }
+            advance();
+            if (!row_done) continue;
+            // ---- push survivors --------------------------------------------------------------
+            bool want = false;
+            uint64_t key = 0;
+            if ((mask >> lane) & 1u) {
+                const float s = METRIC == PSX_METRIC_L2 ? -myscore : myscore;
+                key = make_key(s, p.id_base + row0 + (uint32_t)lane);
+                want = key > tau && key < ceil_key;
+            }
+            const uint32_t bal = __ballot_sync(0xffffffffu, want);
+            if (bal) {
+                int base = 0;
+                if (lane == 0) base = atomicAdd(s_count, __popc(bal));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (want) cand[base + __popc(bal & ((1u << lane) - 1u))] = key;
+                over |= base + __popc(bal) > p.high_water;
             }
         }
-        // ---- push survivors ------------------------------------------------------------
-        bool want = false;
-        uint64_t key = 0;
-        if ((item_mask >> lane) & 1u) {
-            const float s = METRIC == PSX_METRIC_L2 ? -myscore : myscore;
-            key = make_key(s, p.id_base + (uint32_t)(row0 + lane));
-            want = key > tau && key < ceil_key;
-        }
-        const uint32_t bal = __ballot_sync(0xffffffffu, want);
-        if (bal) {
-            int base = 0;
-            if (lane == 0) base = atomicAdd(s_count, __popc(bal));
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if (want) cand[base + __popc(bal & ((1u << lane) - 1u))] = key;
-            over |= base + __popc(bal) > p.high_water;
-        }
         // Warps run free between checks (they overlap each other's latencies); the buffer has
-        // room for sync_every iterations of appends above the high-water mark.
-        if (++since_sync == p.sync_every || it + 1 == iters) {
-            since_sync = 0;
-            if (__syncthreads_or(over)) compact_candidates(cand, s_count, s_tau, p.k);
-            over = 0;
-            tau = *s_tau;
-        }
+        // room for sync_every slots of appends per warp above the high-water mark.
+        if (over) *s_over = 1;
+        over = 0;
+        const int alive = __syncthreads_count(in_flight > 0);
+        if (*s_over) compact_candidates(cand, s_count, s_tau, s_over, p.k);
+        tau = *s_tau;
+        if (!alive) break;
     }
 
     // ---- publish this CTA's k best -------------------------------------------------------------
-    compact_candidates(cand, s_count, s_tau, p.k);
+    compact_candidates(cand, s_count, s_tau, s_over, p.k);
     {
         const int cnt = *s_count < p.k ? *s_count : p.k;
         uint64_t* mine = p.lists + (size_t)blockIdx.x * p.kpad;

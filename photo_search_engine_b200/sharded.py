@@ -81,6 +81,11 @@ class ShardedIndex:
             b["mine"].copy_(self._local_search(q_dev, k, self.row0, flt))
         else:
             stream = t.cuda.current_stream(self.device).cuda_stream
+            if self.world == 1 and self._merge is None:
+                # one shard: the scan's fused cross-CTA merge already emits the final result
+                self.local.search_device(q_dev.data_ptr(), nq, k, b["scores"].data_ptr(), b["ids"].data_ptr(), 0,
+                                         flt=flt, id_base=self.row0, stream=stream)
+                return b["scores"], b["ids"]
             self.local.search_device(q_dev.data_ptr(), nq, k, 0, 0, b["mine"].data_ptr(), flt=flt,
                                      id_base=self.row0, stream=stream)
         if self.world > 1:
