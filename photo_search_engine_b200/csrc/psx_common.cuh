@@ -92,6 +92,7 @@ __device__ __forceinline__ void block_bitonic_sort_desc(uint64_t* buf, int n) {
     const int tid = threadIdx.x, nt = blockDim.x;
     for (int size = 2; size <= n; size <<= 1) {
         for (int stride = size >> 1; stride > 0; stride >>= 1) {
+#pragma unroll 4
             for (int t = tid; t < (n >> 1); t += nt) {
                 const int i = ((t & ~(stride - 1)) << 1) | (t & (stride - 1));
                 const int j = i | stride;
@@ -115,6 +116,7 @@ __device__ __forceinline__ void block_merge_lists(const uint64_t* __restrict__ s
                                                   int cap_lists) {
     const int tid = threadIdx.x, nt = blockDim.x;
     const int half = kp >> 1;
+    const int lg = 31 - __clz(kp);  // kp is a power of two
     bool have_acc = false;
     int pos = 0;
     while (pos < L) {
@@ -128,8 +130,9 @@ __device__ __forceinline__ void block_merge_lists(const uint64_t* __restrict__ s
             // pairs (a = p*2*stride, b = a + stride) with b < m
             const int npairs = (m - stride + 2 * stride - 1) / (2 * stride);
             // half-cleaner across the pair: the kp largest of A u B, as a bitonic sequence in A
+#pragma unroll 4
             for (int w = tid; w < npairs * kp; w += nt) {
-                const int p = w / kp, i = w - p * kp;
+                const int p = w >> lg, i = w & (kp - 1);
                 uint64_t* A = buf + (size_t)(p * 2 * stride) * kp;
                 const uint64_t* B = A + (size_t)stride * kp;
                 const uint64_t x = A[i], y = B[kp - 1 - i];
@@ -137,8 +140,9 @@ __device__ __forceinline__ void block_merge_lists(const uint64_t* __restrict__ s
             }
             __syncthreads();
             for (int j = half; j >= 1; j >>= 1) {
+#pragma unroll 4
                 for (int w = tid; w < npairs * half; w += nt) {
-                    const int p = w / half, t = w - p * half;
+                    const int p = w >> (lg - 1), t = w & (half - 1);
                     uint64_t* A = buf + (size_t)(p * 2 * stride) * kp;
                     const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
                     const uint64_t a = A[i], b = A[i | j];
@@ -153,6 +157,45 @@ __device__ __forceinline__ void block_merge_lists(const uint64_t* __restrict__ s
         have_acc = true;
         pos += nb;
     }
+}
+
+// Exact top-k of `L` descending lists WITHOUT merging them all: gather only the first m keys of
+// every list, sort those, and accept the result once no list's last gathered key still beats the
+// k-th gathered key (every deeper key of a list is smaller than its last gathered one, so it can
+// not enter the top-k).  m starts near 2k/L and doubles on failure; data dealt round-robin to the
+// CTAs passes on the first or second try, so the cost is ~one small sort whatever k is.  Falls
+// back to the full merge tree when the prefixes outgrow `cap_keys`.  Result in buf[0..kp).
+__device__ __forceinline__ void block_select_from_lists(const uint64_t* __restrict__ src, int L, int k, int kp, uint64_t* buf,
+                                                        int cap_keys) {
+    const int tid = threadIdx.x, nt = blockDim.x;
+    int m = (2 * k + L - 1) / L;
+    if (m < 8) m = 8;
+    if (m > kp) m = kp;
+    for (;;) {
+        const long long total = (long long)L * m;
+        if (total > cap_keys) break;
+        int np = kp;
+        while (np < total) np <<= 1;
+        if (np > cap_keys) break;
+        for (int idx = tid; idx < np; idx += nt) {
+            uint64_t v = 0ull;
+            if (idx < total) {
+                const int l = idx / m, j = idx - l * m;
+                v = ld_cg_u64(src + (size_t)l * kp + j);
+            }
+            buf[idx] = v;
+        }
+        __syncthreads();
+        block_bitonic_sort_desc(buf, np);
+        const uint64_t kth = total >= k ? buf[k - 1] : 0ull;
+        int more = 0;
+        if (m < kp) {
+            for (int l = tid; l < L; l += nt) more |= ld_cg_u64(src + (size_t)l * kp + m - 1) > kth;
+        }
+        if (!__syncthreads_or(more)) return;  // buf[0..kp) holds the answer (np >= kp)
+        m = m * 2 > kp ? kp : m * 2;
+    }
+    block_merge_lists(src, L, kp, buf, cap_keys / kp);
 }
 
 // Decode the first k keys of a sorted list into FAISS-shaped outputs.

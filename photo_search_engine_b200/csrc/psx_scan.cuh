@@ -426,8 +426,7 @@ __global__ void __launch_bounds__(PSX_MAX_THREADS, 1) scan_topk_kernel(const Sca
     // ---- last CTA: merge all lists (K2) ---------------------------------------------------------
     __threadfence();
     uint64_t* buf = reinterpret_cast<uint64_t*>(ring);
-    const int cap_lists = (int)(((size_t)W * S * PSX_SLOT_BYTES / 8) / p.kpad);
-    block_merge_lists(p.lists, gridDim.x, p.kpad, buf, cap_lists);
+    block_select_from_lists(p.lists, gridDim.x, p.k, p.kpad, buf, (int)((size_t)W * S * PSX_SLOT_BYTES / 8));
     block_emit_results(buf, p.k, p.kpad, p.metric, p.out_scores, p.out_ids, p.out_keys);
     if (threadIdx.x == 0) *p.counter = 0u;
 }
@@ -439,7 +438,7 @@ merge_keys_kernel(const uint64_t* __restrict__ keys, int nlists, int k, int kpad
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     uint64_t* buf = reinterpret_cast<uint64_t*>(smem_raw);
     const size_t qi = blockIdx.x;
-    block_merge_lists(keys + qi * (size_t)nlists * kpad, nlists, kpad, buf, cap_lists);
+    block_select_from_lists(keys + qi * (size_t)nlists * kpad, nlists, k, kpad, buf, cap_lists * kpad);
     block_emit_results(buf, k, kpad, metric, out_scores + qi * k, out_ids + qi * k, nullptr);
 }
 

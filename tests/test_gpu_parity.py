@@ -214,6 +214,24 @@ def test_k_beyond_one_pass_and_beyond_n():
     ix.close()
 
 
+@pytest.mark.parametrize("k", [100, 1000, 2048])
+def test_skewed_candidate_distribution(k):
+    """All true neighbours sit in one contiguous block of rows, i.e. in the lists of very few
+    CTAs: the prefix-gather merge has to deepen (and finally fall back to the full merge tree)."""
+    rng = np.random.default_rng(k)
+    n, d = 150_000, 64
+    x = unit_rows(rng, n, d)
+    q = unit_rows(rng, 2, d)
+    hot = 40_000
+    x[hot : hot + 3000] = (q[0] + 0.3 * unit_rows(rng, 3000, d)).astype(np.float32)
+    x[hot : hot + 3000] /= np.linalg.norm(x[hot : hot + 3000], axis=1, keepdims=True)
+    ix, oracle = make_index(x), make_oracle(x)
+    D, I = ix.search(q, k)
+    check_against_oracle(D, I, oracle, q, k)
+    assert ((I[0] >= hot) & (I[0] < hot + 3000)).all()
+    ix.close()
+
+
 def test_incremental_add_reset_reconstruct():
     rng = np.random.default_rng(8)
     x = unit_rows(rng, 2500, 40)
