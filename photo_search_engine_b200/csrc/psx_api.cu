@@ -398,7 +398,16 @@ static int plan_scan(psx_index* h, int k, ScanPlan& plan) {
         p.rps = 1;
         p.cpr = (int)((h->row_bytes + PSX_SLOT_BYTES - 1) / PSX_SLOT_BYTES);
     }
-    p.gsize = p.rps * (32 / p.rps);
+    // One predicate ballot covers a group of up to 32 rows, and groups are dealt round-robin to all
+    // warps of the grid.  A lone warp streams slowly (latency bound), so the kernel's tail is one
+    // group: keep groups small enough that every warp gets >= 256 of them (imbalance < 0.4 %), but
+    // not below 4 windows unless the corpus is so small that warps would otherwise stay idle.
+    int wpg = 32 / p.rps;  // windows per group
+    const long long all_warps = (long long)h->sm_count * h->ctas_per_sm * W;
+    auto groups_for = [&](int w) { return (h->n + (long long)p.rps * w - 1) / ((long long)p.rps * w); };
+    while (wpg > 4 && groups_for(wpg) < 256 * all_warps) wpg >>= 1;
+    while (wpg > 1 && groups_for(wpg) < all_warps) wpg >>= 1;
+    p.gsize = p.rps * wpg;
     // CTA-wide overflow checks are spaced so that a few hundred appends fit between two of them
     p.sync_every = std::max(1, std::min(8, 256 / (W * p.rps)));
     const int burst = W * p.rps * p.sync_every;  // most keys a CTA can append between two checks

@@ -87,11 +87,64 @@ __device__ __forceinline__ uint64_t ld_cg_u64(const uint64_t* p) {
 // ---------------------------------------------------------------------------------------
 // block-wide sorting networks over 64-bit keys in shared memory (descending)
 // ---------------------------------------------------------------------------------------
-// Full bitonic sort of buf[0..n), n a power of two.  All threads of the block must call.
+// Compare-exchange strides 32..1 of the bitonic network, for the phases size_from..size_to, on
+// 64-element chunks held two keys per lane: no shared-memory round trips and no block barriers.
+__device__ __forceinline__ void warp_bitonic_strides_le32(uint64_t* buf, int n, int size_from, int size_to) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    for (int base = warp * 64; base < n; base += nwarps * 64) {
+        const int i0 = base + lane, i1 = i0 + 32;
+        uint64_t e0 = buf[i0], e1 = buf[i1];
+        for (int sz = size_from; sz <= size_to; sz <<= 1) {
+            const bool d0 = (i0 & sz) == 0, d1 = (i1 & sz) == 0;  // descending blocks
+            if (sz >= 64) {  // stride 32: partner is the other key of this lane
+                const uint64_t hi = e0 > e1 ? e0 : e1, lo = e0 > e1 ? e1 : e0;
+                e0 = d0 ? hi : lo;
+                e1 = d0 ? lo : hi;
+            }
+#pragma unroll
+            for (int st = 16; st >= 1; st >>= 1) {
+                if (st < sz) {
+                    const bool lower = (lane & st) == 0;
+                    const uint64_t p0 = __shfl_xor_sync(0xffffffffu, e0, st);
+                    const uint64_t p1 = __shfl_xor_sync(0xffffffffu, e1, st);
+                    e0 = ((e0 > p0) == (lower == d0)) ? e0 : p0;
+                    e1 = ((e1 > p1) == (lower == d1)) ? e1 : p1;
+                }
+            }
+        }
+        buf[i0] = e0;
+        buf[i1] = e1;
+    }
+}
+
+// Full bitonic sort of buf[0..n) in shared memory, descending, n a power of two.  All threads of
+// the block must call.  Strides >= 64 go through shared memory with a block barrier each; the
+// six innermost strides of every phase run in registers with warp shuffles, so a 1024-key sort
+// needs 15 barriers instead of 55.
 __device__ __forceinline__ void block_bitonic_sort_desc(uint64_t* buf, int n) {
     const int tid = threadIdx.x, nt = blockDim.x;
-    for (int size = 2; size <= n; size <<= 1) {
-        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+    if (n < 64) {  // tiny: plain network
+        for (int size = 2; size <= n; size <<= 1) {
+            for (int stride = size >> 1; stride > 0; stride >>= 1) {
+                for (int t = tid; t < (n >> 1); t += nt) {
+                    const int i = ((t & ~(stride - 1)) << 1) | (t & (stride - 1));
+                    const int j = i | stride;
+                    const bool desc = (i & size) == 0;
+                    const uint64_t a = buf[i], b = buf[j];
+                    if ((a < b) == desc) {
+                        buf[i] = b;
+                        buf[j] = a;
+                    }
+                }
+                __syncthreads();
+            }
+        }
+        return;
+    }
+    warp_bitonic_strides_le32(buf, n, 2, 64);
+    __syncthreads();
+    for (int size = 128; size <= n; size <<= 1) {
+        for (int stride = size >> 1; stride >= 64; stride >>= 1) {
 #pragma unroll 4
             for (int t = tid; t < (n >> 1); t += nt) {
                 const int i = ((t & ~(stride - 1)) << 1) | (t & (stride - 1));
@@ -105,6 +158,8 @@ __device__ __forceinline__ void block_bitonic_sort_desc(uint64_t* buf, int n) {
             }
             __syncthreads();
         }
+        warp_bitonic_strides_le32(buf, n, size, size);
+        __syncthreads();
     }
 }
 
