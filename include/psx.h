@@ -145,6 +145,19 @@ int psx_search_device(psx_index* h, const float* q_dev, int64_t nq, int64_t k, c
                       uint32_t id_base, float* out_scores_dev, int64_t* out_ids_dev,
                       uint64_t* out_keys_dev, void* stream);
 int64_t psx_kpad(int64_t k);
+
+/* Batched queries on the tensor cores (replaces nq consecutive index.search calls, e.g. the
+ * expansion alternatives of core/searcher.py:1392-1412): S = Q X^T as tcgen05 TF32 GEMM tiles with
+ * the selection fused into the epilogue (the score matrix never reaches HBM), then an exact fp32
+ * re-score of the survivors.  flags_dev[i] == 0 certifies that query i's result is the exact
+ * top-k (bit-identical to psx_search_device); a non-zero flag means "not proven", the caller
+ * re-runs that query with psx_search_device.  psx_search does both steps itself for nq >= the
+ * "batch_min" tunable.  `qnorm_max` >= the largest L2 norm among the queries (1 for cosine).
+ * fp32 inner-product indexes with >= 65536 rows, d >= 32, k <= 512. */
+int psx_search_batch_device(psx_index* h, const float* q_dev, int64_t nq, int64_t k, float qnorm_max, uint32_t id_base,
+                            float* out_scores_dev, int64_t* out_ids_dev, uint64_t* out_keys_dev, int* flags_dev, void* stream);
+/* queries served by the batched path so far, and how many of them had to be re-run on the scan */
+int psx_batch_stats(psx_index* h, int64_t* queries, int64_t* fallbacks);
 /* Final merge of `nlists` sorted key lists per query (layout [nq][nlists][kpad], e.g. the
  * all-gathered per-shard results) into the global top-k.  Pure device work on `stream`. */
 int psx_merge_keys_device(int device, const uint64_t* keys_dev, int64_t nq, int64_t nlists, int64_t k,
@@ -160,8 +173,9 @@ int psx_storage_device(psx_index* h, const void** rows_dev, int64_t* ld_elems, i
 
 /* ---- tuning / introspection ---------------------------------------------------------------- */
 
-/* key: "warps" (consumer warps per CTA), "stages" (ring slots per warp), "ctas_per_sm".
- * Values <= 0 restore the default. */
+/* key: "warps" (consumer warps per CTA), "stages" (ring slots per warp), "ctas_per_sm"
+ * (values <= 0 restore the default), "batch_min" (smallest nq routed to the tensor-core path
+ * by psx_search; 0 disables it, < 0 restores the default of 4). */
 int psx_set_tunable(psx_index* h, const char* key, int value);
 /* Number of kernels launched by this library in the calling process so far. */
 int64_t psx_launch_count(void);

@@ -48,7 +48,8 @@ def build_native(force: bool = False, verbose: bool = False) -> str:
     if not force and not is_stale():
         return LIB
     srcs = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith(".cu")]
-    cmd = [_nvcc(), *NVCC_FLAGS, "-o", LIB + ".tmp", *srcs]
+    extra = ["-DPSX_DEBUG_KERNELS"] if os.environ.get("PSX_DEBUG_KERNELS") == "1" else []
+    cmd = [_nvcc(), *NVCC_FLAGS, *extra, "-o", LIB + ".tmp", *srcs]
     proc = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or proc.returncode != 0:
         sys.stderr.write(proc.stdout + proc.stderr)

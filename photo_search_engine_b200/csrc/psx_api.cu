@@ -5,6 +5,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -12,6 +13,7 @@
 #include <vector>
 
 #include "psx_aux.cuh"
+#include "psx_gemm.cuh"
 #include "psx_scan.cuh"
 
 using namespace psx;
@@ -85,8 +87,26 @@ struct psx_index {
     float* hscores = nullptr;
     long long* hids = nullptr;
     size_t hq_cap = 0, hout_cap = 0;
+    // batched (GEMM) path scratch
+    float* dmax_sumsq = nullptr;  // device: max ||stored row||^2, maintained by the pack kernel
+    float max_norm = 0.f;         // host copy of its square root
+    int batch_min = 4;        // smallest nq routed to the tensor-core path
+    float* bq = nullptr;      // [256][ld] zero-padded query block
+    float* btheta = nullptr;  // [256]
+    int* bcount = nullptr;    // [256]
+    int* bflags = nullptr;    // [256]
+    uint32_t* bcand = nullptr;  // [256][BATCH_CAND_CAP]
+    float* bsample = nullptr;
+    size_t bsample_cap = 0;
+    int* hflags = nullptr;    // pinned [256]
+    long long batch_fallbacks = 0, batch_queries = 0;
     std::mutex mu;
 };
+
+constexpr int BATCH_MAX_Q = 256;
+constexpr int BATCH_CAND_CAP = 4096;
+constexpr int BATCH_BN = 128;
+constexpr int BATCH_STAGES = 4;
 
 static int pow2ceil(long long v) {
     long long p = 1;
@@ -148,6 +168,8 @@ extern "C" int psx_create(int d, int metric, int store_dtype, int device, psx_in
         CU(cudaEventCreateWithFlags(&h->last_ev, cudaEventDisableTiming));
         CU(cudaMalloc(&h->counter, sizeof(unsigned int)));
         CU(cudaMemset(h->counter, 0, sizeof(unsigned int)));
+        CU(cudaMalloc(&h->dmax_sumsq, sizeof(float)));
+        CU(cudaMemset(h->dmax_sumsq, 0, sizeof(float)));
         return set_max_smem(merge_keys_kernel);
     };
     rc = init();
@@ -171,6 +193,14 @@ static void free_all(psx_index* h) {
     cudaFreeHost(h->hq);
     cudaFreeHost(h->hscores);
     cudaFreeHost(h->hids);
+    cudaFree(h->dmax_sumsq);
+    cudaFree(h->bq);
+    cudaFree(h->btheta);
+    cudaFree(h->bcount);
+    cudaFree(h->bflags);
+    cudaFree(h->bcand);
+    cudaFree(h->bsample);
+    cudaFreeHost(h->hflags);
     if (h->last_ev) cudaEventDestroy(h->last_ev);
     if (h->stream) cudaStreamDestroy(h->stream);
 }
@@ -200,6 +230,8 @@ extern "C" int psx_reset(psx_index* h) {
     h->x = nullptr;
     h->attrs = nullptr;
     h->attrs_set = false;
+    cudaMemset(h->dmax_sumsq, 0, sizeof(float));
+    h->max_norm = 0.f;
     h->n = h->cap = 0;
     h->pending.clear();
     h->pending.shrink_to_fit();
@@ -254,10 +286,12 @@ static int launch_pack(psx_index* h, const float* src_dev, long long row0, long 
     if (blocks > (long long)h->sm_count * 16) blocks = (long long)h->sm_count * 16;
     unsigned char* dst = h->x + (size_t)row0 * h->row_bytes;
     if (h->dtype == PSX_STORE_F32)
-        pack_rows_kernel<float><<<(unsigned)blocks, 256, 0, st>>>(src_dev, (float*)dst, n, h->d, h->ld, normalize);
+        pack_rows_kernel<float><<<(unsigned)blocks, 256, 0, st>>>(src_dev, (float*)dst, n, h->d, h->ld, normalize, h->dmax_sumsq);
     else
-        pack_rows_kernel<__nv_bfloat16><<<(unsigned)blocks, 256, 0, st>>>(src_dev, (__nv_bfloat16*)dst, n, h->d, h->ld, normalize);
+        pack_rows_kernel<__nv_bfloat16><<<(unsigned)blocks, 256, 0, st>>>(src_dev, (__nv_bfloat16*)dst, n, h->d, h->ld, normalize,
+                                                                        h->dmax_sumsq);
     g_launches++;
+    h->max_norm = 0.f;  // re-read lazily
     CU(cudaGetLastError());
     return PSX_OK;
 }
@@ -526,6 +560,168 @@ static int launch_scan(psx_index* h, const float* q_dev, int k, const psx_filter
     return PSX_OK;
 }
 
+// ------------------------------------------------------------------------------------------
+// batched path (K3): TF32 tensor-core GEMM with fused threshold selection + exact re-score
+// ------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess) p = nullptr;
+        return (EncodeTiledFn)p;
+    }();
+    return fn;
+}
+// 2-D fp32 tensor [rows][cols] with row stride ld floats, box = 32 floats x box_rows, 128-byte swizzle
+static int make_map(CUtensorMap* map, const float* base, long long rows, int cols, int ld, int box_rows) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn) return fail(PSX_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
+    cuuint32_t box[2] = {(cuuint32_t)GEMM_BK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(PSX_ERR_CUDA, "cuTensorMapEncodeTiled failed with %d", (int)r);
+    return PSX_OK;
+}
+
+static bool batch_eligible(const psx_index* h, int64_t nq, int64_t k, const psx_filter* f) {
+    return h->metric == PSX_METRIC_IP && h->dtype == PSX_STORE_F32 && !(f && f->flags) && h->batch_min > 0 &&
+           nq >= h->batch_min && k <= 512 && h->n >= 65536 && h->d >= 32;
+}
+
+static int ensure_batch_scratch(psx_index* h, size_t sample_floats) {
+    if (!h->bq) {
+        CU(cudaMalloc(&h->bq, (size_t)BATCH_MAX_Q * h->ld * sizeof(float)));
+        CU(cudaMalloc(&h->btheta, BATCH_MAX_Q * sizeof(float)));
+        CU(cudaMalloc(&h->bcount, BATCH_MAX_Q * sizeof(int)));
+        CU(cudaMalloc(&h->bflags, BATCH_MAX_Q * sizeof(int)));
+        CU(cudaMalloc(&h->bcand, (size_t)BATCH_MAX_Q * BATCH_CAND_CAP * sizeof(uint32_t)));
+        CU(cudaMallocHost(&h->hflags, BATCH_MAX_Q * sizeof(int)));
+    }
+    if (sample_floats > h->bsample_cap) {
+        cudaFree(h->bsample);
+        h->bsample = nullptr;
+        h->bsample_cap = 0;
+        CU(cudaMalloc(&h->bsample, sample_floats * sizeof(float)));
+        h->bsample_cap = sample_floats;
+    }
+    return PSX_OK;
+}
+
+// PSX_DEBUG_SYNC=1: synchronise after every launch of the batched path and name the kernel that faulted
+static bool debug_sync() {
+    static const bool on = [] { const char* e = getenv("PSX_DEBUG_SYNC"); return e && *e == '1'; }();
+    return on;
+}
+#define DBG_SYNC(st, what)                                                                                     \
+    do {                                                                                                       \
+        if (debug_sync()) {                                                                                    \
+            cudaError_t e_ = cudaStreamSynchronize(st);                                                        \
+            if (e_ != cudaSuccess) return fail(PSX_ERR_CUDA, "%s faulted: %s", what, cudaGetErrorString(e_)); \
+        }                                                                                                      \
+    } while (0)
+
+template <int MT>
+static int launch_gemm(psx_index* h, const CUtensorMap& mq, const CUtensorMap& mx, const GemmParams& gp, int grid, cudaStream_t st) {
+    constexpr int STAGE_BYTES = (MT * GEMM_M + BATCH_BN) * GEMM_BK * 4;
+    constexpr size_t smem = (size_t)BATCH_STAGES * STAGE_BYTES + 256;
+    static std::atomic<bool> ready[64];
+    if (h->device < 64 && !ready[h->device].load()) {
+        CU(cudaFuncSetAttribute(gemm_filter_kernel<MT, BATCH_BN, BATCH_STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ready[h->device].store(true);
+    }
+    gemm_filter_kernel<MT, BATCH_BN, BATCH_STAGES><<<grid, GEMM_THREADS, smem, st>>>(mq, mx, gp);
+    g_launches++;
+    CU(cudaGetLastError());
+    return PSX_OK;
+}
+
+// One batch of nq <= 256 queries (device pointers).  flags_dev[qi] != 0 marks results that are not
+// proven exact; the caller re-runs those queries on the streaming scan.
+static int launch_batch(psx_index* h, const float* q_dev, int nq, int k, uint32_t id_base, float qnorm_max, float* out_scores,
+                        long long* out_ids, uint64_t* out_keys, int* flags_dev, cudaStream_t st) {
+    const int MT = nq > GEMM_M ? 2 : 1;
+    const int num_tiles = (int)((h->n + BATCH_BN - 1) / BATCH_BN);
+    // theta from a strided sample: aim at ~16 sample scores above the threshold that ~T rows pass
+    const int T = 4 * k + 64;
+    int tile_step = T / 16;
+    if (tile_step < 1) tile_step = 1;
+    while (tile_step > 1 && num_tiles / tile_step < 64) --tile_step;
+    const int sample_tiles = (num_tiles + tile_step - 1) / tile_step;
+    const int grid_s = std::min(h->sm_count, sample_tiles);
+    const int sample_ld = sample_tiles * BATCH_BN;  // sample tile ordinals are 0 .. sample_tiles-1
+    int rc = ensure_batch_scratch(h, (size_t)MT * GEMM_M * sample_ld);
+    if (rc) return rc;
+    // queries -> zero-padded [MT*128][ld] block (rows beyond nq and columns beyond d are zero)
+    CU(cudaMemsetAsync(h->bq, 0, (size_t)MT * GEMM_M * h->ld * sizeof(float), st));
+    CU(cudaMemcpy2DAsync(h->bq, (size_t)h->ld * sizeof(float), q_dev, (size_t)h->d * sizeof(float), (size_t)h->d * sizeof(float), nq,
+                         cudaMemcpyDeviceToDevice, st));
+    CUtensorMap mq, mx;
+    if ((rc = make_map(&mq, h->bq, (long long)MT * GEMM_M, h->d, h->ld, GEMM_M))) return rc;
+    if ((rc = make_map(&mx, (const float*)h->x, h->n, h->d, h->ld, BATCH_BN))) return rc;
+    GemmParams gp;
+    memset(&gp, 0, sizeof gp);
+    gp.n = h->n;
+    gp.d = h->d;
+    gp.nq = nq;
+    gp.num_tiles = num_tiles;
+    gp.theta = h->btheta;
+    gp.cand_ids = h->bcand;
+    gp.cand_count = h->bcount;
+    gp.cand_cap = BATCH_CAND_CAP;
+    gp.sample_scores = h->bsample;
+    gp.sample_ld = sample_ld;
+    // pass 1: sample
+    gp.mode = GEMM_MODE_SAMPLE;
+    gp.tile_step = tile_step;
+    DBG_SYNC(st, "query staging");
+    rc = MT == 2 ? launch_gemm<2>(h, mq, mx, gp, grid_s, st) : launch_gemm<1>(h, mq, mx, gp, grid_s, st);
+    if (rc) return rc;
+    DBG_SYNC(st, "gemm_filter_kernel(sample)");
+    const long long sample_rows = std::min<long long>(h->n, (long long)sample_tiles * BATCH_BN);
+    int rank = (int)((double)T * (double)sample_rows / (double)h->n + 0.5);
+    if (rank < 2) rank = 2;
+    theta_kernel<<<nq, 256, 0, st>>>(h->bsample, sample_ld, sample_ld, rank, 0.0f, h->btheta, h->bcount);
+    g_launches++;
+    CU(cudaGetLastError());
+    DBG_SYNC(st, "theta_kernel");
+    // pass 2: every tile, threshold test fused into the epilogue
+    gp.mode = GEMM_MODE_FILTER;
+    gp.tile_step = 1;
+    const int grid_f = std::min(h->sm_count, num_tiles);
+    rc = MT == 2 ? launch_gemm<2>(h, mq, mx, gp, grid_f, st) : launch_gemm<1>(h, mq, mx, gp, grid_f, st);
+    if (rc) return rc;
+    DBG_SYNC(st, "gemm_filter_kernel(filter)");
+    // exact re-score of the survivors + top-k + proof obligation
+    const int kpad = (int)psx_kpad(k);
+    const size_t smem = (size_t)BATCH_CAND_CAP * 8 + (size_t)(h->ld + 4) * 4;
+    static std::atomic<bool> ready[64];
+    if (h->device < 64 && !ready[h->device].load()) {
+        CU(cudaFuncSetAttribute(rescore_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PSX_SMEM_LIMIT));
+        ready[h->device].store(true);
+    }
+    // TF32 keeps 10 mantissa bits of each operand: |score_tf32 - score| <= 2^-9 * sum|q_i x_i| <= 2^-9 |q| |x|
+    // (Cauchy-Schwarz); 2.2e-3 leaves 12 % slack for the accumulation.
+    if (h->max_norm == 0.f) {
+        float m2 = 0.f;
+        CU(cudaMemcpyAsync(&m2, h->dmax_sumsq, sizeof(float), cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        h->max_norm = sqrtf(m2);
+    }
+    const float eps = 2.2e-3f * (qnorm_max > 0.f ? qnorm_max : 1.0f) * (h->max_norm > 0.f ? h->max_norm : 1.0f);
+    rescore_select_kernel<<<nq, 512, smem, st>>>((const float*)h->x, h->ld, h->d, h->n, q_dev, k, kpad, h->bcand, h->bcount,
+                                                 BATCH_CAND_CAP, h->btheta, eps, id_base, out_scores, out_ids, out_keys, flags_dev);
+    g_launches++;
+    CU(cudaGetLastError());
+    DBG_SYNC(st, "rescore_select_kernel");
+    return PSX_OK;
+}
+
 // scratch is per index: order this search after the previous one if it ran on another stream
 static int enter_stream(psx_index* h, cudaStream_t st) {
     if (h->has_last && h->last_stream != st) CU(cudaStreamWaitEvent(st, h->last_ev, 0));
@@ -557,6 +753,30 @@ extern "C" int psx_search_device(psx_index* h, const float* q_dev, int64_t nq, i
                          out_keys_dev ? out_keys_dev + qi * kpad : nullptr, st);
         if (rc) return rc;
     }
+    return leave_stream(h, st);
+}
+
+extern "C" int psx_search_batch_device(psx_index* h, const float* q_dev, int64_t nq, int64_t k, float qnorm_max, uint32_t id_base,
+                                       float* out_scores_dev, int64_t* out_ids_dev, uint64_t* out_keys_dev, int* flags_dev,
+                                       void* stream) {
+    if (!h || !q_dev || !out_scores_dev || !out_ids_dev || !flags_dev || nq < 1)
+        return fail(PSX_ERR_INVALID, "bad arguments to psx_search_batch_device");
+    std::lock_guard<std::mutex> lk(h->mu);
+    DeviceGuard g(h->device);
+    int rc = flush_pending(h);
+    if (rc) return rc;
+    if (k < 1 || k > 512 || h->metric != PSX_METRIC_IP || h->dtype != PSX_STORE_F32 || h->n < 65536 || h->d < 32)
+        return fail(PSX_ERR_STATE, "tensor-core batch path needs an fp32 inner-product index with >= 65536 rows, d >= 32, k <= 512");
+    cudaStream_t st = (cudaStream_t)stream;
+    if ((rc = enter_stream(h, st))) return rc;
+    const int64_t kpad = psx_kpad(k);
+    for (int64_t q0 = 0; q0 < nq; q0 += BATCH_MAX_Q) {
+        const int gq = (int)std::min<int64_t>(BATCH_MAX_Q, nq - q0);
+        rc = launch_batch(h, q_dev + q0 * h->d, gq, (int)k, id_base, qnorm_max, out_scores_dev + q0 * k,
+                          (long long*)out_ids_dev + q0 * k, out_keys_dev ? out_keys_dev + q0 * kpad : nullptr, flags_dev + q0, st);
+        if (rc) return rc;
+    }
+    h->batch_queries += nq;
     return leave_stream(h, st);
 }
 
@@ -624,6 +844,53 @@ static int ensure_io(psx_index* h, size_t qfloats, size_t outs) {
     return PSX_OK;
 }
 
+// Host-buffer batch search through the tensor-core path; unproven queries are re-run on the scan.
+static int search_batched_host(psx_index* h, const float* q, int64_t nq, int64_t kk, int64_t k, float* out_scores,
+                               int64_t* out_ids) {
+    int rc;
+    cudaStream_t st = h->stream;
+    if ((rc = ensure_batch_scratch(h, 0))) return rc;  // h->bflags / h->hflags must exist before they are passed on
+    if ((rc = enter_stream(h, st))) return rc;
+    for (int64_t q0 = 0; q0 < nq; q0 += BATCH_MAX_Q) {
+        const int gq = (int)std::min<int64_t>(BATCH_MAX_Q, nq - q0);
+        if ((rc = ensure_io(h, (size_t)gq * h->d, (size_t)gq * kk))) return rc;
+        memcpy(h->hq, q + q0 * h->d, (size_t)gq * h->d * sizeof(float));
+        float qn2 = 0.f;
+        for (int qi = 0; qi < gq; ++qi) {
+            double acc = 0.0;
+            const float* v = h->hq + (size_t)qi * h->d;
+            for (int i = 0; i < h->d; ++i) acc += (double)v[i] * v[i];
+            qn2 = std::max(qn2, (float)acc);
+        }
+        CU(cudaMemcpyAsync(h->dq, h->hq, (size_t)gq * h->d * sizeof(float), cudaMemcpyHostToDevice, st));
+        if ((rc = launch_batch(h, h->dq, gq, (int)kk, 0, sqrtf(qn2) * 1.0001f, h->dscores, h->dids, nullptr, h->bflags, st))) return rc;
+        CU(cudaMemcpyAsync(h->hflags, h->bflags, gq * sizeof(int), cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        h->batch_queries += gq;
+        for (int qi = 0; qi < gq; ++qi) {
+            if (!h->hflags[qi]) continue;
+            h->batch_fallbacks++;
+            rc = launch_scan(h, h->dq + (size_t)qi * h->d, (int)kk, nullptr, 0, nullptr, h->dscores + (size_t)qi * kk,
+                             h->dids + (size_t)qi * kk, nullptr, st);
+            if (rc) return rc;
+        }
+        CU(cudaMemcpyAsync(h->hscores, h->dscores, (size_t)gq * kk * sizeof(float), cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(h->hids, h->dids, (size_t)gq * kk * sizeof(long long), cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        for (int qi = 0; qi < gq; ++qi) {
+            float* os = out_scores + (q0 + qi) * k;
+            int64_t* oi = out_ids + (q0 + qi) * k;
+            memcpy(os, h->hscores + (size_t)qi * kk, (size_t)kk * sizeof(float));
+            memcpy(oi, h->hids + (size_t)qi * kk, (size_t)kk * sizeof(long long));
+            for (int64_t i = kk; i < k; ++i) {
+                os[i] = -INFINITY;
+                oi[i] = -1;
+            }
+        }
+    }
+    return leave_stream(h, st);
+}
+
 extern "C" int psx_search(psx_index* h, const float* q, int64_t nq, int64_t k, const psx_filter* filter, float* out_scores,
                           int64_t* out_ids) {
     if (!h || !q || !out_scores || !out_ids || nq < 0) return fail(PSX_ERR_INVALID, "bad arguments to psx_search");
@@ -643,6 +910,7 @@ extern "C" int psx_search(psx_index* h, const float* q, int64_t nq, int64_t k, c
     }
     // results beyond ntotal can never be filled: scan for min(k, n) and pad on the host
     const int64_t kk = std::min<int64_t>(k, h->n);
+    if (batch_eligible(h, nq, kk, filter)) return search_batched_host(h, q, nq, kk, k, out_scores, out_ids);
     const int64_t pages = (kk + PSX_K_PASS_MAX - 1) / PSX_K_PASS_MAX;
     // per-query stride of the device outputs
     const int64_t kslot = pages == 1 ? psx_kpad(kk) : pages * PSX_K_PASS_MAX;
@@ -751,6 +1019,13 @@ extern "C" int psx_storage_device(psx_index* h, const void** rows_dev, int64_t* 
     return PSX_OK;
 }
 
+extern "C" int psx_batch_stats(psx_index* h, int64_t* queries, int64_t* fallbacks) {
+    if (!h) return fail(PSX_ERR_INVALID, "null handle");
+    if (queries) *queries = h->batch_queries;
+    if (fallbacks) *fallbacks = h->batch_fallbacks;
+    return PSX_OK;
+}
+
 extern "C" int psx_set_tunable(psx_index* h, const char* key, int value) {
     if (!h || !key) return fail(PSX_ERR_INVALID, "bad arguments to psx_set_tunable");
     std::lock_guard<std::mutex> lk(h->mu);
@@ -760,6 +1035,8 @@ extern "C" int psx_set_tunable(psx_index* h, const char* key, int value) {
         h->stages = value <= 0 ? 2 : std::max(2, std::min(value, 12));
     } else if (!strcmp(key, "ctas_per_sm")) {
         h->ctas_per_sm = value <= 0 ? 1 : std::min(value, 8);
+    } else if (!strcmp(key, "batch_min")) {  // smallest nq sent to the tensor-core path; 0 disables it
+        h->batch_min = value < 0 ? 4 : value;
     } else {
         return fail(PSX_ERR_INVALID, "unknown tunable '%s'", key);
     }

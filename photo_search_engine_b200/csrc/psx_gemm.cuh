@@ -1,0 +1,387 @@
+// psx_gemm.cuh -- K3: batched queries as a dense contraction on the 5th-generation tensor cores.
+//
+// The reference issues one FAISS search per query (utils/vector_store.py:190); its multi-round
+// drivers (core/searcher.py:1352-1458) and many concurrent users make batches.  For nq >= a
+// handful, S = Q . X^T is a GEMM: 2*N*d*nq FLOP over the same N*d*4 bytes, so the corpus is
+// streamed ONCE for the whole batch.
+//
+//   tcgen05.mma kind::tf32, cta_group::1, M = 128 queries per accumulator, N = BN corpus rows,
+//   K = 8 per instruction; operands staged by TMA (cp.async.bulk.tensor.2d, 128-byte swizzle,
+//   K-major for both) through a STAGES-deep mbarrier ring; fp32 accumulators in TMEM, double
+//   buffered when they fit, read back with tcgen05.ld by four epilogue warps.
+//
+// The score matrix never reaches HBM: the epilogue compares every score with a per-query
+// threshold theta_q and appends only the survivors' row ids to a small per-query candidate list.
+// TF32 keeps 10 mantissa bits, so these scores are approximate; exactness is restored by
+//   (1) rescore_select_kernel: exact fp32 dot (same reduction tree as the streaming scan, hence
+//       bit-identical scores) of every candidate, exact top-k by integer sort, and
+//   (2) a proof obligation per query: the k-th exact score must be >= theta_q + eps, eps = the
+//       TF32 error bound.  Then no row outside the list can belong to the top-k.  Queries that
+//       fail it (or overflow their list) are flagged and re-run by the streaming scan.
+// theta_q comes from a strided sample pass of the same GEMM kernel (MODE_SAMPLE).
+#pragma once
+#include <cuda.h>
+
+#include "psx_common.cuh"
+
+namespace psx {
+
+constexpr int GEMM_BK = 32;        // fp32 elements per k-block = one 128-byte swizzle row
+constexpr int GEMM_UMMA_K = 8;     // tf32
+constexpr int GEMM_M = 128;        // queries per accumulator tile
+constexpr int GEMM_THREADS = 256;  // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warp3 idle, warps4-7 epilogue
+constexpr int GEMM_MODE_SAMPLE = 0, GEMM_MODE_FILTER = 1;
+
+struct GemmParams {
+    long long n;             // corpus rows
+    int d;                   // logical dimension
+    int nq;                  // queries in this batch (<= MT*128)
+    int num_tiles;           // ceil(n / BN)
+    int tile_step;           // MODE_SAMPLE: visit tiles 0, tile_step, 2*tile_step, ...
+    int mode;
+    const float* theta;      // [nq] thresholds (MODE_FILTER)
+    uint32_t* cand_ids;      // [nq][cand_cap]
+    int* cand_count;         // [nq]
+    int cand_cap;
+    float* sample_scores;    // [nq][sample_ld] (MODE_SAMPLE)
+    int sample_ld;
+};
+
+// ---- PTX wrappers -----------------------------------------------------------------------------
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+        "l"(map), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, tf32 inputs, fp32 accumulate
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// shared-memory matrix descriptor: K-major, 128-byte swizzle, 8-row groups 1024 bytes apart
+__device__ __forceinline__ uint64_t umma_smem_desc(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr >> 4) & 0x3fffu) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+// instruction descriptor: D fp32, A/B tf32, both K-major, M x N
+__host__ __device__ constexpr uint32_t umma_idesc_tf32(int m, int n) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+// 32 consecutive fp32 columns of this warp's 32 TMEM lanes -> 32 registers per thread
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// ---- the GEMM + fused selection kernel ---------------------------------------------------------------
+// MT accumulator tiles of 128 queries each, BN corpus rows per tile.  TMEM columns: MT*BN per
+// accumulator stage, 512 in total.
+template <int MT, int BN, int STAGES>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_x, const GemmParams p) {
+    constexpr int ACC_COLS = MT * BN;
+    constexpr int ACC_STAGES = 512 / ACC_COLS >= 2 ? 2 : 1;
+    constexpr int A_BYTES = MT * GEMM_M * GEMM_BK * 4;
+    constexpr int B_BYTES = BN * GEMM_BK * 4;
+    constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static_assert(ACC_COLS <= 512 && BN % 32 == 0 && BN <= 256, "bad tile");
+
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char* tiles = smem_raw;  // [STAGES][A | B], every operand tile 1024-byte aligned
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(tiles + (size_t)STAGES * STAGE_BYTES);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* acc_full = empty_bar + STAGES;
+    uint64_t* acc_empty = acc_full + ACC_STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + ACC_STAGES);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int kblocks = (p.d + GEMM_BK - 1) / GEMM_BK;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&map_q);
+        tma_prefetch_desc(&map_x);
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(smem_u32(full_bar + s), 1);
+            mbar_init(smem_u32(empty_bar + s), 1);
+        }
+        for (int a = 0; a < ACC_STAGES; ++a) {
+            mbar_init(smem_u32(acc_full + a), 1);
+            mbar_init(smem_u32(acc_empty + a), 4);  // one arrive per epilogue warp
+        }
+        mbar_fence_init();
+    }
+    if (warp == 2) tmem_alloc(smem_u32(tmem_slot), 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int first = blockIdx.x * p.tile_step;
+    const int stride = gridDim.x * p.tile_step;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            int s = 0;
+            uint32_t ph = 0;
+            for (int t = first; t < p.num_tiles; t += stride) {
+                const int row0 = t * BN;
+                for (int kb = 0; kb < kblocks; ++kb) {
+                    mbar_wait(smem_u32(empty_bar + s), ph ^ 1u);
+                    const uint32_t bar = smem_u32(full_bar + s);
+                    const uint32_t a_dst = smem_u32(tiles + (size_t)s * STAGE_BYTES);
+                    mbar_arrive_expect_tx(bar, STAGE_BYTES);
+#pragma unroll
+                    for (int m = 0; m < MT; ++m)
+                        tma_load_2d(a_dst + m * (GEMM_M * GEMM_BK * 4), &map_q, bar, kb * GEMM_BK, m * GEMM_M);
+                    tma_load_2d(a_dst + A_BYTES, &map_x, bar, kb * GEMM_BK, row0);
+                    if (++s == STAGES) {
+                        s = 0;
+                        ph ^= 1u;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer (one thread) =====
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_tf32(GEMM_M, BN);
+            int s = 0, a = 0;
+            uint32_t ph = 0, aph = 0;
+            for (int t = first; t < p.num_tiles; t += stride) {
+                mbar_wait(smem_u32(acc_empty + a), aph ^ 1u);  // epilogue drained this accumulator
+                tc_fence_after();
+                for (int kb = 0; kb < kblocks; ++kb) {
+                    mbar_wait(smem_u32(full_bar + s), ph);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_u32(tiles + (size_t)s * STAGE_BYTES);
+                    const uint64_t b_desc = umma_smem_desc(a_addr + A_BYTES);
+#pragma unroll
+                    for (int m = 0; m < MT; ++m) {
+                        const uint64_t a_desc = umma_smem_desc(a_addr + m * (GEMM_M * GEMM_BK * 4));
+                        const uint32_t d_addr = tmem_base + (uint32_t)(a * ACC_COLS + m * BN);
+#pragma unroll
+                        for (int k = 0; k < GEMM_BK / GEMM_UMMA_K; ++k) {
+                            // advancing K inside the 128-byte swizzle row: +32 bytes = +2 in the
+                            // (address >> 4) field of both descriptors
+                            umma_tf32(d_addr, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+                        }
+                    }
+                    umma_commit(smem_u32(empty_bar + s));  // smem slot reusable once these MMAs retire
+                    if (++s == STAGES) {
+                        s = 0;
+                        ph ^= 1u;
+                    }
+                }
+                umma_commit(smem_u32(acc_full + a));  // accumulator complete
+                if (++a == ACC_STAGES) {
+                    a = 0;
+                    aph ^= 1u;
+                }
+            }
+        }
+    } else if (warp >= 4) {
+        // ===== epilogue: TMEM -> registers -> threshold test -> candidate lists =====
+        const int ew = warp - 4;            // TMEM lanes [32*ew, 32*ew + 32)
+        const int qlane = ew * 32 + lane;   // query row inside an accumulator tile
+        float theta[MT];
+#pragma unroll
+        for (int m = 0; m < MT; ++m) {
+            const int qi = m * GEMM_M + qlane;
+            theta[m] = (p.mode == GEMM_MODE_FILTER && qi < p.nq) ? p.theta[qi] : INFINITY;
+        }
+        int a = 0, tile_no = 0;
+        uint32_t aph = 0;
+        for (int t = first; t < p.num_tiles; t += stride, ++tile_no) {
+            mbar_wait(smem_u32(acc_full + a), aph);
+            tc_fence_after();
+            const long long row0 = (long long)t * BN;
+#pragma unroll
+            for (int m = 0; m < MT; ++m) {
+                const int qi = m * GEMM_M + qlane;
+                const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(a * ACC_COLS + m * BN);
+#pragma unroll 1
+                for (int c = 0; c < BN / 32; ++c) {
+                    uint32_t r[32];
+                    tmem_ld_32x32(taddr + c * 32, r);
+                    if (p.mode == GEMM_MODE_FILTER) {
+                        float mx = __uint_as_float(r[0]);
+#pragma unroll
+                        for (int j = 1; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(r[j]));
+                        if (mx >= theta[m]) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) {
+                                const long long row = row0 + c * 32 + j;
+                                if (__uint_as_float(r[j]) >= theta[m] && row < p.n) {
+                                    const int pos = atomicAdd(p.cand_count + qi, 1);
+                                    if (pos < p.cand_cap) p.cand_ids[(size_t)qi * p.cand_cap + pos] = (uint32_t)row;
+                                }
+                            }
+                        }
+                    } else if (qi < p.nq) {
+                        // sample pass: keep the scores of the visited tiles (a few % of the matrix)
+                        float* dst = p.sample_scores + (size_t)qi * p.sample_ld + ((size_t)(blockIdx.x + (size_t)tile_no * gridDim.x)) * BN + c * 32;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const long long row = row0 + c * 32 + j;
+                            dst[j] = row < p.n ? __uint_as_float(r[j]) : -INFINITY;
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(acc_empty + a));
+            if (++a == ACC_STAGES) {
+                a = 0;
+                aph ^= 1u;
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+// ---- theta: per query, an approximate T-th largest of its sample scores -------------------------------
+// One CTA per query.  Every thread keeps the two largest values of its strided share; the 2*256
+// survivors are sorted and the element at the requested rank is taken.  Approximate by design: the
+// threshold only has to land between the k-th and roughly the (4k)-th score -- exactness comes from
+// the proof obligation checked after the exact re-score.
+__global__ void __launch_bounds__(256) theta_kernel(const float* __restrict__ sample, int sample_ld, int ns, int rank,
+                                                    float margin, float* __restrict__ theta, int* __restrict__ cand_count) {
+    __shared__ uint64_t keys[512];
+    const int qi = blockIdx.x;
+    const float* s = sample + (size_t)qi * sample_ld;
+    float b0 = -INFINITY, b1 = -INFINITY;
+    for (int i = threadIdx.x; i < ns; i += blockDim.x) {
+        const float v = s[i];
+        if (v > b0) {
+            b1 = b0;
+            b0 = v;
+        } else if (v > b1) {
+            b1 = v;
+        }
+    }
+    keys[2 * threadIdx.x] = make_key(b0, 2 * threadIdx.x);
+    keys[2 * threadIdx.x + 1] = make_key(b1, 2 * threadIdx.x + 1);
+    __syncthreads();
+    block_bitonic_sort_desc(keys, 512);
+    if (threadIdx.x == 0) {
+        int r = rank < 1 ? 1 : rank;
+        if (r > 512) r = 512;
+        float v = key_score(keys[r - 1]);
+        if (!(v > -INFINITY)) v = -INFINITY;  // fewer samples than the rank: take everything
+        theta[qi] = v - margin;
+        cand_count[qi] = 0;
+    }
+}
+
+// ---- exact re-score + selection ------------------------------------------------------------------------------
+// One CTA per query: every warp takes candidates round-robin, recomputes <q, x_row> in fp32 with
+// exactly the reduction tree of scan_topk_kernel (per-lane pieces lane, lane+32, ... into four
+// accumulators, (a0+a1)+(a2+a3), xor butterfly), so the scores are bit-identical to the
+// single-query path; keys are sorted in shared memory and the first k emitted.
+// flags[qi] != 0  <=>  the result is NOT proven exact (list overflow, fewer than k candidates while
+// more rows exist, or k-th exact score < theta + eps): the caller re-runs that query on the scan.
+__global__ void __launch_bounds__(512, 1)
+rescore_select_kernel(const float* __restrict__ x, int ld, int d, long long n, const float* __restrict__ q, int k, int kpad,
+                      const uint32_t* __restrict__ cand_ids, const int* __restrict__ cand_count, int cand_cap,
+                      const float* __restrict__ theta, float eps, uint32_t id_base, float* out_scores, long long* out_ids,
+                      uint64_t* out_keys, int* flags) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    uint64_t* keys = reinterpret_cast<uint64_t*>(smem_raw);     // [np]
+    const int qi = blockIdx.x;
+    const int raw_count = cand_count[qi];
+    const int count = raw_count < cand_cap ? raw_count : cand_cap;
+    int np = kpad;
+    while (np < count) np <<= 1;
+    float* sq = reinterpret_cast<float*>(keys + np);
+    const int qpad = (ld + 3) & ~3;
+#ifdef PSX_DEBUG_KERNELS
+    if (threadIdx.x == 0) printf("rescore: q=%d raw_count=%d count=%d np=%d theta=%g k=%d kpad=%d ld=%d d=%d\n", qi, raw_count, count, np, theta[qi], k, kpad, ld, d);
+#endif
+    for (int i = threadIdx.x; i < qpad; i += blockDim.x) sq[i] = i < d ? q[(size_t)qi * d + i] : 0.f;
+    for (int i = count + threadIdx.x; i < np; i += blockDim.x) keys[i] = 0ull;
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    const float4* q4 = reinterpret_cast<const float4*>(sq);
+    const int pieces = ld >> 2;
+    for (int c = warp; c < count; c += nwarps) {
+        const uint32_t row = cand_ids[(size_t)qi * cand_cap + c];
+#ifdef PSX_DEBUG_KERNELS
+        if (row >= n) {
+            if (lane == 0) printf("rescore: q=%d c=%d row=%u >= n=%lld (count %d raw %d)\n", qi, c, row, n, count, raw_count);
+            continue;
+        }
+#endif
+        const float4* xr = reinterpret_cast<const float4*>(x + (size_t)row * ld);
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        for (int pc = lane; pc < pieces; pc += 32) {
+            const float4 v = __ldg(xr + pc);
+            const float4 w = q4[pc];
+            a0 = fmaf(v.x, w.x, a0);
+            a1 = fmaf(v.y, w.y, a1);
+            a2 = fmaf(v.z, w.z, a2);
+            a3 = fmaf(v.w, w.w, a3);
+        }
+        float s = (a0 + a1) + (a2 + a3);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) keys[c] = make_key(s, id_base + row);
+    }
+    __syncthreads();
+#ifdef PSX_DEBUG_KERNELS
+    if (threadIdx.x == 0) printf("rescore: q=%d scored, key0=%llx\n", qi, (unsigned long long)keys[0]);
+#endif
+    block_bitonic_sort_desc(keys, np);
+#ifdef PSX_DEBUG_KERNELS
+    if (threadIdx.x == 0) printf("rescore: q=%d sorted, key0=%llx out_scores=%p out_ids=%p flags=%p\n", qi, (unsigned long long)keys[0], out_scores, out_ids, flags);
+#endif
+    const int kk = k;
+    block_emit_results(keys, kk, kpad, PSX_METRIC_IP, out_scores + (size_t)qi * k, out_ids + (size_t)qi * k,
+                       out_keys ? out_keys + (size_t)qi * kpad : nullptr);
+    if (threadIdx.x == 0) {
+        int bad = 0;
+        if (raw_count > cand_cap) bad = 1;                                   // list overflow: survivors were dropped
+        const long long need = n < k ? n : k;
+        if (count < need) bad = 2;                                           // threshold too tight
+        if (!bad && need > 0 && n > count) {
+            const float kth = key_score(keys[need - 1]);
+            if (!(kth >= theta[qi] + eps)) bad = 3;                          // proof obligation not met
+        }
+        flags[qi] = bad;
+    }
+}
+
+}  // namespace psx
