@@ -432,6 +432,59 @@ def run_extras(torch, _native, index, queries, rows, d, k, device, esize):
     for kk in (50, 500, 1333, 2048):
         ms = time_device_search(torch, index, q_ptrs, kk, None, 20)
         out[f"k={kk}"] = {"ms": ms, "qps": 1e3 / ms, "GBps": rows * d * esize / ms / 1e6}
+    if esize == 4:
+        out.update(run_batched(torch, _native, index, rows, d, k, device))
+    return out
+
+
+def run_batched(torch, _native, index, rows, d, k, device):
+    """BASELINE.json configs[2] shape of work: 256 queries at once on the tensor cores (tcgen05 TF32
+    GEMM, selection fused into the epilogue, exact fp32 re-score), on the resident corpus."""
+    out = {}
+    try:
+        tf32_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops"] / 2.0
+    except Exception:
+        tf32_peak = 1590.0 / 2.0
+    hbm_peak, _ = measured_peak()
+    gen = torch.Generator(device=device).manual_seed(QUERY_SEED + 1)
+    stream = torch.cuda.current_stream()
+    for nq in (256, 32):
+        q = torch.randn((nq, d), generator=gen, device=device)
+        q = (q / q.norm(dim=1, keepdim=True)).contiguous()
+        sc = torch.empty((nq, k), device=device)
+        ids = torch.empty((nq, k), dtype=torch.int64, device=device)
+        flags = torch.zeros((nq,), dtype=torch.int32, device=device)
+
+        def run():
+            index.search_batch_device(q.data_ptr(), nq, k, sc.data_ptr(), ids.data_ptr(), flags.data_ptr(), stream=stream.cuda_stream)
+
+        for _ in range(2):
+            run()
+        torch.cuda.synchronize()
+        steps = 5
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        for _ in range(steps):
+            run()
+        b.record(stream)
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b) / steps
+        flops = 2.0 * rows * d * nq
+        t_hbm = rows * d * 4 / (hbm_peak * 1e9) * 1e3
+        t_tc = flops / (tf32_peak * 1e12) * 1e3
+        # parity of the batch against the streaming scan, query by query (bit-identical by design)
+        Ds = torch.empty((4, k), device=device)
+        Is = torch.empty((4, k), dtype=torch.int64, device=device)
+        index.search_device(q.data_ptr(), 4, k, Ds.data_ptr(), Is.data_ptr(), 0, stream=stream.cuda_stream)
+        torch.cuda.synchronize()
+        ok = (flags[:4] == 0)
+        same = bool(((ids[:4] == Is) | ~ok[:, None]).all() and ((sc[:4] == Ds) | ~ok[:, None]).all())
+        out[f"batched/nq={nq}"] = {
+            "ms_per_batch": ms, "queries_per_s": nq / ms * 1e3, "effective_TFLOPs": flops / ms / 1e9,
+            "corpus_GBps": rows * d * 4 / ms / 1e6, "unproven_queries": int((flags != 0).sum()),
+            "roofline_frac": max(t_hbm, t_tc) / ms, "roofline_note": f"max(HBM {t_hbm:.3f} ms, TF32 {t_tc:.3f} ms at {tf32_peak:.0f} TFLOP/s = half the measured bf16 peak) / measured",
+            "bit_identical_to_scan": same,
+        }
     return out
 
 
