@@ -485,6 +485,36 @@ def run_batched(torch, _native, index, rows, d, k, device):
             "roofline_frac": max(t_hbm, t_tc) / ms, "roofline_note": f"max(HBM {t_hbm:.3f} ms, TF32 {t_tc:.3f} ms at {tf32_peak:.0f} TFLOP/s = half the measured bf16 peak) / measured",
             "bit_identical_to_scan": same,
         }
+        if nq == 256:
+            # rest of configs[2]: on-device hybrid fusion of the merged candidates with synthetic keyword
+            # scores (36-150 hits per query, half of them overlapping the vector hits, max score exactly 1.0)
+            from photo_search_engine_b200.fusion import hybrid_fuse
+
+            kw = 150
+            g2 = torch.Generator(device=device).manual_seed(11)
+            pick = torch.randint(0, k, (nq, kw), generator=g2, device=device)
+            overlap = torch.rand((nq, kw), generator=g2, device=device) < 0.5
+            rand_ids = torch.randint(0, rows, (nq, kw), generator=g2, device=device)
+            kw_ids = torch.where(overlap, torch.gather(ids, 1, pick), rand_ids)
+            kw_ids = torch.where(torch.arange(kw, device=device)[None, :] < 36 + (torch.arange(nq, device=device)[:, None] % 115), kw_ids,
+                                 torch.full_like(kw_ids, -1))
+            # duplicates inside one query's keyword list are dropped (an id appears once in ES results)
+            srt, order = torch.sort(kw_ids, dim=1)
+            dup = torch.zeros_like(srt, dtype=torch.bool)
+            dup[:, 1:] = (srt[:, 1:] == srt[:, :-1]) & (srt[:, 1:] >= 0)
+            kw_ids = torch.where(dup, torch.full_like(srt, -1), srt)
+            u = 1.0 - torch.rand((nq, kw), generator=g2, device=device, dtype=torch.float64)
+            kw_scores = u / u.max(dim=1, keepdim=True).values
+            for _ in range(2):
+                fused = hybrid_fuse(sc, ids, kw_ids, kw_scores)
+            torch.cuda.synchronize()
+            a.record(stream)
+            for _ in range(10):
+                fused = hybrid_fuse(sc, ids, kw_ids, kw_scores)
+            b.record(stream)
+            torch.cuda.synchronize()
+            out["batched/nq=256"]["hybrid_fusion_ms"] = a.elapsed_time(b) / 10
+            out["batched/nq=256"]["hybrid_fusion_mean_results"] = float(fused[4].float().mean())
     return out
 
 

@@ -163,6 +163,21 @@ int psx_batch_stats(psx_index* h, int64_t* queries, int64_t* fallbacks);
 int psx_merge_keys_device(int device, const uint64_t* keys_dev, int64_t nq, int64_t nlists, int64_t k,
                           int metric, float* out_scores_dev, int64_t* out_ids_dev, void* stream);
 
+/* On-device form of the numeric core of Searcher._hybrid_search (core/searcher.py:893-986) and
+ * Searcher._distance_to_score (core/searcher.py:605-625) over the merged vector candidates
+ * (vec_dist/vec_ids [nq][kv], id -1 = empty) and the keyword hits (kw_ids/kw_scores [nq][kw], scores
+ * in [0,1] as utils/keyword_store.py:270-279 normalises them).  Python-float (IEEE double)
+ * arithmetic and round(x, 6) are reproduced bit for bit.  *_boost are the per-hit metadata
+ * boosts of core/searcher.py:435-449 (NULL = 1.0).  `keyword_filtered` = the Elasticsearch filter
+ * branch was taken (es_filtered_paths is not None).  Outputs, per query, kv+kw slots sorted by
+ * fused score descending then id ascending: ids (-1 beyond out_count), fused / vector / keyword
+ * scores (rounded to 6 places).  kv + kw <= 2048. */
+int psx_hybrid_fuse_device(int device, int64_t nq, int64_t kv, const float* vec_dist_dev, const int64_t* vec_ids_dev,
+                           const double* vec_boost_dev, int64_t kw, const int64_t* kw_ids_dev, const double* kw_scores_dev,
+                           const double* kw_boost_dev, double vector_weight, double keyword_weight, int metric,
+                           int allow_keyword_only, int keyword_filtered, int64_t* out_ids_dev, double* out_fused_dev,
+                           double* out_vscore_dev, double* out_kscore_dev, int* out_count_dev, void* stream);
+
 /* Replaces index.reconstruct(i) (utils/vector_store.py:207): the stored row as fp32. */
 int psx_reconstruct(psx_index* h, int64_t id, float* out);
 /* Replaces the flat payload of faiss.write_index (utils/vector_store.py:234): rows

@@ -63,6 +63,8 @@ _SIGNATURES = [
     ("psx_search_batch_device", C.c_int, [_P, _P, C.c_int64, C.c_int64, C.c_float, C.c_uint32, _P, _P, _P, _P, _P]),
     ("psx_batch_stats", C.c_int, [_P, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     ("psx_merge_keys_device", C.c_int, [C.c_int, _P, C.c_int64, C.c_int64, C.c_int64, C.c_int, _P, _P, _P]),
+    ("psx_hybrid_fuse_device", C.c_int, [C.c_int, C.c_int64, C.c_int64, _P, _P, _P, C.c_int64, _P, _P, _P, C.c_double, C.c_double,
+                                          C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P, _P]),
     ("psx_reconstruct", C.c_int, [_P, C.c_int64, _P]),
     ("psx_read_rows", C.c_int, [_P, C.c_int64, C.c_int64, _P]),
     ("psx_storage_device", C.c_int, [_P, C.POINTER(_P), C.POINTER(C.c_int64), C.POINTER(C.c_int)]),

@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "psx_aux.cuh"
+#include "psx_fuse.cuh"
 #include "psx_gemm.cuh"
 #include "psx_scan.cuh"
 
@@ -1016,6 +1017,54 @@ extern "C" int psx_storage_device(psx_index* h, const void** rows_dev, int64_t* 
     if (rows_dev) *rows_dev = h->x;
     if (ld_elems) *ld_elems = h->ld;
     if (store_dtype) *store_dtype = h->dtype;
+    return PSX_OK;
+}
+
+extern "C" int psx_hybrid_fuse_device(int device, int64_t nq, int64_t kv, const float* vec_dist_dev, const int64_t* vec_ids_dev,
+                                      const double* vec_boost_dev, int64_t kw, const int64_t* kw_ids_dev,
+                                      const double* kw_scores_dev, const double* kw_boost_dev, double vector_weight,
+                                      double keyword_weight, int metric, int allow_keyword_only, int keyword_filtered,
+                                      int64_t* out_ids_dev, double* out_fused_dev, double* out_vscore_dev,
+                                      double* out_kscore_dev, int* out_count_dev, void* stream) {
+    if (nq < 0 || kv < 0 || kw < 0 || kv + kw < 1 || kv + kw > FUSE_MAX_ENTRIES)
+        return fail(PSX_ERR_INVALID, "hybrid fusion needs 1 <= kv + kw <= %d", FUSE_MAX_ENTRIES);
+    if ((kv && (!vec_dist_dev || !vec_ids_dev)) || (kw && (!kw_ids_dev || !kw_scores_dev)) || !out_ids_dev || !out_fused_dev ||
+        !out_vscore_dev || !out_kscore_dev || !out_count_dev)
+        return fail(PSX_ERR_INVALID, "null pointer passed to psx_hybrid_fuse_device");
+    if (nq == 0) return PSX_OK;
+    DeviceGuard g(device);
+    if (!g.ok) return fail(PSX_ERR_CUDA, "cudaSetDevice(%d) failed", device);
+    FuseParams p;
+    p.vec_dist = vec_dist_dev;
+    p.vec_ids = (const long long*)vec_ids_dev;
+    p.vec_boost = vec_boost_dev;
+    p.kw_ids = (const long long*)kw_ids_dev;
+    p.kw_scores = kw_scores_dev;
+    p.kw_boost = kw_boost_dev;
+    p.out_ids = (long long*)out_ids_dev;
+    p.out_fused = out_fused_dev;
+    p.out_vscore = out_vscore_dev;
+    p.out_kscore = out_kscore_dev;
+    p.out_count = out_count_dev;
+    p.kv = (int)kv;
+    p.kw = (int)kw;
+    p.wv = vector_weight;
+    p.wk = keyword_weight;
+    p.metric = metric;
+    p.allow_keyword_only = allow_keyword_only;
+    p.keyword_filtered = keyword_filtered;
+    const int E = (int)(kv + kw);
+    int np = 64;
+    while (np < E) np <<= 1;
+    const size_t smem = (size_t)np * 8 + (size_t)E * 24 + (size_t)kv * 4 + 16;
+    static std::atomic<bool> ready[64];
+    if (device >= 0 && device < 64 && !ready[device].load()) {
+        CU(cudaFuncSetAttribute(hybrid_fuse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PSX_SMEM_LIMIT));
+        ready[device].store(true);
+    }
+    hybrid_fuse_kernel<<<(unsigned)nq, 256, smem, (cudaStream_t)stream>>>(p);
+    g_launches++;
+    CU(cudaGetLastError());
     return PSX_OK;
 }
 
