@@ -177,7 +177,7 @@ def run_reference(args):
         "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -370,7 +370,7 @@ def run_ours(args):
             line["parity_spot_check"] = parity
         if extras:
             line["extras"] = extras
-        print(json.dumps(line), flush=True)
+        emit(line)
     index.close()
     if world > 1:
         dist.destroy_process_group()
@@ -518,8 +518,22 @@ def run_batched(torch, _native, index, rows, d, k, device):
     return out
 
 
+_REAL_STDOUT = None
+
+
+def emit(line: dict) -> None:
+    """The ONE JSON line goes to the process' real stdout; everything else any library prints
+    (NCCL's version banner, torch warnings) was redirected to stderr in main()."""
+    data = (json.dumps(line) + "\n").encode()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, data)
+
+
 def main():
+    global _REAL_STDOUT
     args = parse_args()
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)  # fd 1 -> stderr for the rest of the run (C libraries included)
     if args.impl == "reference":
         run_reference(args)
     else:
