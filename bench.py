@@ -50,6 +50,8 @@ def parse_args():
     ap.add_argument("--warps", type=int, default=0)
     ap.add_argument("--stages", type=int, default=0)
     ap.add_argument("--ctas-per-sm", type=int, default=0)
+    ap.add_argument("--exchange", default="auto", choices=["auto", "p2p", "nccl"],
+                    help="N>1: candidate exchange fused into the kernels over NVLink peer mappings (p2p) or NCCL all-gather")
     return ap.parse_args()
 
 
@@ -234,7 +236,7 @@ def run_ours(args):
         if val:
             index.set_tunable(key, val)
     build_corpus(torch, index, lo, hi - lo, d, device)
-    sharded = ShardedIndex(index, lo)
+    sharded = ShardedIndex(index, lo, exchange=args.exchange)
     queries = make_queries(torch, N_QUERIES, d, device)
     queries_host = queries.cpu().numpy()
 
@@ -265,6 +267,13 @@ def run_ours(args):
             index.search_device(qptr, 1, k, b["scores"].data_ptr(), b["ids"].data_ptr(), b["mine"].data_ptr(),
                                 id_base=lo, stream=stream.cuda_stream)
             ev[2 * i + 2].record(stream)
+        elif sharded.exchange == "p2p":  # scan publishes its keys into every peer's buffer; wait + merge kernel
+            sharded._seq += 1
+            index.search_exchange_device(qptr, k, rank, world, sharded._xchg_bases, sharded._seq, 0, 0, id_base=lo,
+                                         stream=stream.cuda_stream, phases=1)
+            ev[2 * i + 2].record(stream)
+            index.search_exchange_device(0, k, rank, world, sharded._xchg_bases, sharded._seq, b["scores"].data_ptr(),
+                                         b["ids"].data_ptr(), stream=stream.cuda_stream, phases=2)
         else:  # keys only, then ONE all-gather and the integer merge on every rank
             index.search_device(qptr, 1, k, 0, 0, b["mine"].data_ptr(), id_base=lo, stream=stream.cuda_stream)
             ev[2 * i + 2].record(stream)
@@ -354,7 +363,9 @@ def run_ours(args):
                 "rows": rows, "dim": d, "k": k, "rows_per_gpu": local_rows, "parallelism": f"row-shard x{world}",
                 "l2_policy": "inputs larger than L2 (corpus shard >> 126 MB), no flush needed",
                 "scanned_GBps_aggregate": rows * d * esize / (ms_per_step * 1e-3) / 1e9,
-                "exchange": "all-gather of k 64-bit keys per rank + integer merge" if world > 1 else "none",
+                "exchange": ("none" if world == 1 else
+                             "fused: last CTA of the scan stores its k keys into every peer's buffer over NVLink + flag; one-CTA wait+merge kernel"
+                             if sharded.exchange == "p2p" else "NCCL all-gather of k 64-bit keys per rank + integer merge kernel"),
             },
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": (traffic or {}).get("dram_bytes_per_launch"),

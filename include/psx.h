@@ -163,6 +163,21 @@ int psx_batch_stats(psx_index* h, int64_t* queries, int64_t* fallbacks);
 int psx_merge_keys_device(int device, const uint64_t* keys_dev, int64_t nq, int64_t nlists, int64_t k,
                           int metric, float* out_scores_dev, int64_t* out_ids_dev, void* stream);
 
+/* Row-sharded search with the exchange fused into the kernels (no collective library call on the
+ * query path): the scan's last CTA stores this shard's k keys straight into every rank's receive
+ * buffer over NVLink peer mappings and raises a per-source flag there; a one-CTA kernel on every
+ * rank waits for `world` flags and selects the global top-k.  `peer_bases` is a HOST array of
+ * `world` device addresses: the exchange buffer of every rank as mapped into THIS process
+ * (psx_exchange_bytes() bytes each, zero-initialised once, e.g. torch symmetric memory or CUDA IPC);
+ * peer_bases[rank] is this rank's own buffer.  `seq` >= 1 must increase by one per query and be
+ * the same on all ranks; every rank must issue the same sequence of calls.  world <= 8.
+ * `phases`: 1 = scan + publish, 2 = wait + merge, 3 = both (the normal call; the split exists so
+ * that several ranks can be emulated on one GPU without kernels waiting on one another). */
+int64_t psx_exchange_bytes(void);
+int psx_search_exchange_device(psx_index* h, const float* q_dev, int64_t k, const psx_filter* filter, uint32_t id_base,
+                               int rank, int world, const uint64_t* peer_bases, uint32_t seq, int phases,
+                               float* out_scores_dev, int64_t* out_ids_dev, void* stream);
+
 /* On-device form of the numeric core of Searcher._hybrid_search (core/searcher.py:893-986) and
  * Searcher._distance_to_score (core/searcher.py:605-625) over the merged vector candidates
  * (vec_dist/vec_ids [nq][kv], id -1 = empty) and the keyword hits (kw_ids/kw_scores [nq][kw], scores

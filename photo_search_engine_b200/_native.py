@@ -63,6 +63,9 @@ _SIGNATURES = [
     ("psx_search_batch_device", C.c_int, [_P, _P, C.c_int64, C.c_int64, C.c_float, C.c_uint32, _P, _P, _P, _P, _P]),
     ("psx_batch_stats", C.c_int, [_P, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     ("psx_merge_keys_device", C.c_int, [C.c_int, _P, C.c_int64, C.c_int64, C.c_int64, C.c_int, _P, _P, _P]),
+    ("psx_exchange_bytes", C.c_int64, []),
+    ("psx_search_exchange_device", C.c_int, [_P, _P, C.c_int64, C.POINTER(PsxFilter), C.c_uint32, C.c_int, C.c_int, _P, C.c_uint32,
+                                              C.c_int, _P, _P, _P]),
     ("psx_hybrid_fuse_device", C.c_int, [C.c_int, C.c_int64, C.c_int64, _P, _P, _P, C.c_int64, _P, _P, _P, C.c_double, C.c_double,
                                           C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P, _P]),
     ("psx_reconstruct", C.c_int, [_P, C.c_int64, _P]),
@@ -193,6 +196,14 @@ class NativeIndex:
         check(self._lib.psx_search_device(self._h, q_ptr, int(nq), int(k), fp, int(id_base), out_scores_ptr or None,
                                           out_ids_ptr or None, out_keys_ptr or None, stream or None))
 
+    def search_exchange_device(self, q_ptr: int, k: int, rank: int, world: int, peer_bases: np.ndarray, seq: int,
+                               out_scores_ptr: int, out_ids_ptr: int, flt: Optional[PsxFilter] = None, id_base: int = 0,
+                               stream: int = 0, phases: int = 3) -> None:
+        fp = C.byref(flt) if flt is not None else None
+        check(self._lib.psx_search_exchange_device(self._h, q_ptr or None, int(k), fp, int(id_base), int(rank), int(world),
+                                                   peer_bases.ctypes.data, int(seq), int(phases), out_scores_ptr or None,
+                                                   out_ids_ptr or None, stream or None))
+
     def search_batch_device(self, q_ptr: int, nq: int, k: int, out_scores_ptr: int, out_ids_ptr: int, flags_ptr: int,
                             out_keys_ptr: int = 0, qnorm_max: float = 1.0, id_base: int = 0, stream: int = 0) -> None:
         check(self._lib.psx_search_batch_device(self._h, q_ptr, int(nq), int(k), float(qnorm_max), int(id_base), out_scores_ptr,
@@ -230,6 +241,10 @@ def merge_keys_device(device: int, keys_ptr: int, nq: int, nlists: int, k: int, 
                       out_ids_ptr: int, stream: int = 0) -> None:
     check(load_library().psx_merge_keys_device(int(device), keys_ptr, int(nq), int(nlists), int(k), int(metric),
                                                out_scores_ptr, out_ids_ptr, stream or None))
+
+
+def exchange_bytes() -> int:
+    return int(load_library().psx_exchange_bytes())
 
 
 def launch_count() -> int:

@@ -512,8 +512,16 @@ static int launch_scan_variant(int device, int dtype, int metric, int ppl, bool 
                                    : launch_by_shape<__nv_bfloat16, PSX_METRIC_L2>(device, ppl, qreg, plan, st);
 }
 
+struct XchgArgs {
+    int world, rank;
+    uint32_t seq;
+    const uint64_t* bases;  // host array [world]: base address of every rank's exchange buffer
+};
+static size_t xchg_flag_offset() { return (size_t)2 * PSX_XCHG_MAX_WORLD * PSX_K_PASS_MAX * sizeof(uint64_t); }
+
 static int launch_scan(psx_index* h, const float* q_dev, int k, const psx_filter* f, uint32_t id_base,
-                       const uint64_t* ceil_ptr, float* out_scores, long long* out_ids, uint64_t* out_keys, cudaStream_t st) {
+                       const uint64_t* ceil_ptr, float* out_scores, long long* out_ids, uint64_t* out_keys, cudaStream_t st,
+                       const XchgArgs* xa = nullptr) {
     ScanPlan plan;
     int rc = plan_scan(h, k, plan);
     if (rc) return rc;
@@ -543,6 +551,15 @@ static int launch_scan(psx_index* h, const float* q_dev, int k, const psx_filter
         p.has_filter = 1;
         p.attrs = h->attrs;
         p.f = *f;
+    }
+    if (xa) {
+        p.xchg_world = xa->world;
+        p.xchg_rank = xa->rank;
+        p.xchg_seq = xa->seq;
+        for (int r = 0; r < xa->world; ++r) {
+            p.xchg_recv[r] = (uint64_t*)(uintptr_t)xa->bases[r];
+            p.xchg_flag[r] = (uint32_t*)(uintptr_t)(xa->bases[r] + xchg_flag_offset());
+        }
     }
     const int ppr = (int)(h->row_bytes >> 4);  // 16-byte pieces per row
     int ppl = 0;
@@ -754,6 +771,45 @@ extern "C" int psx_search_device(psx_index* h, const float* q_dev, int64_t nq, i
                          out_keys_dev ? out_keys_dev + qi * kpad : nullptr, st);
         if (rc) return rc;
     }
+    return leave_stream(h, st);
+}
+
+extern "C" int64_t psx_exchange_bytes(void) {
+    return (int64_t)(xchg_flag_offset() + 2 * PSX_XCHG_MAX_WORLD * sizeof(uint32_t) + 192);
+}
+
+extern "C" int psx_search_exchange_device(psx_index* h, const float* q_dev, int64_t k, const psx_filter* filter, uint32_t id_base,
+                                          int rank, int world, const uint64_t* peer_bases, uint32_t seq, int phases,
+                                          float* out_scores_dev, int64_t* out_ids_dev, void* stream) {
+    if (!h || !peer_bases || (!(phases & 1) && !(phases & 2)) || ((phases & 1) && !q_dev) ||
+        ((phases & 2) && (!out_scores_dev || !out_ids_dev)))
+        return fail(PSX_ERR_INVALID, "bad arguments to psx_search_exchange_device");
+    if (world < 1 || world > PSX_XCHG_MAX_WORLD || rank < 0 || rank >= world || seq == 0)
+        return fail(PSX_ERR_INVALID, "exchange needs 1 <= world <= %d, 0 <= rank < world, seq >= 1", PSX_XCHG_MAX_WORLD);
+    if (k < 1 || k > PSX_K_PASS_MAX) return fail(PSX_ERR_INVALID, "k=%lld not in [1,%d]", (long long)k, PSX_K_PASS_MAX);
+    std::lock_guard<std::mutex> lk(h->mu);
+    DeviceGuard g(h->device);
+    int rc = flush_pending(h);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    if ((rc = enter_stream(h, st))) return rc;
+    XchgArgs xa{world, rank, seq, peer_bases};
+    if ((phases & 1) && (rc = launch_scan(h, q_dev, (int)k, filter, id_base, nullptr, nullptr, nullptr, nullptr, st, &xa))) return rc;
+    if (!(phases & 2)) return leave_stream(h, st);
+    const int kpad = (int)psx_kpad(k);
+    int np = kpad;
+    while (np < world * kpad) np <<= 1;
+    const size_t smem = (size_t)np * 8;
+    static std::atomic<bool> ready[64];
+    if (h->device < 64 && !ready[h->device].load()) {
+        CU(cudaFuncSetAttribute(merge_wait_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PSX_SMEM_LIMIT));
+        ready[h->device].store(true);
+    }
+    const uint64_t mine = peer_bases[rank];
+    merge_wait_kernel<<<1, 256, smem, st>>>((const uint64_t*)(uintptr_t)mine, (const uint32_t*)(uintptr_t)(mine + xchg_flag_offset()), world,
+                                           seq, (int)k, kpad, np, h->metric, out_scores_dev, (long long*)out_ids_dev);
+    g_launches++;
+    CU(cudaGetLastError());
     return leave_stream(h, st);
 }
 

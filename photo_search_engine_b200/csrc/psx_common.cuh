@@ -11,6 +11,7 @@
 #define PSX_MAX_WARPS 16
 #define PSX_MAX_THREADS (PSX_MAX_WARPS * 32)
 #define PSX_SMEM_LIMIT (227 * 1024)
+#define PSX_XCHG_MAX_WORLD 8
 
 namespace psx {
 

@@ -52,7 +52,25 @@ struct ScanParams {
     int has_filter;
     uint32_t id_base;
     psx_filter f;
+    // fused cross-GPU exchange (row shards): the last CTA stores this shard's k keys straight into
+    // every peer's receive buffer over NVLink and raises a per-source flag there.  world 0 = off.
+    int xchg_world, xchg_rank;
+    uint32_t xchg_seq;
+    uint64_t* xchg_recv[PSX_XCHG_MAX_WORLD];   // peer p: [2 parities][world][PSX_K_PASS_MAX] keys
+    uint32_t* xchg_flag[PSX_XCHG_MAX_WORLD];   // peer p: [2 parities][PSX_XCHG_MAX_WORLD] sequence numbers
 };
+
+__device__ __forceinline__ void st_relaxed_sys_u64(uint64_t* p, uint64_t v) {
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ void st_release_sys_u32(uint32_t* p, uint32_t v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys_u32(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
 
 __device__ __forceinline__ bool attr_pass(uint64_t a, const psx_filter& f) {
     const uint32_t fl = f.flags;
@@ -429,6 +447,53 @@ __global__ void __launch_bounds__(PSX_MAX_THREADS, 1) scan_topk_kernel(const Sca
     block_select_from_lists(p.lists, gridDim.x, p.k, p.kpad, buf, (int)((size_t)W * S * PSX_SLOT_BYTES / 8));
     block_emit_results(buf, p.k, p.kpad, p.metric, p.out_scores, p.out_ids, p.out_keys);
     if (threadIdx.x == 0) *p.counter = 0u;
+    if (p.xchg_world > 0) {
+        // K4 fused: publish this shard's list to every rank (NVLink P2P stores), then the flags
+        const int slot = (int)(p.xchg_seq & 1u);
+        for (int peer = 0; peer < p.xchg_world; ++peer) {
+            uint64_t* dst = p.xchg_recv[peer] + ((size_t)slot * p.xchg_world + p.xchg_rank) * PSX_K_PASS_MAX;
+            for (int i = threadIdx.x; i < p.kpad; i += blockDim.x) st_relaxed_sys_u64(dst + i, i < p.k ? buf[i] : 0ull);
+        }
+        __threadfence_system();
+        __syncthreads();
+        if ((int)threadIdx.x < p.xchg_world)
+            st_release_sys_u32(p.xchg_flag[threadIdx.x] + slot * PSX_XCHG_MAX_WORLD + p.xchg_rank, p.xchg_seq);
+    }
+}
+
+// K4 fused, receiving side: wait until every rank's list for query `seq` has landed in this GPU's
+// receive buffer, then select the global top-k.  One CTA.  The spin is bounded (a dead peer becomes
+// a trap, not a hung GPU).
+__global__ void __launch_bounds__(256, 1)
+merge_wait_kernel(const uint64_t* __restrict__ recv, const uint32_t* flags, int world, uint32_t seq, int k, int kpad, int cap_keys,
+                  int metric, float* out_scores, long long* out_ids) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    uint64_t* buf = reinterpret_cast<uint64_t*>(smem_raw);
+    const int slot = (int)(seq & 1u);
+    if ((int)threadIdx.x < world) {
+        const uint32_t* f = flags + slot * PSX_XCHG_MAX_WORLD + threadIdx.x;
+        unsigned long long spins = 0;
+        while (ld_acquire_sys_u32(f) != seq) {
+            __nanosleep(64);
+            if (++spins > (1ull << 26)) __trap();
+        }
+    }
+    __syncthreads();
+    const uint64_t* lists = recv + (size_t)slot * world * PSX_K_PASS_MAX;
+    // lists are PSX_K_PASS_MAX apart; compact them to a kpad stride view by reading through an index map
+    // (block_select_from_lists expects stride kpad): gather the heads into shared memory first
+    const int tid = threadIdx.x, nt = blockDim.x;
+    int np = kpad;
+    while (np < world * kpad) np <<= 1;
+    for (int idx = tid; idx < np; idx += nt) {
+        uint64_t v = 0ull;
+        if (idx < world * kpad) v = ld_cg_u64(lists + (size_t)(idx / kpad) * PSX_K_PASS_MAX + (idx % kpad));
+        buf[idx] = v;
+    }
+    __syncthreads();
+    (void)cap_keys;
+    block_bitonic_sort_desc(buf, np);
+    block_emit_results(buf, k, kpad, metric, out_scores, out_ids, nullptr);
 }
 
 // Standalone merge (K4 final merge of all-gathered shard lists): one CTA per query.

@@ -33,7 +33,7 @@ class ShardedIndex:
     """
 
     def __init__(self, local, row0: int, k_max: int = 128, group=None,
-                 local_search: Optional[Callable] = None, merge: Optional[Callable] = None) -> None:
+                 local_search: Optional[Callable] = None, merge: Optional[Callable] = None, exchange: str = "auto") -> None:
         import torch
         import torch.distributed as dist
 
@@ -47,6 +47,32 @@ class ShardedIndex:
         self._merge = merge
         self.device = torch.device("cuda", local.device) if local_search is None else torch.device("cpu")
         self._bufs = {}
+        # exchange: "p2p" = fused into the kernels over NVLink peer mappings (torch symmetric memory
+        # provides the mappings), "nccl" = all_gather_into_tensor + merge kernel, "auto" = p2p if it can
+        # be set up.  The CPU (gloo) test path always uses the collective.
+        self.exchange = "nccl"
+        self._seq = 0
+        if local_search is None and self.world > 1 and exchange in ("auto", "p2p"):
+            try:
+                self._setup_p2p()
+                self.exchange = "p2p"
+            except Exception as exc:  # pragma: no cover - depends on the box
+                if exchange == "p2p":
+                    raise
+                self._p2p_error = repr(exc)
+
+    def _setup_p2p(self) -> None:
+        import torch.distributed._symmetric_memory as symm
+
+        t, dist = self.torch, self.dist
+        nwords = (_native.exchange_bytes() + 7) // 8
+        buf = symm.empty(nwords, dtype=t.int64, device=self.device)
+        handle = symm.rendezvous(buf, self.group if self.group is not None else dist.group.WORLD)
+        buf.zero_()
+        t.cuda.synchronize(self.device)
+        dist.barrier(group=self.group)
+        self._xchg_buf, self._xchg_handle = buf, handle
+        self._xchg_bases = np.array([int(p) for p in handle.buffer_ptrs], dtype=np.uint64)
 
     # -- buffers are cached per (nq, k): the steady-state query allocates nothing ----------------
     def _buffers(self, nq: int, k: int):
@@ -85,6 +111,14 @@ class ShardedIndex:
                 # one shard: the scan's fused cross-CTA merge already emits the final result
                 self.local.search_device(q_dev.data_ptr(), nq, k, b["scores"].data_ptr(), b["ids"].data_ptr(), 0,
                                          flt=flt, id_base=self.row0, stream=stream)
+                return b["scores"], b["ids"]
+            if self.exchange == "p2p":
+                d = self.local.d
+                for qi in range(nq):  # one fused scan+publish / wait+merge pair per query
+                    self._seq += 1
+                    self.local.search_exchange_device(q_dev.data_ptr() + qi * d * 4, k, self.rank, self.world, self._xchg_bases,
+                                                      self._seq, b["scores"].data_ptr() + qi * k * 4, b["ids"].data_ptr() + qi * k * 8,
+                                                      flt=flt, id_base=self.row0, stream=stream)
                 return b["scores"], b["ids"]
             self.local.search_device(q_dev.data_ptr(), nq, k, 0, 0, b["mine"].data_ptr(), flt=flt,
                                      id_base=self.row0, stream=stream)

@@ -414,6 +414,45 @@ def test_device_api_and_shard_merge():
     whole.close()
 
 
+def test_fused_exchange_emulated_ranks():
+    """K4 fused exchange with three ranks emulated on ONE GPU: every shard's scan publishes its keys
+    into all three receive buffers (phase 1), then every rank's wait+merge runs (phase 2) -- phases
+    are issued in an order in which no kernel waits for a later launch.  Result must equal the
+    single-index result bit for bit, on every rank, for consecutive queries (both buffer parities)."""
+    import torch
+
+    n, d, k = 40000, 256, 100
+    rng = np.random.default_rng(23)
+    x = unit_rows(rng, n, d)
+    x[30000] = x[5]
+    q = unit_rows(rng, 3, d)
+    q[0] = x[5]
+    whole = make_index(x)
+    Dw, Iw = whole.search(q, k)
+    bounds = [0, 13000, 13001, n]
+    world = 3
+    shards = [make_index(x[bounds[r] : bounds[r + 1]]) for r in range(world)]
+    nwords = (N().exchange_bytes() + 7) // 8
+    bufs = [torch.zeros(nwords, dtype=torch.int64, device="cuda") for _ in range(world)]
+    bases = np.array([b.data_ptr() for b in bufs], dtype=np.uint64)
+    qd = torch.from_numpy(q).cuda()
+    stream = torch.cuda.current_stream().cuda_stream
+    for seq in range(1, 4):  # three consecutive queries
+        qptr = qd.data_ptr() + (seq - 1) * d * 4
+        for r in range(world):
+            shards[r].search_exchange_device(qptr, k, r, world, bases, seq, 0, 0, id_base=bounds[r], stream=stream, phases=1)
+        for r in range(world):
+            sc = torch.empty((1, k), dtype=torch.float32, device="cuda")
+            ids = torch.empty((1, k), dtype=torch.int64, device="cuda")
+            shards[r].search_exchange_device(0, k, r, world, bases, seq, sc.data_ptr(), ids.data_ptr(), stream=stream, phases=2)
+            torch.cuda.synchronize()
+            assert np.array_equal(ids.cpu().numpy()[0], Iw[seq - 1]) and np.array_equal(sc.cpu().numpy()[0], Dw[seq - 1]), (seq, r)
+    assert Iw[0, 0] == 5 and Iw[0, 1] == 30000
+    for sh in shards:
+        sh.close()
+    whole.close()
+
+
 def test_full_size_properties_1m_x_1024():
     """BASELINE config 2 size, generated on the device.  Checked through size-independent
     properties: planted neighbours are found at the right ranks, results equal a torch fp32
