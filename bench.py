@@ -445,6 +445,58 @@ def run_extras(torch, _native, index, queries, rows, d, k, device, esize):
         out[f"k={kk}"] = {"ms": ms, "qps": 1e3 / ms, "GBps": rows * d * esize / ms / 1e6}
     if esize == 4:
         out.update(run_batched(torch, _native, index, rows, d, k, device))
+        try:
+            out.update(run_bf16_shard(torch, _native, device))
+        except Exception as exc:  # never let a secondary configuration kill the bench line
+            out["bf16_shard/error"] = repr(exc)[:200]
+    return out
+
+
+def run_bf16_shard(torch, _native, device):
+    """One GPU's share of BASELINE.json configs[4] (100M x 768 bf16 over 8 GPUs = 12.5M rows per GPU):
+    image -> image search by stored row id on bf16 storage (fp32 accumulate), recall@100 against the same
+    search on the fp32 master rows."""
+    from photo_search_engine_b200.sharded import ShardedIndex
+
+    rows, d, k, nq = 12_500_000, 768, 100, 32
+    free, _total = torch.cuda.mem_get_info()
+    if free < rows * d * 6 * 1.15:
+        return {"bf16_shard/skipped": "not enough free HBM for the fp32 master next to the bf16 rows"}
+    lo_p = _native.NativeIndex(d, _native.METRIC_IP, _native.STORE_BF16, device.index or 0)
+    hi_p = _native.NativeIndex(d, _native.METRIC_IP, _native.STORE_F32, device.index or 0)
+    lo_p.reserve(rows)
+    hi_p.reserve(rows)
+    done = 0
+    st = torch.cuda.current_stream().cuda_stream
+    while done < rows:
+        take = min(CHUNK, rows - done)
+        gen = torch.Generator(device=device).manual_seed(CORPUS_SEED + 1000 + done // CHUNK)
+        blk = torch.randn((take, d), generator=gen, device=device, dtype=torch.float32)
+        blk = (blk / blk.norm(dim=1, keepdim=True)).contiguous()
+        lo_p.add_device(blk.data_ptr(), take, stream=st)
+        hi_p.add_device(blk.data_ptr(), take, stream=st)
+        done += take
+        del blk
+    lo_s, hi_s = ShardedIndex(lo_p, 0), ShardedIndex(hi_p, 0)
+    gen = torch.Generator(device=device).manual_seed(99)
+    ids = torch.randint(0, rows, (nq,), generator=gen, device=device).tolist()
+    hits = 0
+    for gid in ids:
+        _, a = lo_s.search_by_id(gid, k)
+        _, b = hi_s.search_by_id(gid, k)
+        hits += len(set(a.tolist()) & set(b.tolist()))
+    recall = hits / (nq * k)
+    q = torch.randn((16, d), generator=gen, device=device)
+    q = (q / q.norm(dim=1, keepdim=True)).contiguous()
+    ms = time_device_search(torch, lo_p, [q[i: i + 1].data_ptr() for i in range(16)], k, None, 30)
+    peak, _ = measured_peak()
+    out = {"bf16_shard/12.5Mx768": {"ms": ms, "qps_per_gpu": 1e3 / ms, "GBps": rows * d * 2 / ms / 1e6,
+                                    "frac_of_peak": rows * d * 2 / ms / 1e6 / peak, "recall_at_100_vs_fp32": recall,
+                                    "queries_for_recall": nq,
+                                    "note": "query = stored row (by id), self excluded; uniform random unit vectors are the worst case "
+                                            "for bf16 (score gaps ~ quantisation noise)"}}
+    lo_p.close()
+    hi_p.close()
     return out
 
 

@@ -73,6 +73,7 @@ struct psx_index {
     bool has_last = false;
     int sm_count = 148;
     int warps = 16, stages = 2, ctas_per_sm = 1;
+    bool stages_auto = true;
 
     uint64_t* lists = nullptr;  // [grid][kpad]
     size_t lists_cap = 0;
@@ -459,6 +460,8 @@ static int plan_scan(psx_index* h, int k, ScanPlan& plan) {
     // co-resident CTAs share the SM's 228 KB (1 KB per CTA is reserved by the driver)
     const size_t limit = h->ctas_per_sm <= 1 ? (size_t)PSX_SMEM_LIMIT : (size_t)(228 * 1024) / h->ctas_per_sm - 1024;
     int S = h->stages;
+    // short rows leave part of every 4 KB slot unused: keep the bytes in flight up with a third stage
+    if (h->stages_auto && p.cpr == 1 && (size_t)p.rps * h->row_bytes * 5 < (size_t)PSX_SLOT_BYTES * 4) S = 3;
     while (S > 2 && smem_for(S) > limit) --S;
     // the merge reuses the ring: it must hold at least two lists
     while ((size_t)W * S * PSX_SLOT_BYTES / 8 < (size_t)2 * p.kpad && smem_for(S + 1) <= PSX_SMEM_LIMIT) ++S;
@@ -1138,6 +1141,7 @@ extern "C" int psx_set_tunable(psx_index* h, const char* key, int value) {
         h->warps = value <= 0 ? 16 : std::min(value, PSX_MAX_WARPS);
     } else if (!strcmp(key, "stages")) {
         h->stages = value <= 0 ? 2 : std::max(2, std::min(value, 12));
+        h->stages_auto = value <= 0;
     } else if (!strcmp(key, "ctas_per_sm")) {
         h->ctas_per_sm = value <= 0 ? 1 : std::min(value, 8);
     } else if (!strcmp(key, "batch_min")) {  // smallest nq sent to the tensor-core path; 0 disables it

@@ -376,12 +376,23 @@ __global__ void __launch_bounds__(PSX_MAX_THREADS, 1) scan_topk_kernel(const Sca
             if (cpr == 1) {
                 uint32_t mm = mask;
                 while (mm) {
-                    const int r = __ffs(mm) - 1;
+                    // two rows per trip: their FMA chains and butterflies are independent, which
+                    // halves the latency-bound part for short rows (several rows per slot)
+                    const int r0 = __ffs(mm) - 1;
                     mm &= mm - 1;
-                    float b[4] = {0.f, 0.f, 0.f, 0.f};
-                    dot.accumulate(xs + (size_t)r * pieces_per_row, q4, 0, pieces_per_row, lane, b);
-                    const float s = warp_sum((b[0] + b[1]) + (b[2] + b[3]));
-                    if (lane == r) myscore = s;
+                    const int r1 = mm ? __ffs(mm) - 1 : -1;
+                    if (r1 >= 0) mm &= mm - 1;
+                    float b[4] = {0.f, 0.f, 0.f, 0.f}, c[4] = {0.f, 0.f, 0.f, 0.f};
+                    dot.accumulate(xs + (size_t)r0 * pieces_per_row, q4, 0, pieces_per_row, lane, b);
+                    if (r1 >= 0) dot.accumulate(xs + (size_t)r1 * pieces_per_row, q4, 0, pieces_per_row, lane, c);
+                    float s0 = (b[0] + b[1]) + (b[2] + b[3]), s1 = (c[0] + c[1]) + (c[2] + c[3]);
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+                        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+                    }
+                    if (lane == r0) myscore = s0;
+                    if (lane == r1) myscore = s1;
                 }
             } else {
                 const int piece0 = c_chunk * SLOT_PIECES;

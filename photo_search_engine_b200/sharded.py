@@ -141,6 +141,27 @@ class ShardedIndex:
                                       b["scores"].data_ptr(), b["ids"].data_ptr(), stream)
         return b["scores"], b["ids"]
 
+    def search_by_id(self, global_id: int, k: int, flt=None, n_total: Optional[int] = None):
+        """Image -> image (core/searcher.py:1751-1814): the stored vector of row ``global_id`` is the
+        query.  The owning rank re-reads its row (K6 = ``index.reconstruct``, utils/vector_store.py:207),
+        broadcasts it, every rank scans for k+1 and the row itself is dropped -- the reference drops it
+        by path (``same_file_path``), here by id.  Collective.  Returns device tensors ``(scores [k], ids [k])``."""
+        t = self.torch
+        d = self.local.d
+        owner_mine = self.row0 <= global_id < self.row0 + self.local.ntotal
+        q = t.zeros((1, d), dtype=t.float32, device=self.device)
+        if owner_mine:
+            q.copy_(t.from_numpy(self.local.reconstruct(global_id - self.row0))[None, :])
+        if self.world > 1:
+            owner = t.tensor([self.rank if owner_mine else -1], device=self.device)
+            self.dist.all_reduce(owner, op=self.dist.ReduceOp.MAX, group=self.group)
+            self.dist.broadcast(q, src=int(owner.item()), group=self.group)
+        s, i = self.search_device(q, k + 1, flt)
+        keep = i[0] != global_id
+        # the row itself is the best hit unless an exact duplicate with a lower id exists: drop it wherever it is
+        idx = t.nonzero(keep, as_tuple=False)[:k, 0]
+        return s[0][idx], i[0][idx]
+
     def search(self, q: np.ndarray, k: int, flt=None) -> Tuple[np.ndarray, np.ndarray]:
         """Host in, host out (the call a user makes): pinned H2D of the query, sharded search,
         D2H of the merged result.  Collective: every rank must call it with the same query."""
