@@ -107,8 +107,15 @@ struct psx_index {
 
 constexpr int BATCH_MAX_Q = 256;
 constexpr int BATCH_CAND_CAP = 4096;
-constexpr int BATCH_BN = 128;
-constexpr int BATCH_STAGES = 4;
+// Tile shapes (measured on B200, 1M x 1024): up to 128 queries use one accumulator and 256-row corpus tiles
+// (TMEM double buffered, half the L2 re-reads of the query block); 129..256 queries use two accumulators
+// and 128-row tiles -- 256-row tiles would leave no TMEM for double buffering and lose the MMA/epilogue overlap.
+template <int MT>
+struct BatchCfg {
+    static constexpr int BN = MT == 2 ? 128 : 256;
+    static constexpr int STAGES = 4;  // 48 KB per stage either way
+};
+static int batch_bn(int mt) { return mt == 2 ? BatchCfg<2>::BN : BatchCfg<1>::BN; }
 
 static int pow2ceil(long long v) {
     long long p = 1;
@@ -649,14 +656,16 @@ static bool debug_sync() {
 
 template <int MT>
 static int launch_gemm(psx_index* h, const CUtensorMap& mq, const CUtensorMap& mx, const GemmParams& gp, int grid, cudaStream_t st) {
+    constexpr int STAGES = BatchCfg<MT>::STAGES;
+    constexpr int BATCH_BN = BatchCfg<MT>::BN;
     constexpr int STAGE_BYTES = (MT * GEMM_M + BATCH_BN) * GEMM_BK * 4;
-    constexpr size_t smem = (size_t)BATCH_STAGES * STAGE_BYTES + 256;
+    constexpr size_t smem = (size_t)STAGES * STAGE_BYTES + 256;
     static std::atomic<bool> ready[64];
     if (h->device < 64 && !ready[h->device].load()) {
-        CU(cudaFuncSetAttribute(gemm_filter_kernel<MT, BATCH_BN, BATCH_STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CU(cudaFuncSetAttribute(gemm_filter_kernel<MT, BATCH_BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         ready[h->device].store(true);
     }
-    gemm_filter_kernel<MT, BATCH_BN, BATCH_STAGES><<<grid, GEMM_THREADS, smem, st>>>(mq, mx, gp);
+    gemm_filter_kernel<MT, BATCH_BN, STAGES><<<grid, GEMM_THREADS, smem, st>>>(mq, mx, gp);
     g_launches++;
     CU(cudaGetLastError());
     return PSX_OK;
@@ -667,6 +676,7 @@ static int launch_gemm(psx_index* h, const CUtensorMap& mq, const CUtensorMap& m
 static int launch_batch(psx_index* h, const float* q_dev, int nq, int k, uint32_t id_base, float qnorm_max, float* out_scores,
                         long long* out_ids, uint64_t* out_keys, int* flags_dev, cudaStream_t st) {
     const int MT = nq > GEMM_M ? 2 : 1;
+    const int BATCH_BN = batch_bn(MT);
     const int num_tiles = (int)((h->n + BATCH_BN - 1) / BATCH_BN);
     // theta from a strided sample: aim at ~16 sample scores above the threshold that ~T rows pass
     const int T = 4 * k + 64;
@@ -707,7 +717,11 @@ static int launch_batch(psx_index* h, const float* q_dev, int nq, int k, uint32_
     const long long sample_rows = std::min<long long>(h->n, (long long)sample_tiles * BATCH_BN);
     int rank = (int)((double)T * (double)sample_rows / (double)h->n + 0.5);
     if (rank < 2) rank = 2;
-    theta_kernel<<<nq, 256, 0, st>>>(h->bsample, sample_ld, sample_ld, rank, 0.0f, h->btheta, h->bcount);
+    // the rank statistic is taken from per-thread top-2 lists, good for ranks up to a few dozen: thin the
+    // sample (every `thin`-th score) when the requested rank is larger
+    const int thin = rank > 48 ? rank / 32 : 1;
+    rank /= thin;
+    theta_kernel<<<nq, 256, 0, st>>>(h->bsample, sample_ld, sample_ld, thin, rank, 0.0f, h->btheta, h->bcount);
     g_launches++;
     CU(cudaGetLastError());
     DBG_SYNC(st, "theta_kernel");

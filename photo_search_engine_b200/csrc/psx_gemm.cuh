@@ -278,13 +278,13 @@ gemm_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
 // survivors are sorted and the element at the requested rank is taken.  Approximate by design: the
 // threshold only has to land between the k-th and roughly the (4k)-th score -- exactness comes from
 // the proof obligation checked after the exact re-score.
-__global__ void __launch_bounds__(256) theta_kernel(const float* __restrict__ sample, int sample_ld, int ns, int rank,
+__global__ void __launch_bounds__(256) theta_kernel(const float* __restrict__ sample, int sample_ld, int ns, int thin, int rank,
                                                     float margin, float* __restrict__ theta, int* __restrict__ cand_count) {
     __shared__ uint64_t keys[512];
     const int qi = blockIdx.x;
     const float* s = sample + (size_t)qi * sample_ld;
     float b0 = -INFINITY, b1 = -INFINITY;
-    for (int i = threadIdx.x; i < ns; i += blockDim.x) {
+    for (long long i = (long long)threadIdx.x * thin; i < ns; i += (long long)blockDim.x * thin) {
         const float v = s[i];
         if (v > b0) {
             b1 = b0;
