@@ -449,7 +449,35 @@ def run_extras(torch, _native, index, queries, rows, d, k, device, esize):
             out.update(run_bf16_shard(torch, _native, device))
         except Exception as exc:  # never let a secondary configuration kill the bench line
             out["bf16_shard/error"] = repr(exc)[:200]
+        try:
+            out.update(run_mixed_tier(torch, _native, index, queries, rows, d, k, device))
+        except Exception as exc:
+            out["bf16+fp32_master/error"] = repr(exc)[:200]
     return out
+
+
+def run_mixed_tier(torch, _native, index, queries, rows, d, k, device):
+    """Optional storage tier: bf16 rows for the scan + fp32 master for an exact re-score.  Same corpus
+    bits as the headline index; results must be bit-identical to it."""
+    free, _total = torch.cuda.mem_get_info()
+    if free < rows * d * 6 * 1.1:
+        return {"bf16+fp32_master/skipped": "not enough free HBM"}
+    mixed = _native.NativeIndex(d, _native.METRIC_IP, _native.STORE_BF16_MASTER, device.index or 0)
+    build_corpus(torch, mixed, 0, rows, d, device)
+    q_ptrs = [queries[i: i + 1].data_ptr() for i in range(queries.shape[0])]
+    ms = time_device_search(torch, mixed, q_ptrs, k, None, 30)
+    sc = torch.empty((8, k), device=device)
+    ids = torch.empty((8, k), dtype=torch.int64, device=device)
+    sc2, ids2 = torch.empty_like(sc), torch.empty_like(ids)
+    st = torch.cuda.current_stream().cuda_stream
+    index.search_device(queries.data_ptr(), 8, k, sc.data_ptr(), ids.data_ptr(), 0, stream=st)
+    mixed.search_device(queries.data_ptr(), 8, k, sc2.data_ptr(), ids2.data_ptr(), 0, stream=st)
+    torch.cuda.synchronize()
+    same = bool((ids == ids2).all() and (sc == sc2).all())
+    mixed.close()
+    return {"bf16+fp32_master": {"ms": ms, "qps": 1e3 / ms, "bytes_streamed_per_query": rows * d * 2,
+                                 "hbm_GBps": rows * d * 2 / ms / 1e6, "bit_identical_to_fp32_index": same,
+                                 "note": "exact results at half the bytes per query, 1.5x the HBM footprint"}}
 
 
 def run_bf16_shard(torch, _native, device):

@@ -49,6 +49,12 @@ typedef enum psx_status {
 /* storage precision of the corpus in HBM; arithmetic is always fp32 accumulate */
 #define PSX_STORE_F32 0
 #define PSX_STORE_BF16 1
+/* bf16 rows for the scan PLUS an fp32 master copy (1.5x the fp32 footprint): every search streams
+ * the bf16 rows (half the bytes) for k' = 4k+64 candidates and re-scores them on the master with
+ * the fp32 scan's reduction tree; a per-query proof obligation (k-th exact score >= k'-th bf16
+ * score + rounding bound) certifies the result, otherwise the fp32 master is scanned.  Results are
+ * bit-identical to a PSX_STORE_F32 index. */
+#define PSX_STORE_BF16_MASTER 2
 
 /* hard upper bound of k for ONE scan pass; larger k is served by paging inside psx_search */
 #define PSX_K_PASS_MAX 2048

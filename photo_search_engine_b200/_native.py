@@ -19,7 +19,7 @@ LIB_PATH = os.environ.get("PSX_LIB", os.path.join(_HERE, "libpsx.so"))
 PSX_OK = 0
 PSX_ERR_INVALID, PSX_ERR_CUDA, PSX_ERR_OOM, PSX_ERR_RANGE, PSX_ERR_STATE = -1, -2, -3, -4, -5
 METRIC_IP, METRIC_L2 = 0, 1
-STORE_F32, STORE_BF16 = 0, 1
+STORE_F32, STORE_BF16, STORE_BF16_MASTER = 0, 1, 2
 K_PASS_MAX = 2048
 
 F_SEASON, F_PERIOD, F_YEAR, F_MONTH, F_NEED_DT, F_START, F_END = 0x01, 0x02, 0x04, 0x08, 0x10, 0x20, 0x40

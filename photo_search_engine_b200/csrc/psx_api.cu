@@ -60,7 +60,12 @@ struct DeviceGuard {
 struct psx_index {
     int d = 0, ld = 0, metric = 0, dtype = 0, device = 0;
     size_t esize = 4, row_bytes = 0;
-    unsigned char* x = nullptr;  // [cap][row_bytes]
+    unsigned char* x = nullptr;  // [cap][row_bytes]  the rows the scan streams (fp32 or bf16)
+    // PSX_STORE_BF16_MASTER: an fp32 master copy next to the bf16 rows.  The scan streams the bf16 rows
+    // (half the bytes) for k' > k candidates, the master re-scores them exactly.
+    unsigned char* xm = nullptr;  // [cap][mrow_bytes] fp32
+    int ldm = 0;
+    size_t mrow_bytes = 0;
     uint64_t* attrs = nullptr;   // [cap]
     bool attrs_set = false;
     long long n = 0, cap = 0;
@@ -98,12 +103,19 @@ struct psx_index {
     int* bcount = nullptr;    // [256]
     int* bflags = nullptr;    // [256]
     uint32_t* bcand = nullptr;  // [256][BATCH_CAND_CAP]
+    uint64_t* mkeys = nullptr;  // [PSX_K_PASS_MAX] bf16-prefilter keys (PSX_STORE_BF16_MASTER)
+    float* meps = nullptr;      // [1] its rounding bound
     float* bsample = nullptr;
     size_t bsample_cap = 0;
     int* hflags = nullptr;    // pinned [256]
-    long long batch_fallbacks = 0, batch_queries = 0;
+    long long batch_fallbacks = 0, batch_queries = 0, mixed_queries = 0;
     std::mutex mu;
 };
+
+static inline int scan_dtype(const psx_index* h) { return h->dtype == PSX_STORE_F32 ? PSX_STORE_F32 : PSX_STORE_BF16; }
+static inline bool has_fp32_rows(const psx_index* h) { return h->dtype != PSX_STORE_BF16; }
+static inline const float* fp32_rows(const psx_index* h) { return (const float*)(h->dtype == PSX_STORE_F32 ? h->x : h->xm); }
+static inline int fp32_ld(const psx_index* h) { return h->dtype == PSX_STORE_F32 ? h->ld : h->ldm; }
 
 constexpr int BATCH_MAX_Q = 256;
 constexpr int BATCH_CAND_CAP = 4096;
@@ -145,7 +157,7 @@ extern "C" int psx_create(int d, int metric, int store_dtype, int device, psx_in
     *out = nullptr;
     if (d <= 0 || d > 32768) return fail(PSX_ERR_INVALID, "dimension %d out of range [1, 32768]", d);
     if (metric != PSX_METRIC_IP && metric != PSX_METRIC_L2) return fail(PSX_ERR_INVALID, "bad metric %d", metric);
-    if (store_dtype != PSX_STORE_F32 && store_dtype != PSX_STORE_BF16)
+    if (store_dtype != PSX_STORE_F32 && store_dtype != PSX_STORE_BF16 && store_dtype != PSX_STORE_BF16_MASTER)
         return fail(PSX_ERR_INVALID, "bad store dtype %d", store_dtype);
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -170,6 +182,8 @@ extern "C" int psx_create(int d, int metric, int store_dtype, int device, psx_in
     const int per16 = 16 / (int)h->esize;
     h->ld = (d + per16 - 1) / per16 * per16;
     h->row_bytes = (size_t)h->ld * h->esize;
+    h->ldm = (d + 3) / 4 * 4;
+    h->mrow_bytes = store_dtype == PSX_STORE_BF16_MASTER ? (size_t)h->ldm * 4 : 0;
     h->sm_count = prop.multiProcessorCount;
     int rc = PSX_OK;
     auto init = [&]() -> int {
@@ -192,6 +206,7 @@ extern "C" int psx_create(int d, int metric, int store_dtype, int device, psx_in
 
 static void free_all(psx_index* h) {
     cudaFree(h->x);
+    cudaFree(h->xm);
     cudaFree(h->attrs);
     cudaFree(h->lists);
     cudaFree(h->counter);
@@ -208,6 +223,8 @@ static void free_all(psx_index* h) {
     cudaFree(h->bcount);
     cudaFree(h->bflags);
     cudaFree(h->bcand);
+    cudaFree(h->mkeys);
+    cudaFree(h->meps);
     cudaFree(h->bsample);
     cudaFreeHost(h->hflags);
     if (h->last_ev) cudaEventDestroy(h->last_ev);
@@ -235,8 +252,10 @@ extern "C" int psx_reset(psx_index* h) {
     DeviceGuard g(h->device);
     cudaDeviceSynchronize();
     cudaFree(h->x);
+    cudaFree(h->xm);
     cudaFree(h->attrs);
     h->x = nullptr;
+    h->xm = nullptr;
     h->attrs = nullptr;
     h->attrs_set = false;
     cudaMemset(h->dmax_sumsq, 0, sizeof(float));
@@ -275,14 +294,27 @@ static int ensure_capacity(psx_index* h, long long need, bool exact) {
         cudaFree(nx);
         return fail(PSX_ERR_OOM, "cudaMalloc of attribute words failed: %s", cudaGetErrorString(e));
     }
+    unsigned char* nm = nullptr;
+    if (h->mrow_bytes) {
+        e = cudaMalloc(&nm, (size_t)ncap * h->mrow_bytes);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            cudaFree(nx);
+            cudaFree(na);
+            return fail(PSX_ERR_OOM, "cudaMalloc of the fp32 master (%lld rows) failed: %s", ncap, cudaGetErrorString(e));
+        }
+    }
     CU(cudaMemsetAsync(na, 0, (size_t)ncap * sizeof(uint64_t), h->stream));
     if (h->n > 0) {
         CU(cudaMemcpyAsync(nx, h->x, (size_t)h->n * h->row_bytes, cudaMemcpyDeviceToDevice, h->stream));
         CU(cudaMemcpyAsync(na, h->attrs, (size_t)h->n * sizeof(uint64_t), cudaMemcpyDeviceToDevice, h->stream));
+        if (nm) CU(cudaMemcpyAsync(nm, h->xm, (size_t)h->n * h->mrow_bytes, cudaMemcpyDeviceToDevice, h->stream));
     }
     CU(cudaStreamSynchronize(h->stream));
     cudaFree(h->x);
+    cudaFree(h->xm);
     cudaFree(h->attrs);
+    h->xm = nm;
     h->x = nx;
     h->attrs = na;
     h->cap = ncap;
@@ -300,6 +332,11 @@ static int launch_pack(psx_index* h, const float* src_dev, long long row0, long 
         pack_rows_kernel<__nv_bfloat16><<<(unsigned)blocks, 256, 0, st>>>(src_dev, (__nv_bfloat16*)dst, n, h->d, h->ld, normalize,
                                                                         h->dmax_sumsq);
     g_launches++;
+    if (h->xm) {
+        pack_rows_kernel<float><<<(unsigned)blocks, 256, 0, st>>>(src_dev, (float*)(h->xm + (size_t)row0 * h->mrow_bytes), n, h->d, h->ldm,
+                                                                 normalize, h->dmax_sumsq);
+        g_launches++;
+    }
     h->max_norm = 0.f;  // re-read lazily
     CU(cudaGetLastError());
     return PSX_OK;
@@ -423,23 +460,25 @@ struct ScanPlan {
     size_t smem;
 };
 
-static int plan_scan(psx_index* h, int k, ScanPlan& plan) {
+static int plan_scan(psx_index* h, bool master, int k, ScanPlan& plan) {
     ScanParams& p = plan.p;
     memset(&p, 0, sizeof p);
     const int W = h->warps;
+    // which arena is streamed: the scan rows, or the fp32 master of a PSX_STORE_BF16_MASTER index
+    struct { int ld; size_t row_bytes; } a = {master ? h->ldm : h->ld, master ? h->mrow_bytes : h->row_bytes};
     p.n = h->n;
     p.d = h->d;
-    p.ld = h->ld;
-    p.row_bytes = (int)h->row_bytes;
+    p.ld = a.ld;
+    p.row_bytes = (int)a.row_bytes;
     p.k = k;
     p.kpad = (int)psx_kpad(k);
     p.metric = h->metric;
-    if (h->row_bytes <= PSX_SLOT_BYTES) {
-        p.rps = (int)std::min<size_t>(32, PSX_SLOT_BYTES / h->row_bytes);
+    if (a.row_bytes <= PSX_SLOT_BYTES) {
+        p.rps = (int)std::min<size_t>(32, PSX_SLOT_BYTES / a.row_bytes);
         p.cpr = 1;
     } else {
         p.rps = 1;
-        p.cpr = (int)((h->row_bytes + PSX_SLOT_BYTES - 1) / PSX_SLOT_BYTES);
+        p.cpr = (int)((a.row_bytes + PSX_SLOT_BYTES - 1) / PSX_SLOT_BYTES);
     }
     // One predicate ballot covers a group of up to 32 rows, and groups are dealt round-robin to all
     // warps of the grid.  A lone warp streams slowly (latency bound), so the kernel's tail is one
@@ -459,7 +498,7 @@ static int plan_scan(psx_index* h, int k, ScanPlan& plan) {
     if (cap < 1024) cap = 1024;
     p.cand_cap = cap;
     p.high_water = cap - burst;
-    const int qpad = (h->ld + 7) & ~7;
+    const int qpad = (a.ld + 7) & ~7;
     auto smem_for = [&](int S) {
         return (size_t)W * S * PSX_SLOT_BYTES + (size_t)qpad * 4 + (size_t)cap * 8 + (size_t)W * S * 8 + 8 +
                (size_t)W * S * 8 + 16;
@@ -468,7 +507,7 @@ static int plan_scan(psx_index* h, int k, ScanPlan& plan) {
     const size_t limit = h->ctas_per_sm <= 1 ? (size_t)PSX_SMEM_LIMIT : (size_t)(228 * 1024) / h->ctas_per_sm - 1024;
     int S = h->stages;
     // short rows leave part of every 4 KB slot unused: keep the bytes in flight up with a third stage
-    if (h->stages_auto && p.cpr == 1 && (size_t)p.rps * h->row_bytes * 5 < (size_t)PSX_SLOT_BYTES * 4) S = 3;
+    if (h->stages_auto && p.cpr == 1 && (size_t)p.rps * a.row_bytes * 5 < (size_t)PSX_SLOT_BYTES * 4) S = 3;
     while (S > 2 && smem_for(S) > limit) --S;
     // the merge reuses the ring: it must hold at least two lists
     while ((size_t)W * S * PSX_SLOT_BYTES / 8 < (size_t)2 * p.kpad && smem_for(S + 1) <= PSX_SMEM_LIMIT) ++S;
@@ -531,9 +570,9 @@ static size_t xchg_flag_offset() { return (size_t)2 * PSX_XCHG_MAX_WORLD * PSX_K
 
 static int launch_scan(psx_index* h, const float* q_dev, int k, const psx_filter* f, uint32_t id_base,
                        const uint64_t* ceil_ptr, float* out_scores, long long* out_ids, uint64_t* out_keys, cudaStream_t st,
-                       const XchgArgs* xa = nullptr) {
+                       const XchgArgs* xa = nullptr, bool master = false, const int* cond_flag = nullptr) {
     ScanPlan plan;
-    int rc = plan_scan(h, k, plan);
+    int rc = plan_scan(h, master, k, plan);
     if (rc) return rc;
     ScanParams& p = plan.p;
     const size_t need_lists = (size_t)plan.grid * p.kpad;
@@ -546,7 +585,8 @@ static int launch_scan(psx_index* h, const float* q_dev, int k, const psx_filter
         CU(cudaMalloc(&h->lists, want * sizeof(uint64_t)));
         h->lists_cap = want;
     }
-    p.x = h->x;
+    p.x = master ? h->xm : h->x;
+    p.cond_flag = cond_flag;
     p.q = q_dev;
     p.ceil_ptr = ceil_ptr;
     p.lists = h->lists;
@@ -571,17 +611,18 @@ static int launch_scan(psx_index* h, const float* q_dev, int k, const psx_filter
             p.xchg_flag[r] = (uint32_t*)(uintptr_t)(xa->bases[r] + xchg_flag_offset());
         }
     }
-    const int ppr = (int)(h->row_bytes >> 4);  // 16-byte pieces per row
+    const size_t arena_row_bytes = master ? h->mrow_bytes : h->row_bytes;
+    const int ppr = (int)(arena_row_bytes >> 4);  // 16-byte pieces per row
     int ppl = 0;
     bool qreg = false;
     if (p.cpr == 1 && ppr % 32 == 0) {
         ppl = ppr / 32;
         qreg = true;
         if (ppl == 5 || ppl == 7) ppl = 0, qreg = false;
-    } else if (p.cpr > 1 && h->row_bytes % PSX_SLOT_BYTES == 0) {
+    } else if (p.cpr > 1 && arena_row_bytes % PSX_SLOT_BYTES == 0) {
         ppl = 8;
     }
-    rc = launch_scan_variant(h->device, h->dtype, h->metric, ppl, qreg, plan, st);
+    rc = launch_scan_variant(h->device, master ? PSX_STORE_F32 : scan_dtype(h), h->metric, ppl, qreg, plan, st);
     if (rc) return rc;
     g_launches++;
     CU(cudaGetLastError());
@@ -618,17 +659,19 @@ static int make_map(CUtensorMap* map, const float* base, long long rows, int col
 }
 
 static bool batch_eligible(const psx_index* h, int64_t nq, int64_t k, const psx_filter* f) {
-    return h->metric == PSX_METRIC_IP && h->dtype == PSX_STORE_F32 && !(f && f->flags) && h->batch_min > 0 &&
+    return h->metric == PSX_METRIC_IP && has_fp32_rows(h) && !(f && f->flags) && h->batch_min > 0 &&
            nq >= h->batch_min && k <= 512 && h->n >= 65536 && h->d >= 32;
 }
 
 static int ensure_batch_scratch(psx_index* h, size_t sample_floats) {
     if (!h->bq) {
-        CU(cudaMalloc(&h->bq, (size_t)BATCH_MAX_Q * h->ld * sizeof(float)));
+        CU(cudaMalloc(&h->bq, (size_t)BATCH_MAX_Q * (h->ldm + 8) * sizeof(float)));
         CU(cudaMalloc(&h->btheta, BATCH_MAX_Q * sizeof(float)));
         CU(cudaMalloc(&h->bcount, BATCH_MAX_Q * sizeof(int)));
         CU(cudaMalloc(&h->bflags, BATCH_MAX_Q * sizeof(int)));
         CU(cudaMalloc(&h->bcand, (size_t)BATCH_MAX_Q * BATCH_CAND_CAP * sizeof(uint32_t)));
+        CU(cudaMalloc(&h->mkeys, (size_t)PSX_K_PASS_MAX * sizeof(uint64_t)));
+        CU(cudaMalloc(&h->meps, sizeof(float)));
         CU(cudaMallocHost(&h->hflags, BATCH_MAX_Q * sizeof(int)));
     }
     if (sample_floats > h->bsample_cap) {
@@ -689,12 +732,13 @@ static int launch_batch(psx_index* h, const float* q_dev, int nq, int k, uint32_
     int rc = ensure_batch_scratch(h, (size_t)MT * GEMM_M * sample_ld);
     if (rc) return rc;
     // queries -> zero-padded [MT*128][ld] block (rows beyond nq and columns beyond d are zero)
-    CU(cudaMemsetAsync(h->bq, 0, (size_t)MT * GEMM_M * h->ld * sizeof(float), st));
-    CU(cudaMemcpy2DAsync(h->bq, (size_t)h->ld * sizeof(float), q_dev, (size_t)h->d * sizeof(float), (size_t)h->d * sizeof(float), nq,
+    const int fld = fp32_ld(h);
+    CU(cudaMemsetAsync(h->bq, 0, (size_t)MT * GEMM_M * fld * sizeof(float), st));
+    CU(cudaMemcpy2DAsync(h->bq, (size_t)fld * sizeof(float), q_dev, (size_t)h->d * sizeof(float), (size_t)h->d * sizeof(float), nq,
                          cudaMemcpyDeviceToDevice, st));
     CUtensorMap mq, mx;
-    if ((rc = make_map(&mq, h->bq, (long long)MT * GEMM_M, h->d, h->ld, GEMM_M))) return rc;
-    if ((rc = make_map(&mx, (const float*)h->x, h->n, h->d, h->ld, BATCH_BN))) return rc;
+    if ((rc = make_map(&mq, h->bq, (long long)MT * GEMM_M, h->d, fld, GEMM_M))) return rc;
+    if ((rc = make_map(&mx, fp32_rows(h), h->n, h->d, fld, BATCH_BN))) return rc;
     GemmParams gp;
     memset(&gp, 0, sizeof gp);
     gp.n = h->n;
@@ -734,7 +778,7 @@ static int launch_batch(psx_index* h, const float* q_dev, int nq, int k, uint32_
     DBG_SYNC(st, "gemm_filter_kernel(filter)");
     // exact re-score of the survivors + top-k + proof obligation
     const int kpad = (int)psx_kpad(k);
-    const size_t smem = (size_t)BATCH_CAND_CAP * 8 + (size_t)(h->ld + 4) * 4;
+    const size_t smem = (size_t)BATCH_CAND_CAP * 8 + (size_t)(fld + 4) * 4;
     static std::atomic<bool> ready[64];
     if (h->device < 64 && !ready[h->device].load()) {
         CU(cudaFuncSetAttribute(rescore_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PSX_SMEM_LIMIT));
@@ -749,12 +793,61 @@ static int launch_batch(psx_index* h, const float* q_dev, int nq, int k, uint32_
         h->max_norm = sqrtf(m2);
     }
     const float eps = 2.2e-3f * (qnorm_max > 0.f ? qnorm_max : 1.0f) * (h->max_norm > 0.f ? h->max_norm : 1.0f);
-    rescore_select_kernel<<<nq, 512, smem, st>>>((const float*)h->x, h->ld, h->d, h->n, q_dev, k, kpad, h->bcand, h->bcount,
-                                                 BATCH_CAND_CAP, h->btheta, eps, id_base, out_scores, out_ids, out_keys, flags_dev);
+    rescore_select_kernel<<<nq, 512, smem, st>>>(fp32_rows(h), fld, h->d, h->n, q_dev, k, kpad, h->bcand, h->bcount,
+                                                 BATCH_CAND_CAP, h->btheta, eps, nullptr, id_base, out_scores, out_ids, out_keys, flags_dev);
     g_launches++;
     CU(cudaGetLastError());
     DBG_SYNC(st, "rescore_select_kernel");
     return PSX_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// one exact query, whatever the storage tier
+// ------------------------------------------------------------------------------------------
+// fp32 scan over the rows that hold the exact values (the arena itself, or the master copy)
+static int launch_exact_scan(psx_index* h, const float* q_dev, int k, const psx_filter* f, uint32_t id_base, const uint64_t* ceil_ptr,
+                             float* out_scores, long long* out_ids, uint64_t* out_keys, cudaStream_t st, const int* cond_flag = nullptr) {
+    return launch_scan(h, q_dev, k, f, id_base, ceil_ptr, out_scores, out_ids, out_keys, st, nullptr, h->dtype == PSX_STORE_BF16_MASTER,
+                       cond_flag);
+}
+
+// PSX_STORE_BF16_MASTER: stream the bf16 rows for k' candidates, re-score them on the fp32 master,
+// certify, and fall back to the master scan (a conditional launch: the grid exits at once when the
+// certificate holds) otherwise.  No host synchronisation.
+static int launch_mixed(psx_index* h, const float* q_dev, int k, const psx_filter* f, uint32_t id_base, float* out_scores,
+                        long long* out_ids, uint64_t* out_keys, cudaStream_t st) {
+    int rc = ensure_batch_scratch(h, 0);
+    if (rc) return rc;
+    int kprime = 4 * k + 64;
+    if (kprime > PSX_K_PASS_MAX) kprime = PSX_K_PASS_MAX;
+    if ((rc = launch_scan(h, q_dev, kprime, f, id_base, nullptr, nullptr, nullptr, h->mkeys, st))) return rc;
+    keys_to_cands_kernel<<<1, 256, 0, st>>>(h->mkeys, kprime, id_base, h->bcand, h->bcount, h->btheta, q_dev, h->d, h->dmax_sumsq, h->meps);
+    g_launches++;
+    CU(cudaGetLastError());
+    const int kpad = (int)psx_kpad(k);
+    const size_t smem = (size_t)BATCH_CAND_CAP * 8 + (size_t)(h->ldm + 4) * 4;
+    static std::atomic<bool> ready[64];
+    if (h->device < 64 && !ready[h->device].load()) {
+        CU(cudaFuncSetAttribute(rescore_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PSX_SMEM_LIMIT));
+        ready[h->device].store(true);
+    }
+    rescore_select_kernel<<<1, 512, smem, st>>>((const float*)h->xm, h->ldm, h->d, h->n, q_dev, k, kpad, h->bcand, h->bcount, BATCH_CAND_CAP,
+                                                h->btheta, 0.f, h->meps, id_base, out_scores, out_ids, out_keys, h->bflags);
+    g_launches++;
+    CU(cudaGetLastError());
+    h->mixed_queries++;
+    return launch_exact_scan(h, q_dev, k, f, id_base, nullptr, out_scores, out_ids, out_keys, st, h->bflags);
+}
+
+// the single-query entry every API funnels through
+static int launch_query(psx_index* h, const float* q_dev, int k, const psx_filter* f, uint32_t id_base, const uint64_t* ceil_ptr,
+                        float* out_scores, long long* out_ids, uint64_t* out_keys, cudaStream_t st) {
+    if (h->dtype == PSX_STORE_BF16_MASTER) {
+        // IP only: the rounding bound of the L2 form also involves |x|^2; paged continuations (ceil_ptr) go straight to the master
+        if (h->metric == PSX_METRIC_IP && !ceil_ptr) return launch_mixed(h, q_dev, k, f, id_base, out_scores, out_ids, out_keys, st);
+        return launch_exact_scan(h, q_dev, k, f, id_base, ceil_ptr, out_scores, out_ids, out_keys, st);
+    }
+    return launch_scan(h, q_dev, k, f, id_base, ceil_ptr, out_scores, out_ids, out_keys, st);
 }
 
 // scratch is per index: order this search after the previous one if it ran on another stream
@@ -782,8 +875,8 @@ extern "C" int psx_search_device(psx_index* h, const float* q_dev, int64_t nq, i
     if ((rc = enter_stream(h, st))) return rc;
     const int64_t kpad = psx_kpad(k);
     for (int64_t qi = 0; qi < nq; ++qi) {
-        rc = launch_scan(h, q_dev + qi * h->d, (int)k, filter, id_base, nullptr,
-                         out_scores_dev ? out_scores_dev + qi * k : nullptr,
+        rc = launch_query(h, q_dev + qi * h->d, (int)k, filter, id_base, nullptr,
+                          out_scores_dev ? out_scores_dev + qi * k : nullptr,
                          out_ids_dev ? (long long*)out_ids_dev + qi * k : nullptr,
                          out_keys_dev ? out_keys_dev + qi * kpad : nullptr, st);
         if (rc) return rc;
@@ -804,6 +897,8 @@ extern "C" int psx_search_exchange_device(psx_index* h, const float* q_dev, int6
     if (world < 1 || world > PSX_XCHG_MAX_WORLD || rank < 0 || rank >= world || seq == 0)
         return fail(PSX_ERR_INVALID, "exchange needs 1 <= world <= %d, 0 <= rank < world, seq >= 1", PSX_XCHG_MAX_WORLD);
     if (k < 1 || k > PSX_K_PASS_MAX) return fail(PSX_ERR_INVALID, "k=%lld not in [1,%d]", (long long)k, PSX_K_PASS_MAX);
+    if (h->dtype == PSX_STORE_BF16_MASTER)
+        return fail(PSX_ERR_STATE, "the fused exchange publishes the scan's own keys; a bf16+master index exchanges through psx_search_device keys");
     std::lock_guard<std::mutex> lk(h->mu);
     DeviceGuard g(h->device);
     int rc = flush_pending(h);
@@ -839,7 +934,7 @@ extern "C" int psx_search_batch_device(psx_index* h, const float* q_dev, int64_t
     DeviceGuard g(h->device);
     int rc = flush_pending(h);
     if (rc) return rc;
-    if (k < 1 || k > 512 || h->metric != PSX_METRIC_IP || h->dtype != PSX_STORE_F32 || h->n < 65536 || h->d < 32)
+    if (k < 1 || k > 512 || h->metric != PSX_METRIC_IP || !has_fp32_rows(h) || h->n < 65536 || h->d < 32)
         return fail(PSX_ERR_STATE, "tensor-core batch path needs an fp32 inner-product index with >= 65536 rows, d >= 32, k <= 512");
     cudaStream_t st = (cudaStream_t)stream;
     if ((rc = enter_stream(h, st))) return rc;
@@ -944,8 +1039,8 @@ static int search_batched_host(psx_index* h, const float* q, int64_t nq, int64_t
         for (int qi = 0; qi < gq; ++qi) {
             if (!h->hflags[qi]) continue;
             h->batch_fallbacks++;
-            rc = launch_scan(h, h->dq + (size_t)qi * h->d, (int)kk, nullptr, 0, nullptr, h->dscores + (size_t)qi * kk,
-                             h->dids + (size_t)qi * kk, nullptr, st);
+            rc = launch_exact_scan(h, h->dq + (size_t)qi * h->d, (int)kk, nullptr, 0, nullptr, h->dscores + (size_t)qi * kk,
+                                   h->dids + (size_t)qi * kk, nullptr, st);
             if (rc) return rc;
         }
         CU(cudaMemcpyAsync(h->hscores, h->dscores, (size_t)gq * kk * sizeof(float), cudaMemcpyDeviceToHost, st));
@@ -1003,8 +1098,8 @@ extern "C" int psx_search(psx_index* h, const float* q, int64_t nq, int64_t k, c
                 const size_t off = (size_t)qi * kslot + (size_t)pg * PSX_K_PASS_MAX;
                 // page pg continues strictly below the last key of page pg-1 (a full page)
                 const uint64_t* ceil_ptr = pg ? h->dkeys + off - 1 : nullptr;
-                rc = launch_scan(h, h->dq + qi * h->d, kp, filter, 0, ceil_ptr, h->dscores + off, h->dids + off,
-                                 h->dkeys + off, st);
+                rc = launch_query(h, h->dq + qi * h->d, kp, filter, 0, ceil_ptr, h->dscores + off, h->dids + off,
+                                  h->dkeys + off, st);
                 if (rc) return rc;
             }
         }
@@ -1041,8 +1136,9 @@ static int read_rows_locked(psx_index* h, long long row0, long long n, float* ou
         const long long total = m * h->d;
         unsigned blocks = (unsigned)std::min<long long>((total + 255) / 256, (long long)h->sm_count * 32);
         const unsigned char* src = h->x + (size_t)(row0 + done) * h->row_bytes;
-        if (h->dtype == PSX_STORE_F32)
-            unpack_rows_kernel<float><<<blocks, 256, 0, h->stream>>>((const float*)src, tmp, m, h->d, h->ld);
+        if (has_fp32_rows(h))
+            unpack_rows_kernel<float><<<blocks, 256, 0, h->stream>>>(fp32_rows(h) + (size_t)(row0 + done) * fp32_ld(h), tmp, m, h->d,
+                                                                    fp32_ld(h));
         else
             unpack_rows_kernel<__nv_bfloat16><<<blocks, 256, 0, h->stream>>>((const __nv_bfloat16*)src, tmp, m, h->d, h->ld);
         g_launches++;
@@ -1071,7 +1167,7 @@ extern "C" int psx_reconstruct(psx_index* h, int64_t id, float* out) {
     if (!h || !out) return fail(PSX_ERR_INVALID, "bad arguments to psx_reconstruct");
     std::lock_guard<std::mutex> lk(h->mu);
     if (id < 0 || id >= h->n + h->pending_n) return fail(PSX_ERR_RANGE, "id %lld not in [0,%lld)", (long long)id, h->n + h->pending_n);
-    if (id >= h->n && h->dtype == PSX_STORE_F32) {  // still staged on the host, stored precision == fp32
+    if (id >= h->n && has_fp32_rows(h)) {  // still staged on the host, stored precision == fp32
         memcpy(out, h->pending.data() + (size_t)(id - h->n) * h->d, (size_t)h->d * sizeof(float));
         return PSX_OK;
     }
@@ -1089,7 +1185,7 @@ extern "C" int psx_storage_device(psx_index* h, const void** rows_dev, int64_t* 
     if (rc) return rc;
     if (rows_dev) *rows_dev = h->x;
     if (ld_elems) *ld_elems = h->ld;
-    if (store_dtype) *store_dtype = h->dtype;
+    if (store_dtype) *store_dtype = scan_dtype(h);
     return PSX_OK;
 }
 

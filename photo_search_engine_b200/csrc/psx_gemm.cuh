@@ -317,8 +317,8 @@ __global__ void __launch_bounds__(256) theta_kernel(const float* __restrict__ sa
 __global__ void __launch_bounds__(512, 1)
 rescore_select_kernel(const float* __restrict__ x, int ld, int d, long long n, const float* __restrict__ q, int k, int kpad,
                       const uint32_t* __restrict__ cand_ids, const int* __restrict__ cand_count, int cand_cap,
-                      const float* __restrict__ theta, float eps, uint32_t id_base, float* out_scores, long long* out_ids,
-                      uint64_t* out_keys, int* flags) {
+                      const float* __restrict__ theta, float eps, const float* __restrict__ eps_dev, uint32_t id_base,
+                      float* out_scores, long long* out_ids, uint64_t* out_keys, int* flags) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     uint64_t* keys = reinterpret_cast<uint64_t*>(smem_raw);     // [np]
     const int qi = blockIdx.x;
@@ -378,9 +378,46 @@ rescore_select_kernel(const float* __restrict__ x, int ld, int d, long long n, c
         if (count < need) bad = 2;                                           // threshold too tight
         if (!bad && need > 0 && n > count) {
             const float kth = key_score(keys[need - 1]);
-            if (!(kth >= theta[qi] + eps)) bad = 3;                          // proof obligation not met
+            const float e = eps_dev ? eps_dev[qi] : eps;
+            if (!(kth >= theta[qi] + e)) bad = 3;                          // proof obligation not met
         }
         flags[qi] = bad;
+    }
+}
+
+// bf16-prefilter tier: the k' sorted keys of the bf16 scan -> the candidate list rescore_select_kernel
+// consumes (query 0), with theta = the k'-th bf16 score (or -inf when fewer than k' rows exist /
+// pass the predicate, in which case every eligible row is already a candidate).
+// Also computes the rounding bound for this query: storing x as bf16 (8 significant bits, round to
+// nearest) perturbs <q,x> by at most 2^-8 * sum|q_i x_i| <= 2^-8 |q| |x|; 4.1e-3 adds 5 % slack.
+__global__ void keys_to_cands_kernel(const uint64_t* __restrict__ keys, int kprime, uint32_t id_base, uint32_t* cand_ids,
+                                     int* cand_count, float* theta, const float* __restrict__ q, int d,
+                                     const float* __restrict__ max_sumsq, float* eps_out) {
+    __shared__ int cnt;
+    __shared__ float qsq[32];
+    if (threadIdx.x == 0) cnt = 0;
+    float acc = 0.f;
+    for (int i = threadIdx.x; i < d; i += blockDim.x) acc = fmaf(q[i], q[i], acc);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) qsq[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    int mine = 0;
+    for (int i = threadIdx.x; i < kprime; i += blockDim.x) {
+        const uint64_t key = keys[i];
+        if (key) {
+            cand_ids[i] = key_id(key) - id_base;  // keys are sorted: the non-empty ones form a prefix
+            ++mine;
+        }
+    }
+    atomicAdd(&cnt, mine);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        cand_count[0] = cnt;
+        theta[0] = cnt == kprime ? key_score(keys[kprime - 1]) : -INFINITY;
+        float qq = 0.f;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) qq += qsq[w];
+        eps_out[0] = 4.1e-3f * sqrtf(qq) * sqrtf(fmaxf(*max_sumsq, 0.f)) * 1.001f;
     }
 }
 

@@ -54,6 +54,7 @@ struct ScanParams {
     psx_filter f;
     // fused cross-GPU exchange (row shards): the last CTA stores this shard's k keys straight into
     // every peer's receive buffer over NVLink and raises a per-source flag there.  world 0 = off.
+    const int* cond_flag;  // nullptr, or: run only if *cond_flag != 0 (conditional fallback scan)
     int xchg_world, xchg_rank;
     uint32_t xchg_seq;
     uint64_t* xchg_recv[PSX_XCHG_MAX_WORLD];   // peer p: [2 parities][world][PSX_K_PASS_MAX] keys
@@ -217,6 +218,7 @@ struct RowDot {
 template <typename T, int METRIC, int PPL, bool QREG>
 __global__ void __launch_bounds__(PSX_MAX_THREADS, 1) scan_topk_kernel(const ScanParams p) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
+    if (p.cond_flag && *p.cond_flag == 0) return;  // uniform: the whole grid skips
     const int W = blockDim.x >> 5;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int S = p.stages;

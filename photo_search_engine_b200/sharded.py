@@ -52,7 +52,8 @@ class ShardedIndex:
         # be set up.  The CPU (gloo) test path always uses the collective.
         self.exchange = "nccl"
         self._seq = 0
-        if local_search is None and self.world > 1 and exchange in ("auto", "p2p"):
+        mixed = getattr(local, "store_dtype", 0) == _native.STORE_BF16_MASTER  # exchanges the re-scored keys, not the scan's
+        if local_search is None and self.world > 1 and exchange in ("auto", "p2p") and not mixed:
             try:
                 self._setup_p2p()
                 self.exchange = "p2p"

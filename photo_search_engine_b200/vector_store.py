@@ -14,7 +14,9 @@ library raises ``ImportError`` exactly as the reference does without faiss
 Additive, optional surface (defaults reproduce the reference):
 
 * keyword-only ctor arguments ``device`` / ``store_dtype`` (env ``PSX_DEVICE`` /
-  ``PSX_STORE_DTYPE``);
+  ``PSX_STORE_DTYPE``): ``fp32`` (default), ``bf16`` (half the HBM, approximate), ``bf16+fp32`` (bf16
+  rows for the scan plus an fp32 master: results bit-identical to ``fp32`` at about half the bytes
+  streamed per query);
 * ``search(..., constraints=None)``: fused pre-filter with the semantics of
   ``Searcher._check_time_match_v2`` (core/searcher.py:1884-1950);
 * ``search_batch`` / ``add_batch``: arrays in, arrays out, no per-hit Python objects.
@@ -34,7 +36,8 @@ _native.load_library()
 
 _METRICS = ("l2", "cosine")
 _INDEX_TYPES = ("flat", "hnsw")
-_DTYPES = {"fp32": "fp32", "float32": "fp32", "bf16": "bf16", "bfloat16": "bf16"}
+_DTYPES = {"fp32": "fp32", "float32": "fp32", "bf16": "bf16", "bfloat16": "bf16", "bf16+fp32": "bf16+fp32", "mixed": "bf16+fp32"}
+_DTYPE_CODES = {"fp32": _native.STORE_F32, "bf16": _native.STORE_BF16, "bf16+fp32": _native.STORE_BF16_MASTER}
 
 # messages are part of the observable behaviour (they surface in HTTP 500 bodies, api/routes.py:196-207)
 _E_METRIC = "metric仅支持l2或cosine"
@@ -94,7 +97,7 @@ class VectorStore:
             raise ValueError(_E_INDEX_TYPE)
         dtype_name = _DTYPES.get((store_dtype or os.environ.get("PSX_STORE_DTYPE", "fp32")).strip().lower())
         if dtype_name is None:
-            raise ValueError("store_dtype仅支持fp32或bf16")
+            raise ValueError("store_dtype仅支持fp32、bf16或bf16+fp32")
 
         self.dimension = dimension
         self.index_path = index_path
@@ -124,7 +127,7 @@ class VectorStore:
 
     def _create_index(self, dimension: int):
         """Backend for ``dimension`` (utils/vector_store.py:72-81); ``hnsw`` is served exactly."""
-        dtype = _native.STORE_BF16 if self.store_dtype == "bf16" else _native.STORE_F32
+        dtype = _DTYPE_CODES[self.store_dtype]
         return type(self)._index_factory(int(dimension), self._metric_code, dtype, self.device)
 
     def _require_dimension(self, vector: Sequence[float]) -> None:

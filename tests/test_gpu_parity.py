@@ -198,6 +198,35 @@ def test_bf16_storage(n, d):
     ix.close()
 
 
+@pytest.mark.parametrize("n,d", [(40_000, 1024), (30_000, 768), (5_000, 96), (50_000, 4096 // 8)])
+def test_bf16_plus_master_is_bit_identical_to_fp32(n, d):
+    """PSX_STORE_BF16_MASTER: bf16 prefilter + exact re-score on the fp32 master + certificate /
+    fallback must reproduce the fp32 index bit for bit (ids AND scores), with and without a
+    predicate, for small and large k, on random and on near-duplicate-heavy data."""
+    rng = np.random.default_rng(n + d)
+    x = unit_rows(rng, n, d)
+    x[1000:1400] = (x[999] + 1e-3 * rng.standard_normal((400, d))).astype(np.float32)  # gaps below the bf16 bound
+    x[1000:1400] /= np.linalg.norm(x[1000:1400], axis=1, keepdims=True)
+    q = np.concatenate([unit_rows(rng, 3, d), x[999:1000]]).astype(np.float32)
+    a = make_index(x, dtype=0)
+    b = make_index(x, dtype=2)
+    assert np.array_equal(b.reconstruct(17), x[17]) and np.array_equal(b.read_rows(5, 50), x[5:55])  # served from the master
+    words = (np.arange(n, dtype=np.uint64) + np.uint64(1))
+    a.set_attrs(0, words)
+    b.set_attrs(0, words)
+    flt = N().PsxFilter(flags=N().F_NEED_DT | N().F_START | N().F_END, start=n // 4, end=n // 2)
+    for k in (1, 10, 100, 496, 1500, 2500):
+        Da, Ia = a.search(q, k)
+        Db, Ib = b.search(q, k)
+        assert np.array_equal(Ia, Ib) and np.array_equal(Da, Db), k
+    Da, Ia = a.search(q, 100, flt)
+    Db, Ib = b.search(q, 100, flt)
+    assert np.array_equal(Ia, Ib) and np.array_equal(Da, Db)
+    assert ((Ib >= n // 4 - 1) & (Ib < n // 2)).all()
+    a.close()
+    b.close()
+
+
 def test_k_beyond_one_pass_and_beyond_n():
     rng = np.random.default_rng(3)
     x = unit_rows(rng, 9000, 64)
