@@ -443,6 +443,10 @@ def run_extras(torch, _native, index, queries, rows, d, k, device, esize):
     for kk in (50, 500, 1333, 2048):
         ms = time_device_search(torch, index, q_ptrs, kk, None, 20)
         out[f"k={kk}"] = {"ms": ms, "qps": 1e3 / ms, "GBps": rows * d * esize / ms / 1e6}
+    try:
+        out.update(run_config1(torch, _native, device))
+    except Exception as exc:
+        out["config1/error"] = repr(exc)[:200]
     if esize == 4:
         out.update(run_batched(torch, _native, index, rows, d, k, device))
         try:
@@ -478,6 +482,35 @@ def run_mixed_tier(torch, _native, index, queries, rows, d, k, device):
     return {"bf16+fp32_master": {"ms": ms, "qps": 1e3 / ms, "bytes_streamed_per_query": rows * d * 2,
                                  "hbm_GBps": rows * d * 2 / ms / 1e6, "bit_identical_to_fp32_index": same,
                                  "note": "exact results at half the bytes per query, 1.5x the HBM footprint"}}
+
+
+def run_config1(torch, _native, device):
+    """BASELINE.json configs[0]: 10k x 1024 fp32, single query, top-50 -- the reference's own CPU-runnable case
+    (tests/test_vector_store.py scale).  41 MB: latency bound (launch + two block-wide sorts), not bandwidth bound."""
+    n, d, k = 10_000, 1024, 50
+    ix = _native.NativeIndex(d, _native.METRIC_IP, _native.STORE_F32, device.index or 0)
+    gen = torch.Generator(device=device).manual_seed(3)
+    x = torch.randn((n, d), generator=gen, device=device)
+    x = (x / x.norm(dim=1, keepdim=True)).contiguous()
+    ix.add_device(x.data_ptr(), n, stream=torch.cuda.current_stream().cuda_stream)
+    q = torch.randn((16, d), generator=gen, device=device)
+    q = (q / q.norm(dim=1, keepdim=True)).contiguous()
+    ms = time_device_search(torch, ix, [q[i: i + 1].data_ptr() for i in range(16)], k, None, 300, warmup=20)
+    qh = q.cpu().numpy()
+    for i in range(10):
+        ix.search(qh[i % 16], k)
+    t0 = time.perf_counter()
+    for i in range(300):
+        ix.search(qh[i % 16], k)
+    e2e_us = (time.perf_counter() - t0) / 300 * 1e6
+    # parity against the torch fp32 reference on the same bits
+    D, I = ix.search(qh[:4], k)
+    ref = (x @ q[:4].t()).t()
+    rs, ri = torch.topk(ref, k, dim=1)
+    same = float((torch.from_numpy(I).to(device) == ri).float().mean())
+    ix.close()
+    return {"config1/10k_x_1024_k50": {"device_us_per_query": ms * 1e3, "host_api_us_per_query": e2e_us, "qps_device": 1e3 / ms,
+                                       "ids_equal_to_torch_fp32_topk": same}}
 
 
 def run_bf16_shard(torch, _native, device):
