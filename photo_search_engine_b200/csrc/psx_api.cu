@@ -460,10 +460,22 @@ struct ScanPlan {
     size_t smem;
 };
 
+static int plan_scan_with(psx_index* h, bool master, int k, int W, ScanPlan& plan);
+
+// Very long rows (d up to 32768: a 128 KB query block in shared memory) do not leave room for 16 warp
+// rings: retry with fewer warps before giving up.
 static int plan_scan(psx_index* h, bool master, int k, ScanPlan& plan) {
+    int rc = PSX_ERR_INVALID;
+    for (int W = h->warps; W >= 2; W >>= 1) {
+        rc = plan_scan_with(h, master, k, W, plan);
+        if (rc == PSX_OK) return rc;
+    }
+    return rc;
+}
+
+static int plan_scan_with(psx_index* h, bool master, int k, int W, ScanPlan& plan) {
     ScanParams& p = plan.p;
     memset(&p, 0, sizeof p);
-    const int W = h->warps;
     // which arena is streamed: the scan rows, or the fp32 master of a PSX_STORE_BF16_MASTER index
     struct { int ld; size_t row_bytes; } a = {master ? h->ldm : h->ld, master ? h->mrow_bytes : h->row_bytes};
     p.n = h->n;

@@ -115,6 +115,32 @@ def test_fp32_ip_shapes(n, d, ks):
     ix.close()
 
 
+def test_very_long_rows_and_non_finite_values():
+    """d = 20000 (80 KB rows, 20 chunks per row, fewer warps per CTA) and rows holding NaN / inf:
+    a NaN score ranks last (as -inf), +inf ranks first, the other rows are unaffected."""
+    rng = np.random.default_rng(12)
+    x = unit_rows(rng, 300, 20000)
+    q = unit_rows(rng, 2, 20000)
+    ix, oracle = make_index(x), make_oracle(x)
+    D, I = ix.search(q, 20)
+    check_against_oracle(D, I, oracle, q, 20)
+    ix.close()
+    x = unit_rows(rng, 500, 64)
+    x[7, 3] = np.nan
+    x[9, :] = 0
+    x[9, 0] = np.inf
+    q = np.abs(unit_rows(rng, 1, 64))
+    ix = make_index(x)
+    D, I = ix.search(q, 500)
+    assert I[0, 0] == 9 and np.isposinf(D[0, 0])
+    assert I[0, -1] == 7 and np.isneginf(D[0, -1])
+    clean = np.delete(np.arange(500), [7, 9])
+    o = make_oracle(x[clean])
+    Dw, Iw = o.search(q, 498)
+    assert np.array_equal(clean[Iw[0]], I[0, 1:-1]) or np.allclose(D[0, 1:-1], Dw[0], rtol=1e-5, atol=1e-6)
+    ix.close()
+
+
 def test_reference_tie_cases():
     """tests/test_vector_store.py:35-51 / :150-161 / tests/test_searcher.py:323-350 of the reference."""
     for d in (8, 768, 1024, 4096):
