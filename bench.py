@@ -52,6 +52,8 @@ def parse_args():
     ap.add_argument("--ctas-per-sm", type=int, default=0)
     ap.add_argument("--workload", default="headline", choices=["headline", "config5"],
                     help="config5 = BASELINE.json configs[4]: 100M x 768 bf16 over the ranks, image->image by stored id, recall@100 vs fp32")
+    ap.add_argument("--tier", default="bf16", choices=["bf16", "mixed"],
+                    help="config5 storage: bf16 only, or bf16 rows + fp32 master (exact results)")
     ap.add_argument("--exchange", default="auto", choices=["auto", "p2p", "nccl"],
                     help="N>1: candidate exchange fused into the kernels over NVLink peer mappings (p2p) or NCCL all-gather")
     return ap.parse_args()
@@ -446,6 +448,10 @@ def run_extras(torch, _native, index, queries, rows, d, k, device, esize):
         ms = time_device_search(torch, index, q_ptrs, kk, None, 20)
         out[f"k={kk}"] = {"ms": ms, "qps": 1e3 / ms, "GBps": rows * d * esize / ms / 1e6}
     try:
+        out.update(run_vector_store_call(index, queries, rows, k))
+    except Exception as exc:
+        out["vector_store_search/error"] = repr(exc)[:200]
+    try:
         out.update(run_config1(torch, _native, device))
     except Exception as exc:
         out["config1/error"] = repr(exc)[:200]
@@ -484,6 +490,29 @@ def run_mixed_tier(torch, _native, index, queries, rows, d, k, device):
     return {"bf16+fp32_master": {"ms": ms, "qps": 1e3 / ms, "bytes_streamed_per_query": rows * d * 2,
                                  "hbm_GBps": rows * d * 2 / ms / 1e6, "bit_identical_to_fp32_index": same,
                                  "note": "exact results at half the bytes per query, 1.5x the HBM footprint"}}
+
+
+def run_vector_store_call(index, queries, rows, k):
+    """The reference-facing call itself: VectorStore.search(query_embedding: List[float], top_k) -> List[Dict]
+    (utils/vector_store.py:172-198) on the resident 10M-row index, Python list in, list of dicts out."""
+    from photo_search_engine_b200.vector_store import VectorStore
+
+    store = VectorStore(None, "/tmp/_bench_unused.index", "/tmp/_bench_unused.json")
+    store.dimension = index.d
+    store.index = index
+    shared = {"photo_path": "synthetic"}
+    store.metadata = [shared] * rows  # one placeholder record: the bench has no photo metadata
+    qs = [queries[i].cpu().tolist() for i in range(8)]
+    for i in range(3):
+        hits = store.search(qs[i], k)
+    t0 = time.perf_counter()
+    n = 30
+    for i in range(n):
+        hits = store.search(qs[i % 8], k)
+    ms = (time.perf_counter() - t0) / n * 1e3
+    store.index = None  # the bench owns the index
+    return {"vector_store_search": {"ms_per_call": ms, "qps": 1e3 / ms, "hits": len(hits),
+                                    "note": "drop-in VectorStore.search: list->fp32, normalise, psx_search (H2D, scan, D2H), k result dicts"}}
 
 
 def run_config1(torch, _native, device):
@@ -676,7 +705,8 @@ def run_config5(args):
     d, k, nq = 768, 100, 32
     bounds = shard_bounds(rows, world)
     lo, hi = bounds[rank], bounds[rank + 1]
-    lo_p = _native.NativeIndex(d, _native.METRIC_IP, _native.STORE_BF16, local_rank)
+    tier = _native.STORE_BF16_MASTER if args.tier == "mixed" else _native.STORE_BF16
+    lo_p = _native.NativeIndex(d, _native.METRIC_IP, tier, local_rank)
     hi_p = _native.NativeIndex(d, _native.METRIC_IP, _native.STORE_F32, local_rank)
     lo_p.reserve(hi - lo)
     hi_p.reserve(hi - lo)
@@ -743,8 +773,9 @@ def run_config5(args):
         emit({"metric": "QPS, flat-IP top-100 over 100M x 768 bf16 rows, query = stored row by id (BASELINE.json configs[4])",
               "value": 1e3 / ms, "unit": "queries/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
               "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-              "dtype": "bf16 storage, f32 accumulate", "data": "synthetic",
-              "config": {"workload": f"{rows}x{d} bf16 row-sharded x{world}, image->image by id, top-{k}, self excluded",
+              "dtype": "bf16 storage, f32 accumulate" + (", exact fp32 re-score on the master copy" if args.tier == "mixed" else ""),
+              "data": "synthetic",
+              "config": {"workload": f"{rows}x{d} {'bf16+fp32 master' if args.tier == 'mixed' else 'bf16'} row-sharded x{world}, image->image by id, top-{k}, self excluded",
                          "rows": rows, "dim": d, "k": k, "rows_per_gpu": hi - lo, "exchange": lo_s.exchange,
                          "l2_policy": "inputs larger than L2"},
               "recall_at_100_vs_fp32_exact": recall, "recall_queries": nq,
