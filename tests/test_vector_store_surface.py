@@ -303,3 +303,69 @@ def test_batch_api(VS, tmp_path):
         assert np.allclose([h["distance"] for h in single], D[qi], rtol=1e-6, atol=1e-7)
     D, I = s.search_batch(q, 400)
     assert D.shape == (5, 400) and (I[:, 300:] == -1).all() and np.isinf(D[:, 300:]).all()
+
+
+# ---- the three reference tests that drive a real store with data through Searcher ------------------
+# (tests/test_searcher.py:293-321, 323-350, 352-406), restated at the VectorStore level: what Searcher
+# does around the store there is get_embedding_by_photo_path -> search(k = max(top_k+1, 5*top_k) clamped
+# to N) -> drop the query photo -> dedupe by path (core/searcher.py:1759-1786, 1839-1850).
+def _image_search(store, photo_path, top_k):
+    emb = store.get_embedding_by_photo_path(photo_path)
+    assert emb is not None
+    n = store.get_total_items()
+    hits = store.search(emb, min(n, max(top_k + 1, top_k * 5)))
+    seen, out = set(), []
+    for h in hits:
+        p = h["metadata"]["photo_path"]
+        if p == photo_path or p in seen:
+            continue
+        seen.add(p)
+        out.append(h)
+    return out[:top_k]
+
+
+def test_search_by_image_path_excludes_self(VS, tmp_path):
+    s = VS(8, *_paths(tmp_path))
+    paths = [f"/photos/photo_{i}.jpg" for i in range(3)]
+    for i, p in enumerate(paths):
+        s.add_item([float(i + o) for o in range(8)], {"photo_path": p, "description": f"图片 {i}"})
+    s.save()
+    t = VS(8, s.index_path, s.metadata_path)
+    assert t.load()
+    res = _image_search(t, paths[0], 2)
+    assert len(res) == 2 and all(h["metadata"]["photo_path"] != paths[0] for h in res)
+    assert [h["metadata"]["photo_path"] for h in res] == [paths[1], paths[2]]  # nearest first
+
+
+def test_search_by_image_path_deduplicates_same_photo(VS, tmp_path):
+    s = VS(8, *_paths(tmp_path))
+    s.add_item([1.0] * 8, {"photo_path": "/q.jpg", "description": "query"})
+    s.add_item([0.9] * 8, {"photo_path": "/dup.jpg", "description": "dup-a"})
+    s.add_item([0.9] * 8, {"photo_path": "/dup.jpg", "description": "dup-b"})
+    s.add_item([0.8] * 8, {"photo_path": "/other.jpg", "description": "other"})
+    res = _image_search(s, "/q.jpg", 3)
+    got = [h["metadata"]["photo_path"] for h in res]
+    assert got.count("/dup.jpg") == 1 and set(got) == {"/dup.jpg", "/other.jpg"}
+    # all four rows normalise to the same direction: exact ties come back in insertion order
+    full = s.search([1.0] * 8, 4)
+    assert [h["metadata"]["description"] for h in full] == ["query", "dup-a", "dup-b", "other"]
+
+
+def test_search_with_fake_embedding_service_vectors(VS, tmp_path):
+    """tests/helpers.py FakeEmbeddingService vectors (seed + i): nearly parallel rows, tiny score gaps."""
+    def fake(text, d=8):
+        seed = float(sum(ord(c) for c in text) % 13)
+        return [seed + float(i) for i in range(d)]
+
+    s = VS(8, *_paths(tmp_path))
+    texts = [f"photo 图片 {i}" for i in range(3)]
+    for i, tx in enumerate(texts):
+        s.add_item([float(i + o) for o in range(8)], {"photo_path": f"/p{i}.jpg", "retrieval_text": tx})
+    res = s.search(fake("photo 图片 1 上传图片"), max(2 * 5, 2 + 5))
+    assert len(res) == 3 and {h["metadata"]["photo_path"] for h in res} == {"/p0.jpg", "/p1.jpg", "/p2.jpg"}
+    want = O.OracleVectorStore(8, str(tmp_path / "o"), str(tmp_path / "om"))
+    for i, tx in enumerate(texts):
+        want.add_item([float(i + o) for o in range(8)], {"photo_path": f"/p{i}.jpg"})
+    ref = want.search(fake("photo 图片 1 上传图片"), 7)
+    assert [h["metadata"]["photo_path"] for h in res] == [h["metadata"]["photo_path"] for h in ref]
+    assert np.allclose([h["distance"] for h in res], [h["distance"] for h in ref], rtol=1e-5, atol=1e-6)
