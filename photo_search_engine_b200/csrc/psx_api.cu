@@ -98,6 +98,7 @@ struct psx_index {
     float* dmax_sumsq = nullptr;  // device: max ||stored row||^2, maintained by the pack kernel
     float max_norm = 0.f;         // host copy of its square root
     int batch_min = 4;        // smallest nq routed to the tensor-core path
+    bool batch_pair = true;   // 129..256 queries: CTA-pair (cta_group::2) kernel instead of two accumulators per CTA
     float* bq = nullptr;      // [256][ld] zero-padded query block
     float* btheta = nullptr;  // [256]
     int* bcount = nullptr;    // [256]
@@ -127,7 +128,22 @@ struct BatchCfg {
     static constexpr int BN = MT == 2 ? 128 : 256;
     static constexpr int STAGES = 4;  // 48 KB per stage either way
 };
-static int batch_bn(int mt) { return mt == 2 ? BatchCfg<2>::BN : BatchCfg<1>::BN; }
+constexpr int PAIR_STAGES = 6;
+static int batch_bn(int mt, bool pair) { return mt == 2 ? (pair ? 256 : BatchCfg<2>::BN) : BatchCfg<1>::BN; }
+
+// cta_group::2 variant for 129..256 queries: grid = 2 * pairs, cluster (2,1,1) is a kernel attribute
+static int launch_gemm_pair(psx_index* h, const CUtensorMap& mq, const CUtensorMap& mx, const GemmParams& gp, int pairs, cudaStream_t st) {
+    constexpr size_t smem = (size_t)PAIR_STAGES * (GEMM_M + 128) * GEMM_BK * 4 + 256;
+    static std::atomic<bool> ready[64];
+    if (h->device < 64 && !ready[h->device].load()) {
+        CU(cudaFuncSetAttribute(gemm_filter_pair_kernel<PAIR_STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ready[h->device].store(true);
+    }
+    gemm_filter_pair_kernel<PAIR_STAGES><<<2 * pairs, GEMM_THREADS, smem, st>>>(mq, mx, gp);
+    g_launches++;
+    CU(cudaGetLastError());
+    return PSX_OK;
+}
 
 static int pow2ceil(long long v) {
     long long p = 1;
@@ -731,15 +747,17 @@ static int launch_gemm(psx_index* h, const CUtensorMap& mq, const CUtensorMap& m
 static int launch_batch(psx_index* h, const float* q_dev, int nq, int k, uint32_t id_base, float qnorm_max, float* out_scores,
                         long long* out_ids, uint64_t* out_keys, int* flags_dev, cudaStream_t st) {
     const int MT = nq > GEMM_M ? 2 : 1;
-    const int BATCH_BN = batch_bn(MT);
+    const bool pair = MT == 2 && h->batch_pair;
+    const int BATCH_BN = batch_bn(MT, pair);
     const int num_tiles = (int)((h->n + BATCH_BN - 1) / BATCH_BN);
-    // theta from a strided sample: aim at ~16 sample scores above the threshold that ~T rows pass
-    const int T = 4 * k + 64;
-    int tile_step = T / 16;
+    // theta from a strided sample: aim at ~8 sample scores above the threshold that ~T rows pass (the
+    // threshold only has to land between the k-th and roughly the 2T-th score; the certificate decides)
+    const int T = 3 * k + 48;
+    int tile_step = T / 8;
     if (tile_step < 1) tile_step = 1;
     while (tile_step > 1 && num_tiles / tile_step < 64) --tile_step;
     const int sample_tiles = (num_tiles + tile_step - 1) / tile_step;
-    const int grid_s = std::min(h->sm_count, sample_tiles);
+    const int grid_s = pair ? std::min(h->sm_count / 2, sample_tiles) : std::min(h->sm_count, sample_tiles);
     const int sample_ld = sample_tiles * BATCH_BN;  // sample tile ordinals are 0 .. sample_tiles-1
     int rc = ensure_batch_scratch(h, (size_t)MT * GEMM_M * sample_ld);
     if (rc) return rc;
@@ -750,7 +768,7 @@ static int launch_batch(psx_index* h, const float* q_dev, int nq, int k, uint32_
                          cudaMemcpyDeviceToDevice, st));
     CUtensorMap mq, mx;
     if ((rc = make_map(&mq, h->bq, (long long)MT * GEMM_M, h->d, fld, GEMM_M))) return rc;
-    if ((rc = make_map(&mx, fp32_rows(h), h->n, h->d, fld, BATCH_BN))) return rc;
+    if ((rc = make_map(&mx, fp32_rows(h), h->n, h->d, fld, pair ? 128 : BATCH_BN))) return rc;
     GemmParams gp;
     memset(&gp, 0, sizeof gp);
     gp.n = h->n;
@@ -767,7 +785,8 @@ static int launch_batch(psx_index* h, const float* q_dev, int nq, int k, uint32_
     gp.mode = GEMM_MODE_SAMPLE;
     gp.tile_step = tile_step;
     DBG_SYNC(st, "query staging");
-    rc = MT == 2 ? launch_gemm<2>(h, mq, mx, gp, grid_s, st) : launch_gemm<1>(h, mq, mx, gp, grid_s, st);
+    rc = pair ? launch_gemm_pair(h, mq, mx, gp, grid_s, st)
+              : MT == 2 ? launch_gemm<2>(h, mq, mx, gp, grid_s, st) : launch_gemm<1>(h, mq, mx, gp, grid_s, st);
     if (rc) return rc;
     DBG_SYNC(st, "gemm_filter_kernel(sample)");
     const long long sample_rows = std::min<long long>(h->n, (long long)sample_tiles * BATCH_BN);
@@ -784,8 +803,9 @@ static int launch_batch(psx_index* h, const float* q_dev, int nq, int k, uint32_
     // pass 2: every tile, threshold test fused into the epilogue
     gp.mode = GEMM_MODE_FILTER;
     gp.tile_step = 1;
-    const int grid_f = std::min(h->sm_count, num_tiles);
-    rc = MT == 2 ? launch_gemm<2>(h, mq, mx, gp, grid_f, st) : launch_gemm<1>(h, mq, mx, gp, grid_f, st);
+    const int grid_f = pair ? std::min(h->sm_count / 2, num_tiles) : std::min(h->sm_count, num_tiles);
+    rc = pair ? launch_gemm_pair(h, mq, mx, gp, grid_f, st)
+              : MT == 2 ? launch_gemm<2>(h, mq, mx, gp, grid_f, st) : launch_gemm<1>(h, mq, mx, gp, grid_f, st);
     if (rc) return rc;
     DBG_SYNC(st, "gemm_filter_kernel(filter)");
     // exact re-score of the survivors + top-k + proof obligation
@@ -1266,6 +1286,8 @@ extern "C" int psx_set_tunable(psx_index* h, const char* key, int value) {
         h->stages_auto = value <= 0;
     } else if (!strcmp(key, "ctas_per_sm")) {
         h->ctas_per_sm = value <= 0 ? 1 : std::min(value, 8);
+    } else if (!strcmp(key, "batch_pair")) {
+        h->batch_pair = value > 0;
     } else if (!strcmp(key, "batch_min")) {  // smallest nq sent to the tensor-core path; 0 disables it
         h->batch_min = value < 0 ? 4 : value;
     } else {

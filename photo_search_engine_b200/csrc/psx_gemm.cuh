@@ -273,6 +273,246 @@ gemm_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
     }
 }
 
+// ---- CTA-pair variant (cta_group::2) for 129..256 queries ------------------------------------------------
+// Two CTAs of a cluster (= two SMs of a TPC) cooperate on one 256 x 256 tile per step: CTA r holds queries
+// [128r, 128r+128) (A rows) and corpus rows [256t + 128r, +128) (half of B); the leader issues ONE
+// tcgen05.mma.cta_group::2 (M = 256) that reads both halves and writes each CTA's own 128 TMEM lanes.  Per
+// CTA a pipeline stage is 16 KB (A) + 16 KB (B) instead of 32 + 16, so the ring is 6 deep instead of 4 and
+// the query block is re-read from L2 once per 256 corpus rows instead of once per 128.
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t cta) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(cta));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    // default semantics (as CUTLASS' ClusterBarrier::arrive): an explicit .release.cluster here costs ~1500 cycles per
+    // call -- it waits for the thread's outstanding TMA issues to become visible cluster-wide
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t smem_dst, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm(uint32_t bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+                 "h"(mask)
+                 : "memory");
+}
+__device__ __forceinline__ void umma_tf32_2sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// TMA load whose completion bytes are credited to the LEADER CTA's mbarrier (peer bit of the address cleared)
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+        "l"(map), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1)
+        : "memory");
+}
+
+template <int STAGES>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+gemm_filter_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_x, const GemmParams p) {
+    constexpr int BN = 256;              // corpus rows per pair tile (128 per CTA)
+    constexpr int ACC_STAGES = 2;        // 2 x 256 TMEM columns
+    constexpr int A_BYTES = GEMM_M * GEMM_BK * 4;        // this CTA's 128 queries
+    constexpr int B_BYTES = (BN / 2) * GEMM_BK * 4;      // this CTA's 128 corpus rows
+    constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char* tiles = smem_raw;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(tiles + (size_t)STAGES * STAGE_BYTES);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* acc_full = empty_bar + STAGES;
+    uint64_t* acc_empty = acc_full + ACC_STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + ACC_STAGES);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t cta = cluster_ctarank();
+    const bool leader = cta == 0;
+    const int kblocks = (p.d + GEMM_BK - 1) / GEMM_BK;
+    const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&map_q);
+        tma_prefetch_desc(&map_x);
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(smem_u32(full_bar + s), 2);   // leader: own arrive.expect_tx + the peer's arrive
+            mbar_init(smem_u32(empty_bar + s), 1);  // multicast commit of the leader's MMA thread
+        }
+        for (int a = 0; a < ACC_STAGES; ++a) {
+            mbar_init(smem_u32(acc_full + a), 1);   // multicast commit
+            mbar_init(smem_u32(acc_empty + a), 8);  // four epilogue warps in each of the two CTAs
+        }
+        mbar_fence_init();
+    }
+    if (warp == 2) tmem_alloc_2sm(smem_u32(tmem_slot), 512);
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int first = pair * p.tile_step;
+    const int stride = npairs * p.tile_step;
+
+    if (warp == 0) {
+        // ===== TMA producer (both CTAs; bytes land on the leader's full barrier) =====
+        if (lane == 0) {
+            int s = 0;
+            uint32_t ph = 0;
+#ifdef PSX_DEBUG_KERNELS
+            long long w_empty = 0, t_all = clock64(), nkb = 0;
+#endif
+            for (int t = first; t < p.num_tiles; t += stride) {
+                const int row0 = t * BN + (int)cta * (BN / 2);
+                for (int kb = 0; kb < kblocks; ++kb) {
+#ifdef PSX_DEBUG_KERNELS
+                    long long c0 = clock64();
+                    mbar_wait(smem_u32(empty_bar + s), ph ^ 1u);
+                    w_empty += clock64() - c0;
+                    ++nkb;
+#else
+                    mbar_wait(smem_u32(empty_bar + s), ph ^ 1u);
+#endif
+                    const uint32_t bar = smem_u32(full_bar + s);
+                    const uint32_t a_dst = smem_u32(tiles + (size_t)s * STAGE_BYTES);
+                    if (leader) mbar_arrive_expect_tx(bar, 2 * STAGE_BYTES);
+                    tma_load_2d_2sm(a_dst, &map_q, bar, kb * GEMM_BK, (int)cta * GEMM_M);
+                    tma_load_2d_2sm(a_dst + A_BYTES, &map_x, bar, kb * GEMM_BK, row0);
+                    if (!leader) mbar_arrive_cluster(mapa_shared(bar, 0));
+                    if (++s == STAGES) {
+                        s = 0;
+                        ph ^= 1u;
+                    }
+                }
+            }
+#ifdef PSX_DEBUG_KERNELS
+            if (blockIdx.x < 2) printf("pair producer cta %u: total %lld cyc, %lld kblocks, wait(empty) %lld\n", cta, clock64() - t_all, nkb, w_empty);
+#endif
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer: one thread of the leader CTA drives both tensor cores =====
+        if (leader && lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_tf32(2 * GEMM_M, BN);
+            int s = 0, a = 0;
+            uint32_t ph = 0, aph = 0;
+#ifdef PSX_DEBUG_KERNELS
+            long long w_full = 0, w_acc = 0, t_all = clock64(), nkb = 0;
+#endif
+            for (int t = first; t < p.num_tiles; t += stride) {
+#ifdef PSX_DEBUG_KERNELS
+                long long c0 = clock64();
+#endif
+                mbar_wait(smem_u32(acc_empty + a), aph ^ 1u);
+#ifdef PSX_DEBUG_KERNELS
+                w_acc += clock64() - c0;
+#endif
+                tc_fence_after();
+                for (int kb = 0; kb < kblocks; ++kb) {
+#ifdef PSX_DEBUG_KERNELS
+                    long long c1 = clock64();
+#endif
+                    mbar_wait(smem_u32(full_bar + s), ph);
+#ifdef PSX_DEBUG_KERNELS
+                    w_full += clock64() - c1;
+                    ++nkb;
+#endif
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_u32(tiles + (size_t)s * STAGE_BYTES);
+                    const uint64_t a_desc = umma_smem_desc(a_addr);
+                    const uint64_t b_desc = umma_smem_desc(a_addr + A_BYTES);
+                    const uint32_t d_addr = tmem_base + (uint32_t)(a * BN);
+#pragma unroll
+                    for (int k = 0; k < GEMM_BK / GEMM_UMMA_K; ++k) umma_tf32_2sm(d_addr, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+                    umma_commit_2sm(smem_u32(empty_bar + s), 3);
+                    if (++s == STAGES) {
+                        s = 0;
+                        ph ^= 1u;
+                    }
+                }
+                umma_commit_2sm(smem_u32(acc_full + a), 3);
+                if (++a == ACC_STAGES) {
+                    a = 0;
+                    aph ^= 1u;
+                }
+            }
+#ifdef PSX_DEBUG_KERNELS
+            if (blockIdx.x == 0)
+                printf("pair mma: total %lld cyc, %lld kblocks, wait(full) %lld, wait(acc_empty) %lld\n", clock64() - t_all, nkb, w_full, w_acc);
+#endif
+        }
+    } else if (warp >= 4) {
+        // ===== epilogue (each CTA drains its own 128 TMEM lanes = its 128 queries) =====
+        const int ew = warp - 4;
+        const int qi = (int)cta * GEMM_M + ew * 32 + lane;
+        const float theta = (p.mode == GEMM_MODE_FILTER && qi < p.nq) ? p.theta[qi] : INFINITY;
+        const uint32_t leader_acc_empty = mapa_shared(smem_u32(acc_empty), 0);
+        int a = 0, tile_no = 0;
+        uint32_t aph = 0;
+        for (int t = first; t < p.num_tiles; t += stride, ++tile_no) {
+            mbar_wait(smem_u32(acc_full + a), aph);
+            tc_fence_after();
+            const long long row0 = (long long)t * BN;
+            const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(a * BN);
+#pragma unroll 1
+            for (int c = 0; c < BN / 32; ++c) {
+                uint32_t r[32];
+                tmem_ld_32x32(taddr + c * 32, r);
+                if (p.mode == GEMM_MODE_FILTER) {
+                    float mx = __uint_as_float(r[0]);
+#pragma unroll
+                    for (int j = 1; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(r[j]));
+                    if (mx >= theta) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const long long row = row0 + c * 32 + j;
+                            if (__uint_as_float(r[j]) >= theta && row < p.n) {
+                                const int pos = atomicAdd(p.cand_count + qi, 1);
+                                if (pos < p.cand_cap) p.cand_ids[(size_t)qi * p.cand_cap + pos] = (uint32_t)row;
+                            }
+                        }
+                    }
+                } else if (qi < p.nq) {
+                    float* dst = p.sample_scores + (size_t)qi * p.sample_ld + ((size_t)(pair + (size_t)tile_no * npairs)) * BN + c * 32;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const long long row = row0 + c * 32 + j;
+                        dst[j] = row < p.n ? __uint_as_float(r[j]) : -INFINITY;
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(leader_acc_empty + a * 8);
+            if (++a == ACC_STAGES) {
+                a = 0;
+                aph ^= 1u;
+            }
+        }
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc_2sm(tmem_base, 512);
+    }
+}
+
 // ---- theta: per query, an approximate T-th largest of its sample scores -------------------------------
 // One CTA per query.  Every thread keeps the two largest values of its strided share; the 2*256
 // survivors are sorted and the element at the requested rank is taken.  Approximate by design: the

@@ -59,6 +59,25 @@ def test_batch_equals_scan(n, d, nq, k):
     ix.close()
 
 
+@pytest.mark.parametrize("n,d,nq,k", [(150_000, 1024, 200, 100), (100_000, 768, 300, 50), (70_000, 96, 129, 10)])
+def test_cta_pair_kernel_equals_scan(n, d, nq, k):
+    """The cta_group::2 variant (two SMs share one 256 x 256 tile, M = 256 MMAs issued by the leader CTA)."""
+    rng = np.random.default_rng(n + d + nq + 1)
+    x = unit_rows(rng, n, d)
+    q = unit_rows(rng, nq, d)
+    q[0] = x[4321]
+    q[nq - 1] = x[99]                     # a query handled by the second CTA of the pair
+    ix = N().NativeIndex(d)
+    ix.add(x)
+    ix.set_tunable("batch_pair", 1)
+    (Ds, Is), (Db, Ib), (served, fallbacks) = _both_paths(ix, q, k)
+    assert served == nq
+    assert np.array_equal(Ib, Is) and np.array_equal(Db, Ds)
+    assert Ib[0, 0] == 4321 and Ib[nq - 1, 0] == 99
+    assert fallbacks <= nq // 10
+    ix.close()
+
+
 def test_batch_on_clustered_data_with_duplicates():
     """Tight clusters + exact duplicates: tiny score gaps make the TF32 proof fail for some
     queries; the fallback must keep every answer exact and ties ordered by id."""

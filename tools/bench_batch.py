@@ -22,9 +22,12 @@ def main():
     ap.add_argument("--k", type=int, default=100)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--clustered", action="store_true")
+    ap.add_argument("--pair", action="store_true", help="cta_group::2 kernel for nq > 128")
     a = ap.parse_args()
     ix = _native.NativeIndex(a.dim)
     ix.reserve(a.rows)
+    if a.pair:
+        ix.set_tunable("batch_pair", 1)
     g = torch.Generator(device="cuda").manual_seed(1)
     done = 0
     cent = torch.randn((4096, a.dim), generator=g, device="cuda")
