@@ -159,9 +159,12 @@ int64_t psx_kpad(int64_t k);
  * top-k (bit-identical to psx_search_device); a non-zero flag means "not proven", the caller
  * re-runs that query with psx_search_device.  psx_search does both steps itself for nq >= the
  * "batch_min" tunable.  `qnorm_max` >= the largest L2 norm among the queries (1 for cosine).
- * fp32 inner-product indexes with >= 65536 rows, d >= 32, k <= 512. */
-int psx_search_batch_device(psx_index* h, const float* q_dev, int64_t nq, int64_t k, float qnorm_max, uint32_t id_base,
-                            float* out_scores_dev, int64_t* out_ids_dev, uint64_t* out_keys_dev, int* flags_dev, void* stream);
+ * `filter` (nullable) is the same EXIF predicate as in psx_search, shared by the whole batch: it is
+ * applied to the survivors in the epilogue and to the sample the thresholds come from.
+ * Inner-product indexes with fp32 rows (PSX_STORE_F32 / PSX_STORE_BF16_MASTER), >= 65536 rows, d >= 32, k <= 512. */
+int psx_search_batch_device(psx_index* h, const float* q_dev, int64_t nq, int64_t k, const psx_filter* filter, float qnorm_max,
+                            uint32_t id_base, float* out_scores_dev, int64_t* out_ids_dev, uint64_t* out_keys_dev,
+                            int* flags_dev, void* stream);
 /* queries served by the batched path so far, and how many of them had to be re-run on the scan */
 int psx_batch_stats(psx_index* h, int64_t* queries, int64_t* fallbacks);
 /* Final merge of `nlists` sorted key lists per query (layout [nq][nlists][kpad], e.g. the

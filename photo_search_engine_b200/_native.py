@@ -60,7 +60,7 @@ _SIGNATURES = [
     ("psx_search", C.c_int, [_P, _P, C.c_int64, C.c_int64, C.POINTER(PsxFilter), _P, _P]),
     ("psx_search_device", C.c_int, [_P, _P, C.c_int64, C.c_int64, C.POINTER(PsxFilter), C.c_uint32, _P, _P, _P, _P]),
     ("psx_kpad", C.c_int64, [C.c_int64]),
-    ("psx_search_batch_device", C.c_int, [_P, _P, C.c_int64, C.c_int64, C.c_float, C.c_uint32, _P, _P, _P, _P, _P]),
+    ("psx_search_batch_device", C.c_int, [_P, _P, C.c_int64, C.c_int64, C.POINTER(PsxFilter), C.c_float, C.c_uint32, _P, _P, _P, _P, _P]),
     ("psx_batch_stats", C.c_int, [_P, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     ("psx_merge_keys_device", C.c_int, [C.c_int, _P, C.c_int64, C.c_int64, C.c_int64, C.c_int, _P, _P, _P]),
     ("psx_exchange_bytes", C.c_int64, []),
@@ -205,8 +205,10 @@ class NativeIndex:
                                                    out_ids_ptr or None, stream or None))
 
     def search_batch_device(self, q_ptr: int, nq: int, k: int, out_scores_ptr: int, out_ids_ptr: int, flags_ptr: int,
-                            out_keys_ptr: int = 0, qnorm_max: float = 1.0, id_base: int = 0, stream: int = 0) -> None:
-        check(self._lib.psx_search_batch_device(self._h, q_ptr, int(nq), int(k), float(qnorm_max), int(id_base), out_scores_ptr,
+                            out_keys_ptr: int = 0, qnorm_max: float = 1.0, id_base: int = 0, stream: int = 0,
+                            flt: Optional[PsxFilter] = None) -> None:
+        fp = C.byref(flt) if flt is not None else None
+        check(self._lib.psx_search_batch_device(self._h, q_ptr, int(nq), int(k), fp, float(qnorm_max), int(id_base), out_scores_ptr,
                                                 out_ids_ptr, out_keys_ptr or None, flags_ptr, stream or None))
 
     def batch_stats(self):

@@ -687,7 +687,8 @@ static int make_map(CUtensorMap* map, const float* base, long long rows, int col
 }
 
 static bool batch_eligible(const psx_index* h, int64_t nq, int64_t k, const psx_filter* f) {
-    return h->metric == PSX_METRIC_IP && has_fp32_rows(h) && !(f && f->flags) && h->batch_min > 0 &&
+    (void)f;  // the predicate is applied in the epilogue (candidates) and in the sample (thresholds)
+    return h->metric == PSX_METRIC_IP && has_fp32_rows(h) && h->batch_min > 0 &&
            nq >= h->batch_min && k <= 512 && h->n >= 65536 && h->d >= 32;
 }
 
@@ -744,8 +745,8 @@ static int launch_gemm(psx_index* h, const CUtensorMap& mq, const CUtensorMap& m
 
 // One batch of nq <= 256 queries (device pointers).  flags_dev[qi] != 0 marks results that are not
 // proven exact; the caller re-runs those queries on the streaming scan.
-static int launch_batch(psx_index* h, const float* q_dev, int nq, int k, uint32_t id_base, float qnorm_max, float* out_scores,
-                        long long* out_ids, uint64_t* out_keys, int* flags_dev, cudaStream_t st) {
+static int launch_batch(psx_index* h, const float* q_dev, int nq, int k, const psx_filter* f, uint32_t id_base, float qnorm_max,
+                        float* out_scores, long long* out_ids, uint64_t* out_keys, int* flags_dev, cudaStream_t st) {
     const int MT = nq > GEMM_M ? 2 : 1;
     const bool pair = MT == 2 && h->batch_pair;
     const int BATCH_BN = batch_bn(MT, pair);
@@ -781,6 +782,10 @@ static int launch_batch(psx_index* h, const float* q_dev, int nq, int k, uint32_
     gp.cand_cap = BATCH_CAND_CAP;
     gp.sample_scores = h->bsample;
     gp.sample_ld = sample_ld;
+    if (f && f->flags) {
+        gp.attrs = h->attrs;
+        gp.f = *f;
+    }
     // pass 1: sample
     gp.mode = GEMM_MODE_SAMPLE;
     gp.tile_step = tile_step;
@@ -957,9 +962,9 @@ extern "C" int psx_search_exchange_device(psx_index* h, const float* q_dev, int6
     return leave_stream(h, st);
 }
 
-extern "C" int psx_search_batch_device(psx_index* h, const float* q_dev, int64_t nq, int64_t k, float qnorm_max, uint32_t id_base,
-                                       float* out_scores_dev, int64_t* out_ids_dev, uint64_t* out_keys_dev, int* flags_dev,
-                                       void* stream) {
+extern "C" int psx_search_batch_device(psx_index* h, const float* q_dev, int64_t nq, int64_t k, const psx_filter* filter,
+                                       float qnorm_max, uint32_t id_base, float* out_scores_dev, int64_t* out_ids_dev,
+                                       uint64_t* out_keys_dev, int* flags_dev, void* stream) {
     if (!h || !q_dev || !out_scores_dev || !out_ids_dev || !flags_dev || nq < 1)
         return fail(PSX_ERR_INVALID, "bad arguments to psx_search_batch_device");
     std::lock_guard<std::mutex> lk(h->mu);
@@ -973,7 +978,7 @@ extern "C" int psx_search_batch_device(psx_index* h, const float* q_dev, int64_t
     const int64_t kpad = psx_kpad(k);
     for (int64_t q0 = 0; q0 < nq; q0 += BATCH_MAX_Q) {
         const int gq = (int)std::min<int64_t>(BATCH_MAX_Q, nq - q0);
-        rc = launch_batch(h, q_dev + q0 * h->d, gq, (int)k, id_base, qnorm_max, out_scores_dev + q0 * k,
+        rc = launch_batch(h, q_dev + q0 * h->d, gq, (int)k, filter, id_base, qnorm_max, out_scores_dev + q0 * k,
                           (long long*)out_ids_dev + q0 * k, out_keys_dev ? out_keys_dev + q0 * kpad : nullptr, flags_dev + q0, st);
         if (rc) return rc;
     }
@@ -1046,8 +1051,8 @@ static int ensure_io(psx_index* h, size_t qfloats, size_t outs) {
 }
 
 // Host-buffer batch search through the tensor-core path; unproven queries are re-run on the scan.
-static int search_batched_host(psx_index* h, const float* q, int64_t nq, int64_t kk, int64_t k, float* out_scores,
-                               int64_t* out_ids) {
+static int search_batched_host(psx_index* h, const float* q, int64_t nq, int64_t kk, int64_t k, const psx_filter* filter,
+                               float* out_scores, int64_t* out_ids) {
     int rc;
     cudaStream_t st = h->stream;
     if ((rc = ensure_batch_scratch(h, 0))) return rc;  // h->bflags / h->hflags must exist before they are passed on
@@ -1064,14 +1069,15 @@ static int search_batched_host(psx_index* h, const float* q, int64_t nq, int64_t
             qn2 = std::max(qn2, (float)acc);
         }
         CU(cudaMemcpyAsync(h->dq, h->hq, (size_t)gq * h->d * sizeof(float), cudaMemcpyHostToDevice, st));
-        if ((rc = launch_batch(h, h->dq, gq, (int)kk, 0, sqrtf(qn2) * 1.0001f, h->dscores, h->dids, nullptr, h->bflags, st))) return rc;
+        if ((rc = launch_batch(h, h->dq, gq, (int)kk, filter, 0, sqrtf(qn2) * 1.0001f, h->dscores, h->dids, nullptr, h->bflags, st)))
+            return rc;
         CU(cudaMemcpyAsync(h->hflags, h->bflags, gq * sizeof(int), cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
         h->batch_queries += gq;
         for (int qi = 0; qi < gq; ++qi) {
             if (!h->hflags[qi]) continue;
             h->batch_fallbacks++;
-            rc = launch_exact_scan(h, h->dq + (size_t)qi * h->d, (int)kk, nullptr, 0, nullptr, h->dscores + (size_t)qi * kk,
+            rc = launch_exact_scan(h, h->dq + (size_t)qi * h->d, (int)kk, filter, 0, nullptr, h->dscores + (size_t)qi * kk,
                                    h->dids + (size_t)qi * kk, nullptr, st);
             if (rc) return rc;
         }
@@ -1111,7 +1117,7 @@ extern "C" int psx_search(psx_index* h, const float* q, int64_t nq, int64_t k, c
     }
     // results beyond ntotal can never be filled: scan for min(k, n) and pad on the host
     const int64_t kk = std::min<int64_t>(k, h->n);
-    if (batch_eligible(h, nq, kk, filter)) return search_batched_host(h, q, nq, kk, k, out_scores, out_ids);
+    if (batch_eligible(h, nq, kk, filter)) return search_batched_host(h, q, nq, kk, k, filter, out_scores, out_ids);
     const int64_t pages = (kk + PSX_K_PASS_MAX - 1) / PSX_K_PASS_MAX;
     // per-query stride of the device outputs
     const int64_t kslot = pages == 1 ? psx_kpad(kk) : pages * PSX_K_PASS_MAX;

@@ -45,7 +45,28 @@ struct GemmParams {
     int cand_cap;
     float* sample_scores;    // [nq][sample_ld] (MODE_SAMPLE)
     int sample_ld;
+    const uint64_t* attrs;   // EXIF words [n], or nullptr: rows failing `f` are neither sampled nor kept
+    psx_filter f;
 };
+
+// predicate on packed EXIF words (same conjunction as attr_pass in psx_scan.cuh; this header is included first)
+__device__ __forceinline__ bool gemm_attr_pass(uint64_t a, const psx_filter& f) {
+    const uint32_t fl = f.flags;
+    if (fl & (PSX_F_SEASON | PSX_F_PERIOD | PSX_F_YEAR | PSX_F_MONTH)) {
+        if (!(a >> 63)) return false;
+        if ((fl & PSX_F_SEASON) && (uint32_t)((a >> 60) & 7u) != f.season) return false;
+        if ((fl & PSX_F_PERIOD) && (uint32_t)((a >> 57) & 7u) != f.period) return false;
+        if ((fl & PSX_F_YEAR) && (uint32_t)((a >> 43) & 0x3fffu) != f.year) return false;
+        if ((fl & PSX_F_MONTH) && (uint32_t)((a >> 39) & 0xfu) != f.month) return false;
+    }
+    if (fl & PSX_F_NEED_DT) {
+        const uint64_t dt = a & ((1ull << 39) - 1);
+        if (!dt) return false;
+        if ((fl & PSX_F_START) && dt < f.start) return false;
+        if ((fl & PSX_F_END) && dt > f.end) return false;
+    }
+    return true;
+}
 
 // ---- PTX wrappers -----------------------------------------------------------------------------
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
@@ -239,7 +260,7 @@ gemm_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
 #pragma unroll
                             for (int j = 0; j < 32; ++j) {
                                 const long long row = row0 + c * 32 + j;
-                                if (__uint_as_float(r[j]) >= theta[m] && row < p.n) {
+                                if (__uint_as_float(r[j]) >= theta[m] && row < p.n && (!p.attrs || gemm_attr_pass(__ldg(p.attrs + row), p.f))) {
                                     const int pos = atomicAdd(p.cand_count + qi, 1);
                                     if (pos < p.cand_cap) p.cand_ids[(size_t)qi * p.cand_cap + pos] = (uint32_t)row;
                                 }
@@ -251,7 +272,7 @@ gemm_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
                             const long long row = row0 + c * 32 + j;
-                            dst[j] = row < p.n ? __uint_as_float(r[j]) : -INFINITY;
+                            dst[j] = (row < p.n && (!p.attrs || gemm_attr_pass(__ldg(p.attrs + row), p.f))) ? __uint_as_float(r[j]) : -INFINITY;
                         }
                     }
                 }
@@ -481,7 +502,7 @@ gemm_filter_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
                             const long long row = row0 + c * 32 + j;
-                            if (__uint_as_float(r[j]) >= theta && row < p.n) {
+                            if (__uint_as_float(r[j]) >= theta && row < p.n && (!p.attrs || gemm_attr_pass(__ldg(p.attrs + row), p.f))) {
                                 const int pos = atomicAdd(p.cand_count + qi, 1);
                                 if (pos < p.cand_cap) p.cand_ids[(size_t)qi * p.cand_cap + pos] = (uint32_t)row;
                             }
@@ -492,7 +513,7 @@ gemm_filter_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
                         const long long row = row0 + c * 32 + j;
-                        dst[j] = row < p.n ? __uint_as_float(r[j]) : -INFINITY;
+                        dst[j] = (row < p.n && (!p.attrs || gemm_attr_pass(__ldg(p.attrs + row), p.f))) ? __uint_as_float(r[j]) : -INFINITY;
                     }
                 }
             }

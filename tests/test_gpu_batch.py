@@ -78,6 +78,30 @@ def test_cta_pair_kernel_equals_scan(n, d, nq, k):
     ix.close()
 
 
+@pytest.mark.parametrize("nq", [40, 200])
+def test_batch_with_fused_predicate(nq):
+    """The EXIF predicate in the batched path (candidate epilogue + threshold sample) == the filtered scan."""
+    rng = np.random.default_rng(nq)
+    n, d, k = 120_000, 256, 100
+    x = unit_rows(rng, n, d)
+    q = unit_rows(rng, nq, d)
+    ix = N().NativeIndex(d)
+    ix.add(x)
+    ix.set_attrs(0, np.arange(n, dtype=np.uint64) + np.uint64(1))   # dt = 1 + row
+    for lo, hi in [(30_000, 90_000), (1, 3_000), (100_000, 100_050)]:  # 50 %, 2.5 %, fewer rows than k
+        flt = N().PsxFilter(flags=N().F_NEED_DT | N().F_START | N().F_END, start=lo, end=hi)
+        ix.set_tunable("batch_min", 0)
+        Ds, Is = ix.search(q, k, flt)
+        ix.set_tunable("batch_min", 2)
+        before = ix.batch_stats()
+        Db, Ib = ix.search(q, k, flt)
+        assert ix.batch_stats()[0] - before[0] == nq
+        assert np.array_equal(Ib, Is) and np.array_equal(Db, Ds), (lo, hi)
+        valid = Ib[Ib >= 0]
+        assert ((valid >= lo - 1) & (valid < hi)).all()
+    ix.close()
+
+
 def test_batch_on_clustered_data_with_duplicates():
     """Tight clusters + exact duplicates: tiny score gaps make the TF32 proof fail for some
     queries; the fallback must keep every answer exact and ties ordered by id."""
