@@ -116,6 +116,7 @@ class VectorStore:
         self._embeddings: List[Optional[List[float]]] = []
         self._path_to_index: Dict[str, int] = {}
         self._attrs_built = 0  # rows whose attribute word is already on the device
+        self._attr_words = np.zeros(0, np.uint64)  # host copy of those words (persisted by save())
         self.index = self._create_index(dimension) if dimension else None
 
     # ------------------------------------------------------------------------------------
@@ -158,12 +159,21 @@ class VectorStore:
             self._upload_attrs()
         return flt, never
 
+    @property
+    def attrs_path(self) -> str:
+        """Columnar EXIF sidecar next to the index file: one little-endian uint64 per row (layout:
+        include/psx.h).  Written by ``save()`` once the words exist, picked up by ``load()``; purely a
+        cache of what ``metadata.json`` says -- when it is missing or stale the words are re-packed."""
+        return self.index_path + ".attrs"
+
     def _upload_attrs(self) -> None:
         """Lazy EXIF sidecar: pack and upload attribute words for rows that lack one."""
         total = len(self.metadata)
         if self.index is None or self._attrs_built >= total:
             return
-        self.index.set_attrs(self._attrs_built, attr_words(self.metadata[self._attrs_built : total]))
+        words = attr_words(self.metadata[self._attrs_built : total])
+        self.index.set_attrs(self._attrs_built, words)
+        self._attr_words = np.concatenate([self._attr_words[: self._attrs_built], words])
         self._attrs_built = total
 
     def _run_search(self, queries: np.ndarray, k: int, flt) -> Tuple[np.ndarray, np.ndarray]:
@@ -308,6 +318,10 @@ class VectorStore:
         for target, payload in ((self.meta_path, settings), (self.metadata_path, self.metadata)):
             with open(target, "w", encoding="utf-8") as handle:
                 json.dump(payload, handle, ensure_ascii=False, indent=2)
+        if self._attrs_built == len(self.metadata) and self._attrs_built > 0:
+            self._attr_words.astype("<u8").tofile(self.attrs_path)
+        elif os.path.exists(self.attrs_path):
+            os.remove(self.attrs_path)  # never leave a sidecar that disagrees with metadata.json
 
     def _read_settings(self) -> Dict[str, Any]:
         """``.meta.json`` checks of utils/vector_store.py:116-140."""
@@ -350,6 +364,12 @@ class VectorStore:
         self.metadata = records
         self._embeddings = [None] * info["ntotal"]
         self._attrs_built = 0
+        self._attr_words = np.zeros(0, np.uint64)
+        if os.path.exists(self.attrs_path) and os.path.getsize(self.attrs_path) == 8 * info["ntotal"] and info["ntotal"] > 0 \
+                and os.path.getmtime(self.attrs_path) >= os.path.getmtime(self.metadata_path):
+            words = np.fromfile(self.attrs_path, dtype="<u8").astype(np.uint64)
+            self.index.set_attrs(0, words)
+            self._attr_words, self._attrs_built = words, info["ntotal"]
         self._path_to_index = {}
         for row, metadata in enumerate(records):
             self._remember_path(metadata, row)
@@ -367,3 +387,4 @@ class VectorStore:
         self._embeddings = []
         self._path_to_index = {}
         self._attrs_built = 0
+        self._attr_words = np.zeros(0, np.uint64)

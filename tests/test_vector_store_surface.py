@@ -369,3 +369,26 @@ def test_search_with_fake_embedding_service_vectors(VS, tmp_path):
     ref = want.search(fake("photo 图片 1 上传图片"), 7)
     assert [h["metadata"]["photo_path"] for h in res] == [h["metadata"]["photo_path"] for h in ref]
     assert np.allclose([h["distance"] for h in res], [h["distance"] for h in ref], rtol=1e-5, atol=1e-6)
+
+
+def test_exif_sidecar_round_trip(VS, tmp_path):
+    """<index>.attrs: written by save() once the words exist, reused by load(), ignored when stale."""
+    ip, mp = _paths(tmp_path)
+    s = VS(4, ip, mp)
+    for i in range(6):
+        t = f"202{i}-07-0{i + 1}T10:00:00"
+        s.add_item([1.0, i, 0, 0], {"photo_path": f"/{i}.jpg", "exif_data": {"datetime": t}, "time_info": O.time_info_from_exif(t)})
+    s.save()
+    assert not os.path.exists(ip + ".attrs")            # nothing packed yet: no sidecar
+    assert len(s.search([1, 0, 0, 0], 6, constraints={"year": 2023})) == 1
+    s.save()
+    assert os.path.getsize(ip + ".attrs") == 6 * 8
+    t2 = VS(4, ip, mp)
+    assert t2.load() and t2._attrs_built == 6             # words came from the sidecar
+    assert [h["metadata"]["photo_path"] for h in t2.search([1, 0, 0, 0], 6, constraints={"season": "夏天", "start_date": "2022-01-01"})] \
+        == [f"/{i}.jpg" for i in (2, 3, 4, 5)]
+    with open(ip + ".attrs", "ab") as f:                  # wrong size -> ignored, rebuilt lazily from metadata
+        f.write(b"x")
+    t3 = VS(4, ip, mp)
+    assert t3.load() and t3._attrs_built == 0
+    assert len(t3.search([1, 0, 0, 0], 6, constraints={"year": 2023})) == 1
