@@ -72,6 +72,7 @@ _SIGNATURES = [
     ("psx_read_rows", C.c_int, [_P, C.c_int64, C.c_int64, _P]),
     ("psx_storage_device", C.c_int, [_P, C.POINTER(_P), C.POINTER(C.c_int64), C.POINTER(C.c_int)]),
     ("psx_set_tunable", C.c_int, [_P, C.c_char_p, C.c_int]),
+    ("psx_set_trace_device", C.c_int, [_P, _P]),
     ("psx_launch_count", C.c_int64, []),
 ]
 EXPORTED_SYMBOLS = [s[0] for s in _SIGNATURES]
@@ -230,6 +231,9 @@ class NativeIndex:
         p, ld, dt = _P(), C.c_int64(), C.c_int()
         check(self._lib.psx_storage_device(self._h, C.byref(p), C.byref(ld), C.byref(dt)))
         return p.value or 0, ld.value, dt.value
+
+    def set_trace_device(self, ptr: int) -> None:
+        check(self._lib.psx_set_trace_device(self._h, ptr or None))
 
     def set_tunable(self, key: str, value: int) -> None:
         check(self._lib.psx_set_tunable(self._h, key.encode(), int(value)))

@@ -15,7 +15,8 @@
 #include "psx_aux.cuh"
 #include "psx_fuse.cuh"
 #include "psx_gemm.cuh"
-#include "psx_scan.cuh"
+#include "psx_merge.cuh"
+#include "psx_scan_launch.cuh"
 
 using namespace psx;
 
@@ -82,7 +83,13 @@ struct psx_index {
 
     uint64_t* lists = nullptr;  // [grid][kpad]
     size_t lists_cap = 0;
-    unsigned int* counter = nullptr;
+    unsigned int* counter = nullptr;  // [0] merge tickets, [1] dynamic-tail tickets, [2] entries of rowlist
+    uint32_t* rowlist = nullptr;      // [cap] ids of the rows that pass the current query's predicate
+    long long rowlist_cap = 0;
+    bool deal = true;        // unfiltered scans: dealt units with a dynamic tail (false: static predicate groups)
+    bool dyn_tail = true;
+    int static_batch = 8;
+    int filter_mode = 0;     // 0 = auto, 1 = predicate fused into the scan, 2 = predicate compacted into a row list first
     // device + pinned staging for the host-buffer API
     float* dq = nullptr;
     size_t dq_cap = 0;
@@ -110,6 +117,7 @@ struct psx_index {
     size_t bsample_cap = 0;
     int* hflags = nullptr;    // pinned [256]
     long long batch_fallbacks = 0, batch_queries = 0, mixed_queries = 0;
+    unsigned long long* trace = nullptr;  // diagnostics: phase timestamps of the next scans (caller-owned)
     std::mutex mu;
 };
 
@@ -205,8 +213,8 @@ extern "C" int psx_create(int d, int metric, int store_dtype, int device, psx_in
     auto init = [&]() -> int {
         CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
         CU(cudaEventCreateWithFlags(&h->last_ev, cudaEventDisableTiming));
-        CU(cudaMalloc(&h->counter, sizeof(unsigned int)));
-        CU(cudaMemset(h->counter, 0, sizeof(unsigned int)));
+        CU(cudaMalloc(&h->counter, 4 * sizeof(unsigned int)));
+        CU(cudaMemset(h->counter, 0, 4 * sizeof(unsigned int)));
         CU(cudaMalloc(&h->dmax_sumsq, sizeof(float)));
         CU(cudaMemset(h->dmax_sumsq, 0, sizeof(float)));
         return set_max_smem(merge_keys_kernel);
@@ -226,6 +234,7 @@ static void free_all(psx_index* h) {
     cudaFree(h->attrs);
     cudaFree(h->lists);
     cudaFree(h->counter);
+    cudaFree(h->rowlist);
     cudaFree(h->dq);
     cudaFree(h->dscores);
     cudaFree(h->dids);
@@ -472,26 +481,27 @@ extern "C" int psx_set_attrs_device(psx_index* h, int64_t row0, const uint64_t* 
 // ------------------------------------------------------------------------------------------
 struct ScanPlan {
     ScanParams p;
-    int grid, block;
+    int grid, block, mode;
     size_t smem;
 };
 
-static int plan_scan_with(psx_index* h, bool master, int k, int W, ScanPlan& plan);
+static int plan_scan_with(psx_index* h, bool master, int k, int W, int mode, bool listed, ScanPlan& plan);
 
 // Very long rows (d up to 32768: a 128 KB query block in shared memory) do not leave room for 16 warp
 // rings: retry with fewer warps before giving up.
-static int plan_scan(psx_index* h, bool master, int k, ScanPlan& plan) {
+static int plan_scan(psx_index* h, bool master, int k, int mode, bool listed, ScanPlan& plan) {
     int rc = PSX_ERR_INVALID;
     for (int W = h->warps; W >= 2; W >>= 1) {
-        rc = plan_scan_with(h, master, k, W, plan);
+        rc = plan_scan_with(h, master, k, W, mode, listed, plan);
         if (rc == PSX_OK) return rc;
     }
     return rc;
 }
 
-static int plan_scan_with(psx_index* h, bool master, int k, int W, ScanPlan& plan) {
+static int plan_scan_with(psx_index* h, bool master, int k, int W, int mode, bool listed, ScanPlan& plan) {
     ScanParams& p = plan.p;
     memset(&p, 0, sizeof p);
+    plan.mode = mode;
     // which arena is streamed: the scan rows, or the fp32 master of a PSX_STORE_BF16_MASTER index
     struct { int ld; size_t row_bytes; } a = {master ? h->ldm : h->ld, master ? h->mrow_bytes : h->row_bytes};
     p.n = h->n;
@@ -529,7 +539,7 @@ static int plan_scan_with(psx_index* h, bool master, int k, int W, ScanPlan& pla
     const int qpad = (a.ld + 7) & ~7;
     auto smem_for = [&](int S) {
         return (size_t)W * S * PSX_SLOT_BYTES + (size_t)qpad * 4 + (size_t)cap * 8 + (size_t)W * S * 8 + 8 +
-               (size_t)W * S * 8 + 16;
+               (size_t)W * S * 8 + 16 + (listed ? (size_t)W * S * 32 * 4 : 0);
     };
     // co-resident CTAs share the SM's 228 KB (1 KB per CTA is reserved by the driver)
     const size_t limit = h->ctas_per_sm <= 1 ? (size_t)PSX_SMEM_LIMIT : (size_t)(228 * 1024) / h->ctas_per_sm - 1024;
@@ -543,50 +553,32 @@ static int plan_scan_with(psx_index* h, bool master, int k, int W, ScanPlan& pla
         return fail(PSX_ERR_INVALID, "d=%d k=%d does not fit the shared-memory plan", h->d, k);
     p.stages = S;
     plan.smem = smem_for(S);
-    const long long num_groups = (h->n + p.gsize - 1) / p.gsize;
+    // one warp per group (predicate groups) / per unit (dealt windows) until the machine is full; the
+    // length of a row list is only known on the device, so a list launch always takes the full grid
+    const long long num_groups = mode == PSX_SCAN_GROUPS ? (h->n + p.gsize - 1) / p.gsize : (h->n + p.rps - 1) / p.rps;
     long long grid = (num_groups + W - 1) / W;
     const long long maxgrid = (long long)h->sm_count * h->ctas_per_sm;
-    if (grid > maxgrid) grid = maxgrid;
+    if (grid > maxgrid || listed) grid = maxgrid;
+    // a row-list batch is the 32 list entries one lane-wide load fetches (its latency is paid once per batch)
+    p.static_batch = listed ? std::max(1, 32 / p.rps) : std::max(1, std::min(h->static_batch, 32));
+    p.dyn_tail = h->dyn_tail ? 1 : 0;
     if (grid < 1) grid = 1;
     plan.grid = (int)grid;
     plan.block = W * 32;
     return PSX_OK;
 }
 
-template <typename T, int METRIC, int PPL, bool QREG>
-static int launch_one(int device, const ScanPlan& plan, cudaStream_t st) {
-    static std::atomic<bool> ready[64];
-    if (device >= 0 && device < 64 && !ready[device].load()) {
-        CU(cudaFuncSetAttribute(scan_topk_kernel<T, METRIC, PPL, QREG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                PSX_SMEM_LIMIT));
-        ready[device].store(true);
-    }
-    scan_topk_kernel<T, METRIC, PPL, QREG><<<plan.grid, plan.block, plan.smem, st>>>(plan.p);
-    return PSX_OK;
-}
-template <typename T, int METRIC>
-static int launch_by_shape(int device, int ppl, bool qreg, const ScanPlan& plan, cudaStream_t st) {
-    if (qreg) {
-        switch (ppl) {
-            case 1: return launch_one<T, METRIC, 1, true>(device, plan, st);
-            case 2: return launch_one<T, METRIC, 2, true>(device, plan, st);
-            case 3: return launch_one<T, METRIC, 3, true>(device, plan, st);
-            case 4: return launch_one<T, METRIC, 4, true>(device, plan, st);
-            case 6: return launch_one<T, METRIC, 6, true>(device, plan, st);
-            case 8: return launch_one<T, METRIC, 8, true>(device, plan, st);
-            default: break;
-        }
-    } else if (ppl == 8) {
-        return launch_one<T, METRIC, 8, false>(device, plan, st);
-    }
-    return launch_one<T, METRIC, 0, false>(device, plan, st);
-}
 static int launch_scan_variant(int device, int dtype, int metric, int ppl, bool qreg, const ScanPlan& plan, cudaStream_t st) {
+    const ScanLaunch l{plan.grid, plan.block, plan.smem};
+    cudaError_t e;
     if (dtype == PSX_STORE_F32)
-        return metric == PSX_METRIC_IP ? launch_by_shape<float, PSX_METRIC_IP>(device, ppl, qreg, plan, st)
-                                       : launch_by_shape<float, PSX_METRIC_L2>(device, ppl, qreg, plan, st);
-    return metric == PSX_METRIC_IP ? launch_by_shape<__nv_bfloat16, PSX_METRIC_IP>(device, ppl, qreg, plan, st)
-                                   : launch_by_shape<__nv_bfloat16, PSX_METRIC_L2>(device, ppl, qreg, plan, st);
+        e = metric == PSX_METRIC_IP ? launch_scan_shape<float, PSX_METRIC_IP>(device, ppl, qreg, plan.mode, plan.p, l, st)
+                                    : launch_scan_shape<float, PSX_METRIC_L2>(device, ppl, qreg, plan.mode, plan.p, l, st);
+    else
+        e = metric == PSX_METRIC_IP ? launch_scan_shape<__nv_bfloat16, PSX_METRIC_IP>(device, ppl, qreg, plan.mode, plan.p, l, st)
+                                    : launch_scan_shape<__nv_bfloat16, PSX_METRIC_L2>(device, ppl, qreg, plan.mode, plan.p, l, st);
+    if (e != cudaSuccess) return fail(PSX_ERR_CUDA, "scan_topk_kernel launch: %s", cudaGetErrorString(e));
+    return PSX_OK;
 }
 
 struct XchgArgs {
@@ -599,10 +591,32 @@ static size_t xchg_flag_offset() { return (size_t)2 * PSX_XCHG_MAX_WORLD * PSX_K
 static int launch_scan(psx_index* h, const float* q_dev, int k, const psx_filter* f, uint32_t id_base,
                        const uint64_t* ceil_ptr, float* out_scores, long long* out_ids, uint64_t* out_keys, cudaStream_t st,
                        const XchgArgs* xa = nullptr, bool master = false, const int* cond_flag = nullptr) {
+    const bool filtered = f && f->flags;
+    // the predicate: compacted into a row list first (default), or evaluated group by group inside the scan
+    const bool listed = filtered && h->filter_mode != 1;
+    const int mode = listed || (!filtered && h->deal) ? PSX_SCAN_DEAL : PSX_SCAN_GROUPS;
     ScanPlan plan;
-    int rc = plan_scan(h, master, k, plan);
+    int rc = plan_scan(h, master, k, mode, listed, plan);
     if (rc) return rc;
     ScanParams& p = plan.p;
+    if (listed) {
+        if (h->rowlist_cap < h->cap) {
+            CU(cudaStreamSynchronize(st));
+            cudaFree(h->rowlist);
+            h->rowlist = nullptr;
+            h->rowlist_cap = 0;
+            CU(cudaMalloc(&h->rowlist, (size_t)h->cap * sizeof(uint32_t)));
+            h->rowlist_cap = h->cap;
+        }
+        const long long chunks = (h->n + 1023) / 1024;
+        const unsigned blocks = (unsigned)std::max<long long>(1, std::min<long long>(chunks, (long long)h->sm_count * 8));
+        filter_list_kernel<<<blocks, 256, 0, st>>>(h->attrs, h->n, *f, h->rowlist, h->counter + 2, cond_flag);
+        g_launches++;
+        CU(cudaGetLastError());
+        p.rowlist = h->rowlist;
+    }
+    p.list_count = h->counter + 2;
+    p.work = h->counter + 1;
     const size_t need_lists = (size_t)plan.grid * p.kpad;
     if (need_lists > h->lists_cap) {
         CU(cudaStreamSynchronize(st));
@@ -615,6 +629,7 @@ static int launch_scan(psx_index* h, const float* q_dev, int k, const psx_filter
     }
     p.x = master ? h->xm : h->x;
     p.cond_flag = cond_flag;
+    p.trace = h->trace;
     p.q = q_dev;
     p.ceil_ptr = ceil_ptr;
     p.lists = h->lists;
@@ -625,7 +640,7 @@ static int launch_scan(psx_index* h, const float* q_dev, int k, const psx_filter
     p.id_base = id_base;
     p.has_filter = 0;
     p.attrs = nullptr;
-    if (f && f->flags) {
+    if (filtered && !listed) {
         p.has_filter = 1;
         p.attrs = h->attrs;
         p.f = *f;
@@ -726,6 +741,40 @@ static bool debug_sync() {
         }                                                                                                      \
     } while (0)
 
+// PSX_BATCH_TIMING=1: CUDA events between the phases of a batch, printed to stderr (synchronises the stream)
+struct BatchTimer {
+    static bool enabled() {
+        static const bool on = [] { const char* e = getenv("PSX_BATCH_TIMING"); return e && *e == '1'; }();
+        return on;
+    }
+    cudaStream_t st;
+    cudaEvent_t ev[8];
+    const char* names[8];
+    int n = 0;
+    explicit BatchTimer(cudaStream_t s) : st(s) {
+        if (enabled()) mark("start");
+    }
+    void mark(const char* name) {
+        if (!enabled() || n >= 8) return;
+        cudaEventCreate(&ev[n]);
+        cudaEventRecord(ev[n], st);
+        names[n++] = name;
+    }
+    void report() {
+        if (!enabled()) return;
+        cudaStreamSynchronize(st);
+        fprintf(stderr, "psx batch phases:");
+        for (int i = 1; i < n; ++i) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, ev[i - 1], ev[i]);
+            fprintf(stderr, " %s %.1f us;", names[i], ms * 1e3f);
+        }
+        fprintf(stderr, "\n");
+        for (int i = 0; i < n; ++i) cudaEventDestroy(ev[i]);
+        n = 0;
+    }
+};
+
 template <int MT>
 static int launch_gemm(psx_index* h, const CUtensorMap& mq, const CUtensorMap& mx, const GemmParams& gp, int grid, cudaStream_t st) {
     constexpr int STAGES = BatchCfg<MT>::STAGES;
@@ -751,10 +800,13 @@ static int launch_batch(psx_index* h, const float* q_dev, int nq, int k, const p
     const bool pair = MT == 2 && h->batch_pair;
     const int BATCH_BN = batch_bn(MT, pair);
     const int num_tiles = (int)((h->n + BATCH_BN - 1) / BATCH_BN);
-    // theta from a strided sample: aim at ~8 sample scores above the threshold that ~T rows pass (the
-    // threshold only has to land between the k-th and roughly the 2T-th score; the certificate decides)
-    const int T = 3 * k + 48;
-    int tile_step = T / 8;
+    // theta from a strided sample: aim at ~16 sample scores above the threshold that ~T rows pass.  The
+    // threshold has to land between the k-th score and roughly the (cand_cap)-th; the certificate decides.  The
+    // number of rows above the sample's 16th score is ~ T * Gamma(16)/16: it undercuts k + (rows within eps of
+    // the k-th) with probability ~3e-5 per query at k = 100 (8 sample scores and T = 3k+48 failed 2.7 % of the
+    // queries of a 10M-row corpus, each of which costs a full scan).
+    const int T = 4 * k + 64;
+    int tile_step = T / 16;
     if (tile_step < 1) tile_step = 1;
     while (tile_step > 1 && num_tiles / tile_step < 64) --tile_step;
     const int sample_tiles = (num_tiles + tile_step - 1) / tile_step;
@@ -786,6 +838,7 @@ static int launch_batch(psx_index* h, const float* q_dev, int nq, int k, const p
         gp.attrs = h->attrs;
         gp.f = *f;
     }
+    BatchTimer bt(st);
     // pass 1: sample
     gp.mode = GEMM_MODE_SAMPLE;
     gp.tile_step = tile_step;
@@ -794,6 +847,7 @@ static int launch_batch(psx_index* h, const float* q_dev, int nq, int k, const p
               : MT == 2 ? launch_gemm<2>(h, mq, mx, gp, grid_s, st) : launch_gemm<1>(h, mq, mx, gp, grid_s, st);
     if (rc) return rc;
     DBG_SYNC(st, "gemm_filter_kernel(sample)");
+    bt.mark("sample pass");
     const long long sample_rows = std::min<long long>(h->n, (long long)sample_tiles * BATCH_BN);
     int rank = (int)((double)T * (double)sample_rows / (double)h->n + 0.5);
     if (rank < 2) rank = 2;
@@ -805,6 +859,7 @@ static int launch_batch(psx_index* h, const float* q_dev, int nq, int k, const p
     g_launches++;
     CU(cudaGetLastError());
     DBG_SYNC(st, "theta_kernel");
+    bt.mark("theta");
     // pass 2: every tile, threshold test fused into the epilogue
     gp.mode = GEMM_MODE_FILTER;
     gp.tile_step = 1;
@@ -813,6 +868,7 @@ static int launch_batch(psx_index* h, const float* q_dev, int nq, int k, const p
               : MT == 2 ? launch_gemm<2>(h, mq, mx, gp, grid_f, st) : launch_gemm<1>(h, mq, mx, gp, grid_f, st);
     if (rc) return rc;
     DBG_SYNC(st, "gemm_filter_kernel(filter)");
+    bt.mark("filter pass");
     // exact re-score of the survivors + top-k + proof obligation
     const int kpad = (int)psx_kpad(k);
     const size_t smem = (size_t)BATCH_CAND_CAP * 8 + (size_t)(fld + 4) * 4;
@@ -835,6 +891,8 @@ static int launch_batch(psx_index* h, const float* q_dev, int nq, int k, const p
     g_launches++;
     CU(cudaGetLastError());
     DBG_SYNC(st, "rescore_select_kernel");
+    bt.mark("rescore");
+    bt.report();
     return PSX_OK;
 }
 
@@ -1282,6 +1340,13 @@ extern "C" int psx_batch_stats(psx_index* h, int64_t* queries, int64_t* fallback
     return PSX_OK;
 }
 
+extern "C" int psx_set_trace_device(psx_index* h, uint64_t* trace_dev) {
+    if (!h) return fail(PSX_ERR_INVALID, "null handle");
+    std::lock_guard<std::mutex> lk(h->mu);
+    h->trace = (unsigned long long*)trace_dev;
+    return PSX_OK;
+}
+
 extern "C" int psx_set_tunable(psx_index* h, const char* key, int value) {
     if (!h || !key) return fail(PSX_ERR_INVALID, "bad arguments to psx_set_tunable");
     std::lock_guard<std::mutex> lk(h->mu);
@@ -1292,6 +1357,14 @@ extern "C" int psx_set_tunable(psx_index* h, const char* key, int value) {
         h->stages_auto = value <= 0;
     } else if (!strcmp(key, "ctas_per_sm")) {
         h->ctas_per_sm = value <= 0 ? 1 : std::min(value, 8);
+    } else if (!strcmp(key, "deal")) {  // unfiltered scans: 1 = dealt units (default), 0 = static groups
+        h->deal = value != 0;
+    } else if (!strcmp(key, "dyn_tail")) {  // dealt units: 1 = dynamic tail (default), 0 = all static
+        h->dyn_tail = value != 0;
+    } else if (!strcmp(key, "static_batch")) {
+        h->static_batch = value <= 0 ? 8 : std::min(value, 32);
+    } else if (!strcmp(key, "filter_mode")) {  // 0 auto, 1 predicate inside the scan, 2 row list
+        h->filter_mode = value < 0 || value > 2 ? 0 : value;
     } else if (!strcmp(key, "batch_pair")) {
         h->batch_pair = value > 0;
     } else if (!strcmp(key, "batch_min")) {  // smallest nq sent to the tensor-core path; 0 disables it

@@ -218,36 +218,42 @@ __device__ __forceinline__ void block_merge_lists(const uint64_t* __restrict__ s
 // Exact top-k of `L` descending lists WITHOUT merging them all: gather only the first m keys of
 // every list, sort those, and accept the result once no list's last gathered key still beats the
 // k-th gathered key (every deeper key of a list is smaller than its last gathered one, so it can
-// not enter the top-k).  m starts near 2k/L and doubles on failure; data dealt round-robin to the
-// CTAs passes on the first or second try, so the cost is ~one small sort whatever k is.  Falls
-// back to the full merge tree when the prefixes outgrow `cap_keys`.  Result in buf[0..kp).
+// not enter the top-k).  m starts near 2k/L (at least 4, then widened to fill the power of two the
+// sort pads to anyway) and doubles on failure; data dealt evenly to the CTAs passes on the first try
+// (k = 100 over 148 lists: m = 6, a 1024-key sort, retry probability ~1 %), so the cost is ~one small
+// sort whatever k is.  Falls back to the full merge tree when the prefixes outgrow `cap_keys`.
+// Result in buf[0..kp).
 __device__ __forceinline__ void block_select_from_lists(const uint64_t* __restrict__ src, int L, int k, int kp, uint64_t* buf,
                                                         int cap_keys) {
     const int tid = threadIdx.x, nt = blockDim.x;
     int m = (2 * k + L - 1) / L;
-    if (m < 8) m = 8;
+    if (m < 4) m = 4;
     if (m > kp) m = kp;
     for (;;) {
-        const long long total = (long long)L * m;
+        long long total = (long long)L * m;
         if (total > cap_keys) break;
         int np = kp;
         while (np < total) np <<= 1;
         if (np > cap_keys) break;
+        if (np / L > m) {  // the sort costs the same up to np keys: take deeper prefixes for free
+            m = np / L < kp ? np / L : kp;
+            total = (long long)L * m;
+        }
+        // the last gathered key of every list stays in a register of the thread that fetched it
+        uint64_t tail_key = 0ull;
         for (int idx = tid; idx < np; idx += nt) {
             uint64_t v = 0ull;
             if (idx < total) {
                 const int l = idx / m, j = idx - l * m;
                 v = ld_cg_u64(src + (size_t)l * kp + j);
+                if (j == m - 1 && v > tail_key) tail_key = v;
             }
             buf[idx] = v;
         }
         __syncthreads();
         block_bitonic_sort_desc(buf, np);
         const uint64_t kth = total >= k ? buf[k - 1] : 0ull;
-        int more = 0;
-        if (m < kp) {
-            for (int l = tid; l < L; l += nt) more |= ld_cg_u64(src + (size_t)l * kp + m - 1) > kth;
-        }
+        const int more = m < kp && tail_key > kth;
         if (!__syncthreads_or(more)) return;  // buf[0..kp) holds the answer (np >= kp)
         m = m * 2 > kp ? kp : m * 2;
     }

@@ -1,0 +1,114 @@
+// psx_merge.cuh -- the small non-template kernels around the scan: K1a (EXIF predicate -> row list),
+// K4 (merge of the per-shard key lists: after an all-gather, or fused with the NVLink exchange).
+// Included by psx_api.cu only (the scan kernel template is instantiated in several translation units).
+#pragma once
+#include "psx_scan.cuh"
+
+namespace psx {
+
+// K1a: the EXIF predicate as a stream compaction.  Evaluates the packed attribute word of every row
+// and appends the ids of the passing rows to `list` (order: by block-sized chunks, chunks in ticket
+// order); *count must be 0 at launch (the scan that consumes the list resets it).  HBM-bound: 8 bytes
+// read per row, 4 bytes written per passing row.
+__global__ void __launch_bounds__(256) filter_list_kernel(const uint64_t* __restrict__ attrs, long long n, psx_filter f,
+                                                          uint32_t* __restrict__ list, unsigned int* count, const int* cond_flag) {
+    __shared__ unsigned int s_warp[8];
+    if (cond_flag && *cond_flag == 0) return;  // the conditional scan this list is for will not run either
+    __shared__ unsigned int s_base;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr int PER = 4;  // rows per thread and trip: lane-contiguous pairs, 16-byte loads
+    const long long chunk = (long long)blockDim.x * PER;
+    for (long long c0 = (long long)blockIdx.x * chunk; c0 < n; c0 += (long long)gridDim.x * chunk) {
+        // thread t covers rows c0 + 2t, 2t+1 and c0 + 512 + 2t, 2t+1
+        uint32_t bits = 0;
+#pragma unroll
+        for (int h = 0; h < PER / 2; ++h) {
+            const long long r = c0 + (long long)h * 2 * blockDim.x + 2 * threadIdx.x;
+            uint64_t a0 = 0, a1 = 0;
+            if (r + 1 < n) {
+                const ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2*>(attrs + r));
+                a0 = v.x;
+                a1 = v.y;
+            } else if (r < n) {
+                a0 = __ldg(attrs + r);
+            }
+            if (r < n && attr_pass(a0, f)) bits |= 1u << (2 * h);
+            if (r + 1 < n && attr_pass(a1, f)) bits |= 2u << (2 * h);
+        }
+        const unsigned int mine = __popc(bits);
+        unsigned int incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned int v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned int tot = 0;
+            for (int w = 0; w < 8; ++w) {
+                const unsigned int c = s_warp[w];
+                s_warp[w] = tot;
+                tot += c;
+            }
+            s_base = tot ? atomicAdd(count, tot) : 0u;
+        }
+        __syncthreads();
+        unsigned int pos = s_base + s_warp[warp] + incl - mine;
+#pragma unroll
+        for (int h = 0; h < PER / 2; ++h) {
+            const uint32_t r = (uint32_t)(c0 + (long long)h * 2 * blockDim.x + 2 * threadIdx.x);
+            if (bits & (1u << (2 * h))) list[pos++] = r;
+            if (bits & (2u << (2 * h))) list[pos++] = r + 1;
+        }
+        __syncthreads();  // s_warp / s_base are reused by the next trip
+    }
+}
+
+// K4 fused, receiving side: wait until every rank's list for query `seq` has landed in this GPU's
+// receive buffer, then select the global top-k.  One CTA.  The spin is bounded (a dead peer becomes
+// a trap, not a hung GPU).
+__global__ void __launch_bounds__(256, 1)
+merge_wait_kernel(const uint64_t* __restrict__ recv, const uint32_t* flags, int world, uint32_t seq, int k, int kpad, int cap_keys,
+                  int metric, float* out_scores, long long* out_ids) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    uint64_t* buf = reinterpret_cast<uint64_t*>(smem_raw);
+    const int slot = (int)(seq & 1u);
+    if ((int)threadIdx.x < world) {
+        const uint32_t* f = flags + slot * PSX_XCHG_MAX_WORLD + threadIdx.x;
+        unsigned long long spins = 0;
+        while (ld_acquire_sys_u32(f) != seq) {
+            __nanosleep(64);
+            if (++spins > (1ull << 26)) __trap();
+        }
+    }
+    __syncthreads();
+    const uint64_t* lists = recv + (size_t)slot * world * PSX_K_PASS_MAX;
+    // lists are PSX_K_PASS_MAX apart; compact them to a kpad stride view by reading through an index map
+    // (block_select_from_lists expects stride kpad): gather the heads into shared memory first
+    const int tid = threadIdx.x, nt = blockDim.x;
+    int np = kpad;
+    while (np < world * kpad) np <<= 1;
+    for (int idx = tid; idx < np; idx += nt) {
+        uint64_t v = 0ull;
+        if (idx < world * kpad) v = ld_cg_u64(lists + (size_t)(idx / kpad) * PSX_K_PASS_MAX + (idx % kpad));
+        buf[idx] = v;
+    }
+    __syncthreads();
+    (void)cap_keys;
+    block_bitonic_sort_desc(buf, np);
+    block_emit_results(buf, k, kpad, metric, out_scores, out_ids, nullptr);
+}
+
+// Standalone merge (K4 final merge of all-gathered shard lists): one CTA per query.
+__global__ void __launch_bounds__(256, 1)
+merge_keys_kernel(const uint64_t* __restrict__ keys, int nlists, int k, int kpad, int cap_lists, int metric,
+                  float* out_scores, long long* out_ids) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    uint64_t* buf = reinterpret_cast<uint64_t*>(smem_raw);
+    const size_t qi = blockIdx.x;
+    block_select_from_lists(keys + qi * (size_t)nlists * kpad, nlists, k, kpad, buf, cap_lists * kpad);
+    block_emit_results(buf, k, kpad, metric, out_scores + qi * k, out_ids + qi * k, nullptr);
+}
+
+}  // namespace psx

@@ -55,6 +55,13 @@ struct ScanParams {
     // fused cross-GPU exchange (row shards): the last CTA stores this shard's k keys straight into
     // every peer's receive buffer over NVLink and raises a per-source flag there.  world 0 = off.
     const int* cond_flag;  // nullptr, or: run only if *cond_flag != 0 (conditional fallback scan)
+    unsigned long long* trace;  // nullptr, or [grid][8] phase timestamps in ns (psx_set_trace_device)
+    // PSX_SCAN_DEAL
+    const uint32_t* rowlist;    // nullptr = the rows of the arena in order; else the ids of the rows to scan
+    unsigned int* list_count;   // number of entries of rowlist (device value, reset by the last CTA)
+    unsigned int* work;         // ticket counter of the dynamically dealt tail (0 at launch, reset by the last CTA)
+    int static_batch;           // units per statically dealt batch (and cap of a dynamic one)
+    int dyn_tail;               // 0 = deal everything statically
     int xchg_world, xchg_rank;
     uint32_t xchg_seq;
     uint64_t* xchg_recv[PSX_XCHG_MAX_WORLD];   // peer p: [2 parities][world][PSX_K_PASS_MAX] keys
@@ -71,6 +78,16 @@ __device__ __forceinline__ uint32_t ld_acquire_sys_u32(const uint32_t* p) {
     uint32_t v;
     asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
+}
+
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+// diagnostics: phase `i` of this CTA reached (entry, prologue done, stream done, list published, merged, emitted)
+__device__ __forceinline__ void trace_stamp(unsigned long long* trace, int i) {
+    if (trace && threadIdx.x == 0) trace[(size_t)blockIdx.x * 8 + i] = globaltimer_ns();
 }
 
 __device__ __forceinline__ bool attr_pass(uint64_t a, const psx_filter& f) {
@@ -215,10 +232,24 @@ struct RowDot {
     }
 };
 
-template <typename T, int METRIC, int PPL, bool QREG>
+// How the rows of a launch reach the warps.
+//   PSX_SCAN_DEAL   : the launch is a range of `units` (one unit = one window = the rows of one ring
+//                     slot, or one long row).  Most units are dealt round-robin in small static batches;
+//                     the tail of the range is dealt dynamically from a global ticket counter in batches
+//                     that shrink towards the end (guided self-scheduling), so that every warp drains at
+//                     the same moment whatever the per-SM bandwidth was.  A unit is either `rps`
+//                     consecutive rows of the arena, or `rps` consecutive entries of a row-id list (the
+//                     rows that pass the EXIF predicate, written by filter_list_kernel).
+//   PSX_SCAN_GROUPS : the predicate is evaluated inside the scan, one ballot per group of <= 32 rows
+//                     dealt round-robin (attribute words prefetched two groups ahead).
+#define PSX_SCAN_DEAL 0
+#define PSX_SCAN_GROUPS 1
+
+template <typename T, int METRIC, int PPL, bool QREG, int MODE>
 __global__ void __launch_bounds__(PSX_MAX_THREADS, 1) scan_topk_kernel(const ScanParams p) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     if (p.cond_flag && *p.cond_flag == 0) return;  // uniform: the whole grid skips
+    trace_stamp(p.trace, 0);
     const int W = blockDim.x >> 5;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int S = p.stages;
@@ -235,6 +266,7 @@ __global__ void __launch_bounds__(PSX_MAX_THREADS, 1) scan_topk_kernel(const Sca
     int* s_count = reinterpret_cast<int*>(row0s + W * S);
     int* s_flag = s_count + 1;
     int* s_over = s_count + 2;
+    uint32_t* rowids = reinterpret_cast<uint32_t*>(s_count + 4);  // [W*S][32], list launches only
 
     // ---- prologue ------------------------------------------------------------------------
     for (int i = threadIdx.x; i < qpad; i += blockDim.x) sq[i] = i < p.d ? p.q[i] : 0.0f;
@@ -249,67 +281,149 @@ __global__ void __launch_bounds__(PSX_MAX_THREADS, 1) scan_topk_kernel(const Sca
     }
     mbar_fence_init();
     __syncthreads();
+    trace_stamp(p.trace, 1);
 
     const uint64_t ceil_key = p.ceil_ptr ? *p.ceil_ptr : ~0ull;
-    const int R = p.rps, G = p.gsize, cpr = p.cpr, row_bytes = p.row_bytes;
-    const uint32_t rmask = R >= 32 ? 0xffffffffu : ((1u << R) - 1u);
-    const long long num_groups = (p.n + G - 1) / G;
-    const long long Wt = (long long)gridDim.x * W;
-    const long long gw = (long long)blockIdx.x * W + warp;
+    const int R = p.rps, cpr = p.cpr, row_bytes = p.row_bytes;
+    const uint32_t Wt = gridDim.x * (uint32_t)W;
+    const uint32_t gw = blockIdx.x * (uint32_t)W + warp;
 
     const uint32_t ring_base = smem_u32(ring) + (uint32_t)(warp * S) * PSX_SLOT_BYTES;
     const uint32_t bar_base = smem_u32(bars + warp * S);
     uint32_t* my_masks = masks + warp * S;
     uint32_t* my_row0s = row0s + warp * S;
+    uint32_t* my_rowids = rowids + (size_t)warp * S * 32;
     const float4* q4 = reinterpret_cast<const float4*>(sq);
     RowDot<T, METRIC, PPL, QREG> dot;
     dot.load_query(q4, lane);
 
-    // ---- producer: walks this warp's row groups, skips windows the predicate empties -----------
+    const bool listed = MODE == PSX_SCAN_DEAL && p.rowlist != nullptr;
+    bool p_exhausted = false;
+    int p_chunk = 0;         // long rows: next chunk of the current row
+    int in_flight = 0;
+    uint32_t cur_mask = 0;   // window being streamed (bit r = r-th row of the window)
+    uint32_t cur_row0 = 0;   // its first row (arena launches) / its row (long rows of a list launch)
+
+    // ---- PSX_SCAN_DEAL producer state --------------------------------------------------------
+    uint32_t n_rows = 0, n_units = 0, n_static = 0, bs = 1;  // rows, units, statically dealt units, static batch
+    uint32_t s_next = 0;              // next static batch of this warp
+    uint32_t u_cur = 0, u_end = 0;    // open batch of units
+    uint32_t u_first = 0;             // list launches: unit whose entries sit in lane 0.. of rid_batch
+    uint32_t rid_batch = 0;           // list launches: lane l holds list[u_first * R + l]
+    uint32_t grab_base = 0, grab_cnt = 0;  // dynamic batch requested ahead of time (base valid in lane 0)
+    bool grab_pending = false;
+    // ---- PSX_SCAN_GROUPS producer state ------------------------------------------------------
+    const int G = p.gsize;
+    const uint32_t rmask = R >= 32 ? 0xffffffffu : ((1u << R) - 1u);
+    const long long num_groups = (p.n + G - 1) / G;
     long long g_next = gw;   // next group to open
     long long g_row0 = 0;    // first row of the open group
     uint32_t g_mask = 0;     // rows of the open group still to be streamed (bit i = row g_row0 + i)
-    uint32_t cur_mask = 0;   // window being streamed (bit r = row cur_row0 + r)
-    long long cur_row0 = 0;
-    int p_chunk = 0;         // long rows: next chunk of the current row
-    bool p_exhausted = false;
-    int in_flight = 0;
     uint64_t attr_a = 0, attr_b = 0;  // attribute words of the next two groups (prefetched)
+
+    if constexpr (MODE == PSX_SCAN_DEAL) {
+        n_rows = listed ? *p.list_count : (uint32_t)p.n;
+        n_units = (n_rows + (uint32_t)R - 1u) / (uint32_t)R;
+        // the dynamically dealt tail: an eighth of the launch, at least 16 and at most 48 units per warp;
+        // launches too small for that are dealt statically (their warps finish within one unit of each other)
+        uint32_t dyn = 0;
+        if (p.dyn_tail && n_units >= 64u * Wt) {
+            dyn = n_units >> 3;
+            if (dyn < 16u * Wt) dyn = 16u * Wt;
+            if (dyn > 48u * Wt) dyn = 48u * Wt;
+        }
+        n_static = n_units - dyn;
+        bs = (uint32_t)p.static_batch;
+        while (bs > 1 && n_static / (Wt * bs) < 8) bs >>= 1;
+        s_next = gw;
+    }
+    auto request_grab = [&](uint32_t remaining) {  // ask for the next dynamic batch; the reply is read later
+        uint32_t c = remaining / Wt;
+        c = c < 1u ? 1u : (c > (uint32_t)p.static_batch ? (uint32_t)p.static_batch : c);
+        grab_cnt = c;
+        if (lane == 0) grab_base = atomicAdd(p.work, c);
+        grab_pending = true;
+    };
+    auto open_batch = [&]() -> bool {
+        if ((uint64_t)s_next * bs < n_static) {
+            u_cur = s_next * bs;
+            u_end = u_cur + bs < n_static ? u_cur + bs : n_static;
+            s_next += Wt;
+            if (n_static < n_units && (uint64_t)s_next * bs >= n_static) request_grab(n_units - n_static);
+        } else {
+            if (n_static == n_units) return false;
+            if (!grab_pending) request_grab(n_units - n_static);  // this warp had no static batch at all
+            const uint32_t base = n_static + __shfl_sync(0xffffffffu, grab_base, 0);
+            grab_pending = false;
+            if (base >= n_units || base < n_static) return false;
+            u_cur = base;
+            u_end = n_units - base < grab_cnt ? n_units : base + grab_cnt;
+            request_grab(n_units - u_end);
+        }
+        if (listed) {  // the row ids of the whole batch: (u_end - u_cur) * R <= 32 entries
+            u_first = u_cur;
+            const uint32_t idx = u_cur * (uint32_t)R + lane;
+            rid_batch = (lane < (u_end - u_cur) * (uint32_t)R && idx < n_rows) ? __ldg(p.rowlist + idx) : 0u;
+        }
+        return true;
+    };
+
     auto load_attr = [&](long long g) -> uint64_t {
         const long long row = g * G + lane;
         return (p.has_filter && g < num_groups && lane < G && row < p.n) ? __ldg(p.attrs + row) : 0ull;
     };
-    attr_a = load_attr(g_next);
-    attr_b = load_attr(g_next + Wt);
+    if constexpr (MODE == PSX_SCAN_GROUPS) {
+        attr_a = load_attr(g_next);
+        attr_b = load_attr(g_next + Wt);
+    }
     auto open_group = [&]() -> bool {
-        if (g_next >= num_groups) {
-            p_exhausted = true;
-            return false;
-        }
+        if (g_next >= num_groups) return false;
         g_row0 = g_next * G;
         const long long left = p.n - g_row0;
         const int rows = left < G ? (int)left : G;
         if (p.has_filter) {
             g_mask = __ballot_sync(0xffffffffu, lane < rows && attr_pass(attr_a, p.f));
             attr_a = attr_b;
-            attr_b = load_attr(g_next + 2 * Wt);
+            attr_b = load_attr(g_next + 2 * (long long)Wt);
         } else {
             g_mask = rows >= 32 ? 0xffffffffu : ((1u << rows) - 1u);
         }
         g_next += Wt;
         return true;
     };
+
     // Fill `slot` with the next window (or the next chunk of a long row).  false = stream exhausted.
     auto produce = [&](int slot) -> bool {
+        uint32_t rid = 0;  // list launches: the row this lane copies
         if (p_chunk == 0) {
-            while (g_mask == 0) {
-                if (!open_group()) return false;
+            if constexpr (MODE == PSX_SCAN_DEAL) {
+                if (u_cur == u_end && !open_batch()) {
+                    p_exhausted = true;
+                    return false;
+                }
+                const uint32_t u = u_cur++;
+                const uint32_t first = u * (uint32_t)R;  // first row / first list entry of the unit
+                const uint32_t cnt = n_rows - first < (uint32_t)R ? n_rows - first : (uint32_t)R;
+                cur_mask = cnt >= 32 ? 0xffffffffu : ((1u << cnt) - 1u);
+                if (listed) {
+                    rid = __shfl_sync(0xffffffffu, rid_batch, ((u - u_first) * (uint32_t)R + lane) & 31);
+                    cur_row0 = __shfl_sync(0xffffffffu, rid, 0);
+                } else {
+                    cur_row0 = first;
+                }
+            } else {
+                while (g_mask == 0) {
+                    if (!open_group()) {
+                        p_exhausted = true;
+                        return false;
+                    }
+                }
+                const int b = __ffs(g_mask) - 1;
+                const int w = R == 1 ? b : b / R;
+                cur_mask = (g_mask >> (w * R)) & rmask;
+                g_mask &= ~(rmask << (w * R));
+                cur_row0 = (uint32_t)(g_row0 + (long long)w * R);
             }
-            const int b = __ffs(g_mask) - 1;
-            const int w = R == 1 ? b : b / R;
-            cur_mask = (g_mask >> (w * R)) & rmask;
-            g_mask &= ~(rmask << (w * R));
-            cur_row0 = g_row0 + (long long)w * R;
         }
         const uint32_t mask = cur_mask;
         const uint32_t bar = bar_base + slot * 8;
@@ -317,7 +431,7 @@ __global__ void __launch_bounds__(PSX_MAX_THREADS, 1) scan_topk_kernel(const Sca
         const unsigned char* src = p.x + (size_t)cur_row0 * row_bytes;
         if (lane == 0) {
             my_masks[slot] = mask;
-            my_row0s[slot] = (uint32_t)cur_row0;
+            my_row0s[slot] = cur_row0;
         }
         if (cpr > 1) {
             const int off = p_chunk * PSX_SLOT_BYTES;
@@ -327,6 +441,11 @@ __global__ void __launch_bounds__(PSX_MAX_THREADS, 1) scan_topk_kernel(const Sca
                 bulk_g2s(dst, src + off, bytes, bar);
             }
             if (++p_chunk == cpr) p_chunk = 0;
+        } else if (listed) {  // one bulk copy per listed row
+            if (lane == 0) mbar_arrive_expect_tx(bar, __popc(mask) * row_bytes);
+            if ((mask >> lane) & 1u) my_rowids[slot * 32 + lane] = rid;
+            __syncwarp();
+            if ((mask >> lane) & 1u) bulk_g2s(dst + lane * row_bytes, p.x + (size_t)rid * row_bytes, row_bytes, bar);
         } else {
             const int hi = 32 - __clz(mask);  // rows [0, hi) of the window, all passing <=> one copy
             if (mask == (hi >= 32 ? 0xffffffffu : ((1u << hi) - 1u))) {
@@ -366,12 +485,14 @@ __global__ void __launch_bounds__(PSX_MAX_THREADS, 1) scan_topk_kernel(const Sca
     int over = 0;
     float a[4] = {0.f, 0.f, 0.f, 0.f};  // long rows: carried across the chunks of a row
     int c_chunk = 0;
+    int n_compact = 0;
     for (;;) {
         for (int m = 0; m < p.sync_every && in_flight > 0; ++m) {
             const int slot = c_slot;
             mbar_wait(bar_base + slot * 8, c_phase);
             const uint32_t mask = my_masks[slot];
-            const uint32_t row0 = my_row0s[slot];
+            // global row of this lane's score: consecutive rows of the arena, or the listed row
+            const uint32_t myrow = (listed && cpr == 1) ? my_rowids[slot * 32 + lane] : my_row0s[slot] + (uint32_t)lane;
             const uint4* xs = reinterpret_cast<const uint4*>(ring + ((size_t)(warp * S + slot)) * PSX_SLOT_BYTES);
             float myscore = 0.0f;
             bool row_done = true;
@@ -416,7 +537,7 @@ __global__ void __launch_bounds__(PSX_MAX_THREADS, 1) scan_topk_kernel(const Sca
             uint64_t key = 0;
             if ((mask >> lane) & 1u) {
                 const float s = METRIC == PSX_METRIC_L2 ? -myscore : myscore;
-                key = make_key(s, p.id_base + row0 + (uint32_t)lane);
+                key = make_key(s, p.id_base + myrow);
                 want = key > tau && key < ceil_key;
             }
             const uint32_t bal = __ballot_sync(0xffffffffu, want);
@@ -433,11 +554,16 @@ __global__ void __launch_bounds__(PSX_MAX_THREADS, 1) scan_topk_kernel(const Sca
         if (over) *s_over = 1;
         over = 0;
         const int alive = __syncthreads_count(in_flight > 0);
-        if (*s_over) compact_candidates(cand, s_count, s_tau, s_over, p.k);
+        if (*s_over) {
+            compact_candidates(cand, s_count, s_tau, s_over, p.k);
+            ++n_compact;
+        }
         tau = *s_tau;
         if (!alive) break;
     }
 
+    trace_stamp(p.trace, 2);
+    if (p.trace && threadIdx.x == 0) p.trace[(size_t)blockIdx.x * 8 + 6] = (unsigned long long)n_compact;
     // ---- publish this CTA's k best -------------------------------------------------------------
     compact_candidates(cand, s_count, s_tau, s_over, p.k);
     {
@@ -447,6 +573,7 @@ __global__ void __launch_bounds__(PSX_MAX_THREADS, 1) scan_topk_kernel(const Sca
     }
     __threadfence();
     __syncthreads();
+    trace_stamp(p.trace, 3);
     if (threadIdx.x == 0) {
         const unsigned int ticket = atomicAdd(p.counter, 1u);
         *s_flag = ticket == gridDim.x - 1;
@@ -458,8 +585,17 @@ __global__ void __launch_bounds__(PSX_MAX_THREADS, 1) scan_topk_kernel(const Sca
     __threadfence();
     uint64_t* buf = reinterpret_cast<uint64_t*>(ring);
     block_select_from_lists(p.lists, gridDim.x, p.k, p.kpad, buf, (int)((size_t)W * S * PSX_SLOT_BYTES / 8));
+    trace_stamp(p.trace, 4);
     block_emit_results(buf, p.k, p.kpad, p.metric, p.out_scores, p.out_ids, p.out_keys);
-    if (threadIdx.x == 0) *p.counter = 0u;
+    if (threadIdx.x == 0) {
+        // every warp of the grid has read the reply to its last ticket request before its CTA took a
+        // merge ticket, so both counters are idle now: leave them ready for the next launch
+        *p.counter = 0u;
+        if (MODE == PSX_SCAN_DEAL) {
+            *p.work = 0u;
+            if (listed) *p.list_count = 0u;
+        }
+    }
     if (p.xchg_world > 0) {
         // K4 fused: publish this shard's list to every rank (NVLink P2P stores), then the flags
         const int slot = (int)(p.xchg_seq & 1u);
@@ -472,52 +608,8 @@ __global__ void __launch_bounds__(PSX_MAX_THREADS, 1) scan_topk_kernel(const Sca
         if ((int)threadIdx.x < p.xchg_world)
             st_release_sys_u32(p.xchg_flag[threadIdx.x] + slot * PSX_XCHG_MAX_WORLD + p.xchg_rank, p.xchg_seq);
     }
-}
-
-// K4 fused, receiving side: wait until every rank's list for query `seq` has landed in this GPU's
-// receive buffer, then select the global top-k.  One CTA.  The spin is bounded (a dead peer becomes
-// a trap, not a hung GPU).
-__global__ void __launch_bounds__(256, 1)
-merge_wait_kernel(const uint64_t* __restrict__ recv, const uint32_t* flags, int world, uint32_t seq, int k, int kpad, int cap_keys,
-                  int metric, float* out_scores, long long* out_ids) {
-    extern __shared__ __align__(1024) unsigned char smem_raw[];
-    uint64_t* buf = reinterpret_cast<uint64_t*>(smem_raw);
-    const int slot = (int)(seq & 1u);
-    if ((int)threadIdx.x < world) {
-        const uint32_t* f = flags + slot * PSX_XCHG_MAX_WORLD + threadIdx.x;
-        unsigned long long spins = 0;
-        while (ld_acquire_sys_u32(f) != seq) {
-            __nanosleep(64);
-            if (++spins > (1ull << 26)) __trap();
-        }
-    }
     __syncthreads();
-    const uint64_t* lists = recv + (size_t)slot * world * PSX_K_PASS_MAX;
-    // lists are PSX_K_PASS_MAX apart; compact them to a kpad stride view by reading through an index map
-    // (block_select_from_lists expects stride kpad): gather the heads into shared memory first
-    const int tid = threadIdx.x, nt = blockDim.x;
-    int np = kpad;
-    while (np < world * kpad) np <<= 1;
-    for (int idx = tid; idx < np; idx += nt) {
-        uint64_t v = 0ull;
-        if (idx < world * kpad) v = ld_cg_u64(lists + (size_t)(idx / kpad) * PSX_K_PASS_MAX + (idx % kpad));
-        buf[idx] = v;
-    }
-    __syncthreads();
-    (void)cap_keys;
-    block_bitonic_sort_desc(buf, np);
-    block_emit_results(buf, k, kpad, metric, out_scores, out_ids, nullptr);
-}
-
-// Standalone merge (K4 final merge of all-gathered shard lists): one CTA per query.
-__global__ void __launch_bounds__(256, 1)
-merge_keys_kernel(const uint64_t* __restrict__ keys, int nlists, int k, int kpad, int cap_lists, int metric,
-                  float* out_scores, long long* out_ids) {
-    extern __shared__ __align__(1024) unsigned char smem_raw[];
-    uint64_t* buf = reinterpret_cast<uint64_t*>(smem_raw);
-    const size_t qi = blockIdx.x;
-    block_select_from_lists(keys + qi * (size_t)nlists * kpad, nlists, k, kpad, buf, cap_lists * kpad);
-    block_emit_results(buf, k, kpad, metric, out_scores + qi * k, out_ids + qi * k, nullptr);
+    trace_stamp(p.trace, 5);
 }
 
 }  // namespace psx

@@ -330,10 +330,12 @@ def _random_meta(rng, n):
     return meta
 
 
+@pytest.mark.parametrize("filter_mode", [1, 2])
 @pytest.mark.parametrize("n,d", [(6000, 1024), (5000, 8), (3000, 4096), (4000, 200)])
-def test_fused_predicate(n, d):
+def test_fused_predicate(n, d, filter_mode):
     """Scan restricted by the packed EXIF word == oracle restricted to rows passing the restated
-    ``_check_time_match_v2`` (core/searcher.py:1884-1950)."""
+    ``_check_time_match_v2`` (core/searcher.py:1884-1950).  filter_mode 1 evaluates the predicate inside
+    the scan, 2 (the default) compacts the passing rows into a list that the scan then streams."""
     from photo_search_engine_b200.exif_attrs import attr_words, build_filter
 
     rng = np.random.default_rng(n + d)
@@ -341,6 +343,7 @@ def test_fused_predicate(n, d):
     q = unit_rows(rng, 2, d)
     meta = _random_meta(rng, n)
     ix, oracle = make_index(x), make_oracle(x)
+    ix.set_tunable("filter_mode", filter_mode)
     ix.set_attrs(0, attr_words(meta))
     cases = [
         {"season": "夏天"},
@@ -395,11 +398,47 @@ def test_determinism_and_tunables():
     q = unit_rows(rng, 1, 1024)
     ix = make_index(x)
     D0, I0 = ix.search(q, 100)
-    for key, val in (("warps", 4), ("stages", 2), ("warps", 16), ("stages", 3), ("ctas_per_sm", 2), ("warps", 8)):
+    for key, val in (("warps", 4), ("stages", 2), ("warps", 16), ("stages", 3), ("ctas_per_sm", 2), ("warps", 8),
+                     ("deal", 0), ("warps", 16), ("deal", 1), ("static_batch", 3), ("dyn_tail", 0), ("static_batch", 32)):
         ix.set_tunable(key, val)
         D, I = ix.search(q, 100)
         # same reduction tree per row -> bit-identical scores whatever the launch geometry
         assert np.array_equal(I, I0) and np.array_equal(D, D0), (key, val)
+    ix.close()
+
+
+@pytest.mark.parametrize("d", [1024, 96, 2048])
+def test_dynamic_tail_and_row_list_geometry(d):
+    """Launches large enough for the dynamically dealt tail (>= 64 units per warp; 4 warps per CTA keep the
+    corpus small): every row is scanned exactly once whichever warp takes it -- results equal the
+    statically dealt scan bit for bit, with and without a predicate (row-list launches), for rows that
+    share a slot (d=96), fill one (d=1024) and span two (d=2048)."""
+    from photo_search_engine_b200._native import F_END, F_NEED_DT, F_START, PsxFilter
+
+    rng = np.random.default_rng(d)
+    n = {1024: 46_000, 96: 480_000, 2048: 46_000}[d]
+    x = unit_rows(rng, n, d)
+    q = unit_rows(rng, 2, d)
+    ix, oracle = make_index(x), make_oracle(x)
+    ix.set_tunable("warps", 4)
+    words = (rng.integers(1, 1000, n)).astype(np.uint64)
+    ix.set_attrs(0, words)
+    flt = PsxFilter(flags=F_NEED_DT | F_START | F_END, start=100, end=950)  # ~85 % of the rows pass
+    mask = (words >= 100) & (words <= 950)
+    ref = {}
+    for dyn in (0, 1):
+        ix.set_tunable("dyn_tail", dyn)
+        for name, f in (("plain", None), ("filtered", flt)):
+            for k in (10, 300):
+                D, I = ix.search(q, k, f)
+                if dyn == 0:
+                    check_against_oracle(D, I, oracle, q, k, mask=mask if f is not None else None)
+                    ref[name, k] = (D, I)
+                else:
+                    assert np.array_equal(I, ref[name, k][1]) and np.array_equal(D, ref[name, k][0]), (name, k)
+    ix.set_tunable("filter_mode", 1)
+    D, I = ix.search(q, 300, flt)
+    assert np.array_equal(I, ref["filtered", 300][1]) and np.array_equal(D, ref["filtered", 300][0])
     ix.close()
 
 
