@@ -808,10 +808,9 @@ static int launch_batch(psx_index* h, const float* q_dev, int nq, int k, const p
     const int T = 4 * k + 64;
     int tile_step = T / 16;
     if (tile_step < 1) tile_step = 1;
-    while (tile_step > 1 && num_tiles / tile_step < 64) --tile_step;
     const int sample_tiles = (num_tiles + tile_step - 1) / tile_step;
     const int grid_s = pair ? std::min(h->sm_count / 2, sample_tiles) : std::min(h->sm_count, sample_tiles);
-    const int sample_ld = sample_tiles * BATCH_BN;  // sample tile ordinals are 0 .. sample_tiles-1
+    const int sample_ld = grid_s * SAMPLE_KEEP;  // every sample CTA (pair) leaves its 8 best scores per query
     int rc = ensure_batch_scratch(h, (size_t)MT * GEMM_M * sample_ld);
     if (rc) return rc;
     // queries -> zero-padded [MT*128][ld] block (rows beyond nq and columns beyond d are zero)
@@ -851,11 +850,7 @@ static int launch_batch(psx_index* h, const float* q_dev, int nq, int k, const p
     const long long sample_rows = std::min<long long>(h->n, (long long)sample_tiles * BATCH_BN);
     int rank = (int)((double)T * (double)sample_rows / (double)h->n + 0.5);
     if (rank < 2) rank = 2;
-    // the rank statistic is taken from per-thread top-2 lists, good for ranks up to a few dozen: thin the
-    // sample (every `thin`-th score) when the requested rank is larger
-    const int thin = rank > 48 ? rank / 32 : 1;
-    rank /= thin;
-    theta_kernel<<<nq, 256, 0, st>>>(h->bsample, sample_ld, sample_ld, thin, rank, 0.0f, h->btheta, h->bcount);
+    theta_kernel<<<nq, 256, 0, st>>>(h->bsample, sample_ld, sample_ld, rank, h->btheta, h->bcount);
     g_launches++;
     CU(cudaGetLastError());
     DBG_SYNC(st, "theta_kernel");

@@ -18,7 +18,8 @@
 //   (2) a proof obligation per query: the k-th exact score must be >= theta_q + eps, eps = the
 //       TF32 error bound.  Then no row outside the list can belong to the top-k.  Queries that
 //       fail it (or overflow their list) are flagged and re-run by the streaming scan.
-// theta_q comes from a strided sample pass of the same GEMM kernel (MODE_SAMPLE).
+// theta_q comes from a strided sample pass of the same GEMM kernel (MODE_SAMPLE): every (CTA, query)
+// keeps its 8 best sample scores in registers, theta_kernel takes the ~16th best of the whole sample.
 #pragma once
 #include <cuda.h>
 
@@ -43,7 +44,7 @@ struct GemmParams {
     uint32_t* cand_ids;      // [nq][cand_cap]
     int* cand_count;         // [nq]
     int cand_cap;
-    float* sample_scores;    // [nq][sample_ld] (MODE_SAMPLE)
+    float* sample_scores;    // [nq][sample_ld] (MODE_SAMPLE): SAMPLE_KEEP scores per sample CTA (pair)
     int sample_ld;
     const uint64_t* attrs;   // EXIF words [n], or nullptr: rows failing `f` are neither sampled nor kept
     psx_filter f;
@@ -120,6 +121,34 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32])
         : "memory");
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+
+// Sample pass: the 8 largest scores one (CTA, query) has seen, kept sorted in registers.  Only these
+// reach memory -- the thresholds need the ~16th largest score of the whole sample, and no CTA holds more
+// than 8 of the top 16 (probability < 3e-4 even with 9 CTAs; the error only lowers theta, i.e. admits more
+// candidates).
+constexpr int SAMPLE_KEEP = 8;
+struct SampleTop {
+    float t[SAMPLE_KEEP];
+    __device__ __forceinline__ void init() {
+#pragma unroll
+        for (int i = 0; i < SAMPLE_KEEP; ++i) t[i] = -INFINITY;
+    }
+    __device__ __forceinline__ void offer(float v) {
+        if (v > t[SAMPLE_KEEP - 1]) {
+            t[SAMPLE_KEEP - 1] = v;
+#pragma unroll
+            for (int i = SAMPLE_KEEP - 1; i > 0; --i) {
+                const float hi = fmaxf(t[i - 1], t[i]), lo = fminf(t[i - 1], t[i]);
+                t[i - 1] = hi;
+                t[i] = lo;
+            }
+        }
+    }
+    __device__ __forceinline__ void store(float* dst) const {
+#pragma unroll
+        for (int i = 0; i < SAMPLE_KEEP; ++i) dst[i] = t[i];
+    }
+};
 
 // ---- the GEMM + fused selection kernel ---------------------------------------------------------------
 // MT accumulator tiles of 128 queries each, BN corpus rows per tile.  TMEM columns: MT*BN per
@@ -233,10 +262,12 @@ gemm_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
         const int ew = warp - 4;            // TMEM lanes [32*ew, 32*ew + 32)
         const int qlane = ew * 32 + lane;   // query row inside an accumulator tile
         float theta[MT];
+        SampleTop top[MT];
 #pragma unroll
         for (int m = 0; m < MT; ++m) {
             const int qi = m * GEMM_M + qlane;
             theta[m] = (p.mode == GEMM_MODE_FILTER && qi < p.nq) ? p.theta[qi] : INFINITY;
+            top[m].init();
         }
         int a = 0, tile_no = 0;
         uint32_t aph = 0;
@@ -267,12 +298,18 @@ gemm_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
                             }
                         }
                     } else if (qi < p.nq) {
-                        // sample pass: keep the scores of the visited tiles (a few % of the matrix)
-                        float* dst = p.sample_scores + (size_t)qi * p.sample_ld + ((size_t)(blockIdx.x + (size_t)tile_no * gridDim.x)) * BN + c * 32;
+                        // sample pass: only this query's running top-8 of the visited tiles is kept
+                        float mx = __uint_as_float(r[0]);
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            const long long row = row0 + c * 32 + j;
-                            dst[j] = (row < p.n && (!p.attrs || gemm_attr_pass(__ldg(p.attrs + row), p.f))) ? __uint_as_float(r[j]) : -INFINITY;
+                        for (int j = 1; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(r[j]));
+                        if (mx > top[m].t[SAMPLE_KEEP - 1]) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) {
+                                const long long row = row0 + c * 32 + j;
+                                if (__uint_as_float(r[j]) > top[m].t[SAMPLE_KEEP - 1] && row < p.n &&
+                                    (!p.attrs || gemm_attr_pass(__ldg(p.attrs + row), p.f)))
+                                    top[m].offer(__uint_as_float(r[j]));
+                            }
                         }
                     }
                 }
@@ -283,6 +320,13 @@ gemm_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
             if (++a == ACC_STAGES) {
                 a = 0;
                 aph ^= 1u;
+            }
+        }
+        if (p.mode == GEMM_MODE_SAMPLE) {
+#pragma unroll
+            for (int m = 0; m < MT; ++m) {
+                const int qi = m * GEMM_M + qlane;
+                if (qi < p.nq) top[m].store(p.sample_scores + (size_t)qi * p.sample_ld + (size_t)blockIdx.x * SAMPLE_KEEP);
             }
         }
     }
@@ -482,6 +526,8 @@ gemm_filter_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
         const int ew = warp - 4;
         const int qi = (int)cta * GEMM_M + ew * 32 + lane;
         const float theta = (p.mode == GEMM_MODE_FILTER && qi < p.nq) ? p.theta[qi] : INFINITY;
+        SampleTop top;
+        top.init();
         const uint32_t leader_acc_empty = mapa_shared(smem_u32(acc_empty), 0);
         int a = 0, tile_no = 0;
         uint32_t aph = 0;
@@ -509,11 +555,17 @@ gemm_filter_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
                         }
                     }
                 } else if (qi < p.nq) {
-                    float* dst = p.sample_scores + (size_t)qi * p.sample_ld + ((size_t)(pair + (size_t)tile_no * npairs)) * BN + c * 32;
+                    float mx = __uint_as_float(r[0]);
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const long long row = row0 + c * 32 + j;
-                        dst[j] = (row < p.n && (!p.attrs || gemm_attr_pass(__ldg(p.attrs + row), p.f))) ? __uint_as_float(r[j]) : -INFINITY;
+                    for (int j = 1; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(r[j]));
+                    if (mx > top.t[SAMPLE_KEEP - 1]) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const long long row = row0 + c * 32 + j;
+                            if (__uint_as_float(r[j]) > top.t[SAMPLE_KEEP - 1] && row < p.n &&
+                                (!p.attrs || gemm_attr_pass(__ldg(p.attrs + row), p.f)))
+                                top.offer(__uint_as_float(r[j]));
+                        }
                     }
                 }
             }
@@ -525,6 +577,7 @@ gemm_filter_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
                 aph ^= 1u;
             }
         }
+        if (p.mode == GEMM_MODE_SAMPLE && qi < p.nq) top.store(p.sample_scores + (size_t)qi * p.sample_ld + (size_t)pair * SAMPLE_KEEP);
     }
     tc_fence_before();
     cluster_sync_all();
@@ -534,36 +587,37 @@ gemm_filter_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
     }
 }
 
-// ---- theta: per query, an approximate T-th largest of its sample scores -------------------------------
-// One CTA per query.  Every thread keeps the two largest values of its strided share; the 2*256
-// survivors are sorted and the element at the requested rank is taken.  Approximate by design: the
-// threshold only has to land between the k-th and roughly the (4k)-th score -- exactness comes from
-// the proof obligation checked after the exact re-score.
-__global__ void __launch_bounds__(256) theta_kernel(const float* __restrict__ sample, int sample_ld, int ns, int thin, int rank,
-                                                    float margin, float* __restrict__ theta, int* __restrict__ cand_count) {
-    __shared__ uint64_t keys[512];
+// ---- theta: per query, the rank-th largest of its sample ------------------------------------------------------
+// One CTA per query over the ns = (sample CTAs) x 8 kept scores.  Every thread keeps the three largest of
+// its strided share (ns <= 1184: at most 5 values each); the 768 survivors are sorted and the element at
+// the requested rank is taken.  Approximate by design: the threshold only has to land between the k-th and
+// roughly the (cand_cap)-th score -- exactness comes from the proof obligation checked after the exact re-score.
+__global__ void __launch_bounds__(256) theta_kernel(const float* __restrict__ sample, int sample_ld, int ns, int rank,
+                                                    float* __restrict__ theta, int* __restrict__ cand_count) {
+    __shared__ uint64_t keys[1024];
     const int qi = blockIdx.x;
     const float* s = sample + (size_t)qi * sample_ld;
-    float b0 = -INFINITY, b1 = -INFINITY;
-    for (long long i = (long long)threadIdx.x * thin; i < ns; i += (long long)blockDim.x * thin) {
+    float b0 = -INFINITY, b1 = -INFINITY, b2 = -INFINITY;
+    for (int i = threadIdx.x; i < ns; i += blockDim.x) {
         const float v = s[i];
-        if (v > b0) {
-            b1 = b0;
-            b0 = v;
-        } else if (v > b1) {
-            b1 = v;
+        if (v > b2) {
+            b2 = v;
+            if (b2 > b1) { const float t = b1; b1 = b2; b2 = t; }
+            if (b1 > b0) { const float t = b0; b0 = b1; b1 = t; }
         }
     }
-    keys[2 * threadIdx.x] = make_key(b0, 2 * threadIdx.x);
-    keys[2 * threadIdx.x + 1] = make_key(b1, 2 * threadIdx.x + 1);
+    keys[3 * threadIdx.x] = make_key(b0, 3 * threadIdx.x);
+    keys[3 * threadIdx.x + 1] = make_key(b1, 3 * threadIdx.x + 1);
+    keys[3 * threadIdx.x + 2] = make_key(b2, 3 * threadIdx.x + 2);
+    for (int i = 3 * blockDim.x + threadIdx.x; i < 1024; i += blockDim.x) keys[i] = 0ull;
     __syncthreads();
-    block_bitonic_sort_desc(keys, 512);
+    block_bitonic_sort_desc(keys, 1024);
     if (threadIdx.x == 0) {
         int r = rank < 1 ? 1 : rank;
-        if (r > 512) r = 512;
-        float v = key_score(keys[r - 1]);
+        if (r > 768) r = 768;
+        float v = keys[r - 1] ? key_score(keys[r - 1]) : -INFINITY;
         if (!(v > -INFINITY)) v = -INFINITY;  // fewer samples than the rank: take everything
-        theta[qi] = v - margin;
+        theta[qi] = v;
         cand_count[qi] = 0;
     }
 }
@@ -575,7 +629,7 @@ __global__ void __launch_bounds__(256) theta_kernel(const float* __restrict__ sa
 // single-query path; keys are sorted in shared memory and the first k emitted.
 // flags[qi] != 0  <=>  the result is NOT proven exact (list overflow, fewer than k candidates while
 // more rows exist, or k-th exact score < theta + eps): the caller re-runs that query on the scan.
-__global__ void __launch_bounds__(512, 1)
+__global__ void __launch_bounds__(512, 2)
 rescore_select_kernel(const float* __restrict__ x, int ld, int d, long long n, const float* __restrict__ q, int k, int kpad,
                       const uint32_t* __restrict__ cand_ids, const int* __restrict__ cand_count, int cand_cap,
                       const float* __restrict__ theta, float eps, const float* __restrict__ eps_dev, uint32_t id_base,
@@ -608,6 +662,7 @@ rescore_select_kernel(const float* __restrict__ x, int ld, int d, long long n, c
 #endif
         const float4* xr = reinterpret_cast<const float4*>(x + (size_t)row * ld);
         float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll 4
         for (int pc = lane; pc < pieces; pc += 32) {
             const float4 v = __ldg(xr + pc);
             const float4 w = q4[pc];
