@@ -168,6 +168,57 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
+// Sums of R rows' lane partials at once.  The xor butterfly of warp_sum leaves every row's total in all
+// 32 lanes -- 5 shuffles per row.  Here the first log2(R) steps halve the number of rows a lane carries
+// instead (a lane keeps the rows selected by its high lane bits and sends the others to its partner), so
+// R rows cost R - 1 + (5 - log2 R) shuffles in total.  Every row still goes through exactly the additions
+// of the butterfly (partner pairs at distance 16, 8, 4, 2, 1, in that order), hence bit-identical sums.
+// Returns the total of row (lane >> (5 - log2 R)).
+template <int N>
+__device__ __forceinline__ void reduce_rows_step(float (&s)[N < 1 ? 1 : N], int lane, int o) {
+    const bool upper = (lane & o) != 0;
+#pragma unroll
+    for (int i = 0; i < N / 2; ++i) {
+        const float keep = upper ? s[i + N / 2] : s[i];
+        const float send = upper ? s[i] : s[i + N / 2];
+        s[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+    }
+}
+template <int R>
+__device__ __forceinline__ float reduce_rows(float (&s)[R], int lane) {
+    static_assert(R == 1 || R == 2 || R == 4 || R == 8, "rows per slot");
+    if constexpr (R == 8) {
+        reduce_rows_step<8>(s, lane, 16);
+        float t4[4] = {s[0], s[1], s[2], s[3]};
+        reduce_rows_step<4>(t4, lane, 8);
+        float t2[2] = {t4[0], t4[1]};
+        reduce_rows_step<2>(t2, lane, 4);
+        float v = t2[0];
+        v += __shfl_xor_sync(0xffffffffu, v, 2);
+        v += __shfl_xor_sync(0xffffffffu, v, 1);
+        return v;
+    } else if constexpr (R == 4) {
+        reduce_rows_step<4>(s, lane, 16);
+        float t2[2] = {s[0], s[1]};
+        reduce_rows_step<2>(t2, lane, 8);
+        float v = t2[0];
+        v += __shfl_xor_sync(0xffffffffu, v, 4);
+        v += __shfl_xor_sync(0xffffffffu, v, 2);
+        v += __shfl_xor_sync(0xffffffffu, v, 1);
+        return v;
+    } else if constexpr (R == 2) {
+        reduce_rows_step<2>(s, lane, 16);
+        float v = s[0];
+        v += __shfl_xor_sync(0xffffffffu, v, 8);
+        v += __shfl_xor_sync(0xffffffffu, v, 4);
+        v += __shfl_xor_sync(0xffffffffu, v, 2);
+        v += __shfl_xor_sync(0xffffffffu, v, 1);
+        return v;
+    } else {
+        return warp_sum(s[0]);
+    }
+}
+
 // Sort the candidate buffer, keep the k best, raise tau.  Block-wide.
 __device__ __forceinline__ void compact_candidates(uint64_t* cand, int* s_count, uint64_t* s_tau, int* s_over, int k) {
     const int n = *s_count;
@@ -496,7 +547,27 @@ __global__ void __launch_bounds__(PSX_MAX_THREADS, 1) scan_topk_kernel(const Sca
             const uint4* xs = reinterpret_cast<const uint4*>(ring + ((size_t)(warp * S + slot)) * PSX_SLOT_BYTES);
             float myscore = 0.0f;
             bool row_done = true;
-            if (cpr == 1) {
+            bool fast = false;
+            if constexpr (PPL > 0 && QREG) {
+                // rows of PPL*32 pieces: a full window is a compile-time number of rows -- no mask walking,
+                // all dot products in flight together, one transposed reduction for the whole window
+                constexpr int RC = SLOT_PIECES / (PPL * 32);
+                constexpr int SH = RC == 8 ? 2 : RC == 4 ? 3 : RC == 2 ? 4 : 5;
+                if (mask == (RC >= 32 ? 0xffffffffu : (1u << RC) - 1u)) {
+                    float s[RC];
+#pragma unroll
+                    for (int r = 0; r < RC; ++r) {
+                        float b[4] = {0.f, 0.f, 0.f, 0.f};
+                        dot.accumulate(xs + r * (PPL * 32), q4, 0, PPL * 32, lane, b);
+                        s[r] = (b[0] + b[1]) + (b[2] + b[3]);
+                    }
+                    const float v = reduce_rows<RC>(s, lane);
+                    myscore = RC == 1 ? v : __shfl_sync(0xffffffffu, v, (lane << SH) & 31);  // lane r takes row r
+                    fast = true;
+                }
+            }
+            if (fast) {
+            } else if (cpr == 1) {
                 uint32_t mm = mask;
                 while (mm) {
                     // two rows per trip: their FMA chains and butterflies are independent, which

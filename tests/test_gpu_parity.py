@@ -95,6 +95,10 @@ def make_oracle(x, metric=0):
         (33, 12, [33]),
         (1000, 8, [50]),
         (777, 100, [1, 100, 777]),
+        (9000, 128, [10, 300]),
+        (7000, 256, [100]),
+        (6000, 384, [100]),
+        (5000, 512, [100]),
         (5000, 768, [50, 500]),
         (20000, 1024, [50, 100, 1333]),
         (3000, 4096, [100, 2048]),
@@ -206,7 +210,7 @@ def _bf16_round(x):
     return r.astype(np.uint32).view(np.float32).reshape(x.shape)
 
 
-@pytest.mark.parametrize("n,d", [(3000, 768), (2000, 1024), (500, 72), (300, 4104)])
+@pytest.mark.parametrize("n,d", [(3000, 768), (2000, 1024), (500, 72), (300, 4104), (4000, 256)])
 def test_bf16_storage(n, d):
     """bf16 rows, fp32 query and accumulate: exact against the oracle run on the rounded rows,
     and recall against the fp32 rows is reported by bench/DESIGN (north star >= 0.999)."""
@@ -404,6 +408,33 @@ def test_determinism_and_tunables():
         D, I = ix.search(q, 100)
         # same reduction tree per row -> bit-identical scores whatever the launch geometry
         assert np.array_equal(I, I0) and np.array_equal(D, D0), (key, val)
+    ix.close()
+
+
+@pytest.mark.parametrize("d,dtype", [(128, 0), (256, 0), (384, 0), (512, 0), (768, 0), (1024, 0), (256, 1), (768, 1), (1024, 1), (100, 0)])
+def test_scores_do_not_depend_on_window_shape(d, dtype):
+    """Full windows take the unrolled path with the transposed multi-row reduction, partly passing windows
+    (predicate inside the scan) and listed rows take the row-at-a-time path: the score of a row must be the
+    same bits whichever path computed it (the reference's exact-tie behaviour rests on that)."""
+    from photo_search_engine_b200._native import F_END, F_NEED_DT, F_START, PsxFilter
+
+    rng = np.random.default_rng(d * 7 + dtype)
+    n = 6000
+    x = unit_rows(rng, n, d)
+    q = unit_rows(rng, 2, d)
+    ix = make_index(x, dtype=dtype)
+    words = rng.integers(1, 1000, n).astype(np.uint64)
+    ix.set_attrs(0, words)
+    D0, I0 = ix.search(q, n)  # every row, full windows
+    score_of = [dict(zip(I0[qi].tolist(), D0[qi].tolist())) for qi in range(2)]
+    flt = PsxFilter(flags=F_NEED_DT | F_START | F_END, start=1, end=600)  # ~60 % pass: most windows are partial
+    npass = int((words <= 600).sum())
+    for mode in (1, 2):
+        ix.set_tunable("filter_mode", mode)
+        D1, I1 = ix.search(q, npass, flt)
+        for qi in range(2):
+            assert sorted(I1[qi].tolist()) == sorted(np.nonzero(words <= 600)[0].tolist())
+            assert all(score_of[qi][i] == s for i, s in zip(I1[qi].tolist(), D1[qi].tolist())), (mode, qi)
     ix.close()
 
 
