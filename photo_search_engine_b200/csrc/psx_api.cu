@@ -608,7 +608,7 @@ static int launch_scan(psx_index* h, const float* q_dev, int k, const psx_filter
             CU(cudaMalloc(&h->rowlist, (size_t)h->cap * sizeof(uint32_t)));
             h->rowlist_cap = h->cap;
         }
-        const long long chunks = (h->n + 1023) / 1024;
+        const long long chunks = (h->n + 2047) / 2048;  // 256 threads x 8 rows per trip
         const unsigned blocks = (unsigned)std::max<long long>(1, std::min<long long>(chunks, (long long)h->sm_count * 8));
         filter_list_kernel<<<blocks, 256, 0, st>>>(h->attrs, h->n, *f, h->rowlist, h->counter + 2, cond_flag);
         g_launches++;

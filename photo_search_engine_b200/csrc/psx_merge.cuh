@@ -13,27 +13,32 @@ namespace psx {
 __global__ void __launch_bounds__(256) filter_list_kernel(const uint64_t* __restrict__ attrs, long long n, psx_filter f,
                                                           uint32_t* __restrict__ list, unsigned int* count, const int* cond_flag) {
     __shared__ unsigned int s_warp[8];
-    if (cond_flag && *cond_flag == 0) return;  // the conditional scan this list is for will not run either
     __shared__ unsigned int s_base;
+    if (cond_flag && *cond_flag == 0) return;  // the conditional scan this list is for will not run either
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    constexpr int PER = 4;  // rows per thread and trip: lane-contiguous pairs, 16-byte loads
+    constexpr int PER = 8;  // rows per thread and trip: four 16-byte loads in flight per thread
     const long long chunk = (long long)blockDim.x * PER;
     for (long long c0 = (long long)blockIdx.x * chunk; c0 < n; c0 += (long long)gridDim.x * chunk) {
-        // thread t covers rows c0 + 2t, 2t+1 and c0 + 512 + 2t, 2t+1
+        // thread t covers the row pairs c0 + h*512 + 2t, +1 for h = 0..3
+        uint64_t a[PER];
+#pragma unroll
+        for (int h = 0; h < PER / 2; ++h) {
+            const long long r = c0 + (long long)h * 2 * blockDim.x + 2 * threadIdx.x;
+            a[2 * h] = a[2 * h + 1] = 0ull;
+            if (r + 1 < n) {
+                const ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2*>(attrs + r));
+                a[2 * h] = v.x;
+                a[2 * h + 1] = v.y;
+            } else if (r < n) {
+                a[2 * h] = __ldg(attrs + r);
+            }
+        }
         uint32_t bits = 0;
 #pragma unroll
         for (int h = 0; h < PER / 2; ++h) {
             const long long r = c0 + (long long)h * 2 * blockDim.x + 2 * threadIdx.x;
-            uint64_t a0 = 0, a1 = 0;
-            if (r + 1 < n) {
-                const ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2*>(attrs + r));
-                a0 = v.x;
-                a1 = v.y;
-            } else if (r < n) {
-                a0 = __ldg(attrs + r);
-            }
-            if (r < n && attr_pass(a0, f)) bits |= 1u << (2 * h);
-            if (r + 1 < n && attr_pass(a1, f)) bits |= 2u << (2 * h);
+            if (r < n && attr_pass(a[2 * h], f)) bits |= 1u << (2 * h);
+            if (r + 1 < n && attr_pass(a[2 * h + 1], f)) bits |= 2u << (2 * h);
         }
         const unsigned int mine = __popc(bits);
         unsigned int incl = mine;

@@ -1,0 +1,111 @@
+"""Subprocess body of tests/test_searcher_ext.py: the reference's UNMODIFIED Searcher with and without
+``BatchedExpansionMixin`` over the same drop-in store; prints one JSON object.  Run with the reference
+checkout first on PYTHONPATH (its ``tests``/``core``/``utils`` packages must win)."""
+from __future__ import annotations
+
+import json
+import os
+import sys
+import tempfile
+
+import numpy as np
+
+import ref_inject_plugin  # noqa: F401  (installs utils.vector_store -> the drop-in class; fake or gpu backend)
+from core.searcher import Searcher  # the reference, unmodified
+from tests.helpers import FakeQueryFormatter, FakeTimeParser  # the reference's own fakes
+
+from photo_search_engine_b200.searcher_ext import BatchedExpansionMixin
+from photo_search_engine_b200.vector_store import VectorStore
+
+D = 16
+
+
+class CountingEmbedding:
+    """Deterministic text -> vector; counts single and batch calls."""
+
+    def __init__(self):
+        self.single = 0
+        self.batch = 0
+
+    def _vec(self, text):
+        rng = np.random.default_rng(sum(ord(c) * (i + 1) for i, c in enumerate(text)) % (2 ** 32))
+        return rng.standard_normal(D).astype(np.float32).tolist()
+
+    def generate_embedding(self, text):
+        self.single += 1
+        return self._vec(text)
+
+    def generate_embedding_batch(self, texts):
+        self.batch += 1
+        return [self._vec(t) for t in texts]
+
+
+class CountingStore(VectorStore):
+    def __init__(self, *a, **k):
+        super().__init__(*a, **k)
+        self.n_search = 0
+        self.n_batch = 0
+
+    def search(self, *a, **k):
+        self.n_search += 1
+        return super().search(*a, **k)
+
+    def search_batch(self, *a, **k):
+        self.n_batch += 1
+        return super().search_batch(*a, **k)
+
+
+class BatchedSearcher(BatchedExpansionMixin, Searcher):
+    pass
+
+
+def alt(text, terms=()):
+    return {"search_text": text, "media_terms": list(terms), "identity_terms": [], "strict_identity_filter": False,
+            "intent_mode": "open", "time_hint": None, "season": None, "time_period": None, "original_query": QUERY,
+            "reason": "test"}
+
+
+QUERY = "海边 日落"
+ALTS = [alt("海滩 黄昏 天空"), alt("沙滩 夕阳", ["landscape"]), alt("ocean sunset photo"), alt("海滩 黄昏 天空")]
+
+
+def build(cls, tmp, tag):
+    store = CountingStore(D, os.path.join(tmp, tag + ".index"), os.path.join(tmp, tag + ".json"))
+    rng = np.random.default_rng(5)
+    for i in range(400):
+        store.add_item(rng.standard_normal(D).astype(np.float32).tolist(),
+                       {"photo_path": f"/photos/{i}.jpg", "description": f"photo {i}", "exif_data": {}, "time_info": {}})
+    fmt = FakeQueryFormatter()
+    fmt.expansion_mapping[QUERY] = ALTS
+    emb = CountingEmbedding()
+    s = cls(embedding=emb, time_parser=FakeTimeParser(), vector_store=store, keyword_store=None, query_formatter=fmt,
+            query_expansion_max_alternatives=4, query_multi_round_enabled=True, query_reflection_enabled=False,
+            embedding_cache_enabled=False)
+    s.index_loaded = True
+    return s, store, emb
+
+
+def slim(results):
+    return [[r.get("photo_path"), r.get("score"), r.get("rank"), r.get("vector_score")] for r in results]
+
+
+def main():
+    out = {}
+    with tempfile.TemporaryDirectory() as tmp:
+        for tag, cls in (("plain", Searcher), ("batched", BatchedSearcher)):
+            s, store, emb = build(cls, tmp, tag)
+            debug = s._empty_search_debug()
+            base_intent = s.query_formatter.format_query(QUERY)
+            direct = s._maybe_expand_query_results(query=QUERY, base_intent=base_intent, base_results=[], base_round_quality=None,
+                                                   normalized_top_k=10, constraints={}, has_filter=False, debug=debug)
+            after_direct = (store.n_search, store.n_batch, emb.single, emb.batch)
+            full = s.search(QUERY, top_k=10, search_mode="high_recall")
+            out[tag] = {"direct": slim(direct), "full": slim(full), "alternatives_run": len(debug["alternatives"]),
+                        "after_direct": after_direct, "total": (store.n_search, store.n_batch, emb.single, emb.batch),
+                        "stats": getattr(s, "psx_batch_stats", None),
+                        "expansion_triggered_full": bool(s._last_search_debug.get("expansion_triggered"))}
+    print("RESULT " + json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()
