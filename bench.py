@@ -357,7 +357,12 @@ def run_ours(args):
         local_rows = hi - lo
         algo_bytes = local_rows * d * esize  # per scan launch, per GPU (N*d*4 per query)
         achieved = algo_bytes / (scan_ms * 1e-3) / 1e9
-        traffic = recorded_traffic()
+        # dram bytes of one launch from the committed ncu capture (taken at 10M x 1024 fp32 on one GPU), scaled to this
+        # launch's row count: the kernel reads every row exactly once whatever the shard size
+        rec = recorded_traffic() or {}
+        traffic = None
+        if rec.get("rows") and rec.get("dim") == d and rec.get("esize") == esize:
+            traffic = rec["dram_bytes_per_launch"] * local_rows / rec["rows"]
         line = {
             "metric": METRIC, "value": qps, "unit": "queries/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -372,7 +377,7 @@ def run_ours(args):
                              if sharded.exchange == "p2p" else "NCCL all-gather of k 64-bit keys per rank + integer merge kernel"),
             },
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": (traffic or {}).get("dram_bytes_per_launch"),
+                         "traffic": traffic, "traffic_source": rec.get("source"),
                          "kernel": "psx::scan_topk_kernel", "algorithmic_bytes_per_launch": algo_bytes,
                          "kernel_ms": scan_ms, "peak_source": peak_src, "frac_of_8TBps_spec": achieved / 8000.0},
             "cpu_baseline": cpu,
@@ -470,6 +475,11 @@ def run_configs_2_3(torch, _native, queries, k, device):
         out[f"config2/1Mx1024/{name}"] = v
     out.update(run_batched(torch, _native, ix, rows, d, k, device, tag="config3/1Mx1024"))
     ix.close()
+    # same batch on the optional bf16 + fp32-master tier: bf16 GEMM over the bf16 rows, exact re-score on the master
+    mixed = _native.NativeIndex(d, _native.METRIC_IP, _native.STORE_BF16_MASTER, device.index or 0)
+    build_corpus(torch, mixed, 0, rows, d, device)
+    out.update(run_batched(torch, _native, mixed, rows, d, k, device, tag="config3/1Mx1024/bf16+fp32_master", bf16_gemm=True, nqs=(256,)))
+    mixed.close()
     return out
 
 
@@ -525,8 +535,9 @@ def run_mixed_tier(torch, _native, index, queries, rows, d, k, device):
     mixed.search_device(queries.data_ptr(), 8, k, sc2.data_ptr(), ids2.data_ptr(), 0, stream=st)
     torch.cuda.synchronize()
     same = bool((ids == ids2).all() and (sc == sc2).all())
+    extra = run_batched(torch, _native, mixed, rows, d, k, device, tag="batched/bf16+fp32_master", bf16_gemm=True, nqs=(256,))
     mixed.close()
-    return {"bf16+fp32_master": {"ms": ms, "qps": 1e3 / ms, "bytes_streamed_per_query": rows * d * 2,
+    return {**extra, "bf16+fp32_master": {"ms": ms, "qps": 1e3 / ms, "bytes_streamed_per_query": rows * d * 2,
                                  "hbm_GBps": rows * d * 2 / ms / 1e6, "bit_identical_to_fp32_index": same,
                                  "note": "exact results at half the bytes per query, 1.5x the HBM footprint"}}
 
@@ -631,18 +642,21 @@ def run_bf16_shard(torch, _native, device):
     return out
 
 
-def run_batched(torch, _native, index, rows, d, k, device, tag="batched"):
+def run_batched(torch, _native, index, rows, d, k, device, tag="batched", bf16_gemm=False, nqs=(256, 32)):
     """BASELINE.json configs[2] shape of work: 256 queries at once on the tensor cores (tcgen05 TF32
-    GEMM, selection fused into the epilogue, exact fp32 re-score), on the resident corpus."""
+    GEMM -- or bf16 GEMM over the bf16 rows of a bf16+fp32-master index --, selection fused into the
+    epilogue, exact fp32 re-score), on the resident corpus."""
     out = {}
     try:
-        tf32_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops"] / 2.0
+        tf32_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops"] / (1.0 if bf16_gemm else 2.0)
     except Exception:
-        tf32_peak = 1590.0 / 2.0
+        tf32_peak = 1590.0 / (1.0 if bf16_gemm else 2.0)
+    gemm_esize = 2 if bf16_gemm else 4
+    kind = "bf16" if bf16_gemm else "TF32"
     hbm_peak, _ = measured_peak()
     gen = torch.Generator(device=device).manual_seed(QUERY_SEED + 1)
     stream = torch.cuda.current_stream()
-    for nq in (256, 32):
+    for nq in nqs:
         q = torch.randn((nq, d), generator=gen, device=device)
         q = (q / q.norm(dim=1, keepdim=True)).contiguous()
         sc = torch.empty((nq, k), device=device)
@@ -684,7 +698,7 @@ def run_batched(torch, _native, index, rows, d, k, device, tag="batched"):
         ms = sum(ev[3 * i + 1].elapsed_time(ev[3 * i + 2]) for i in range(steps)) / steps
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         flops = 2.0 * rows * d * nq
-        t_hbm = rows * d * 4 / (hbm_peak * 1e9) * 1e3
+        t_hbm = rows * d * gemm_esize / (hbm_peak * 1e9) * 1e3
         t_tc = flops / (tf32_peak * 1e12) * 1e3
         # parity of the batch against the streaming scan, query by query (bit-identical by design)
         Ds = torch.empty((4, k), device=device)
@@ -695,10 +709,11 @@ def run_batched(torch, _native, index, rows, d, k, device, tag="batched"):
         same = bool(((ids[:4] == Is) | ~ok[:, None]).all() and ((sc[:4] == Ds) | ~ok[:, None]).all())
         out[f"{tag}/nq={nq}"] = {
             "ms_per_batch": ms, "queries_per_s": nq / ms * 1e3, "effective_TFLOPs": flops / ms / 1e9,
-            "corpus_GBps": rows * d * 4 / ms / 1e6, "ms_per_batch_kernels_only": ms_kernels,
+            "corpus_GBps": rows * d * gemm_esize / ms / 1e6, "ms_per_batch_kernels_only": ms_kernels,
             "unproven_queries_rerun_on_scan_per_batch": unproven / steps,
             "timing_note": "ms_per_batch includes the certificate read-back (one host sync) and the scan re-runs of unproven queries",
-            "roofline_frac": max(t_hbm, t_tc) / ms, "roofline_note": f"max(HBM {t_hbm:.3f} ms, TF32 {t_tc:.3f} ms at {tf32_peak:.0f} TFLOP/s = half the measured bf16 peak) / measured",
+            "roofline_frac": max(t_hbm, t_tc) / ms, "roofline_note": f"max(HBM {t_hbm:.3f} ms, {kind} {t_tc:.3f} ms at {tf32_peak:.0f} TFLOP/s"
+                                                                    f"{'' if bf16_gemm else ' = half the measured bf16 peak'}) / measured",
             "bit_identical_to_scan": same,
         }
         if nq == 256:

@@ -106,6 +106,7 @@ struct psx_index {
     float max_norm = 0.f;         // host copy of its square root
     int batch_min = 4;        // smallest nq routed to the tensor-core path
     bool batch_pair = true;   // 129..256 queries: CTA-pair (cta_group::2) kernel instead of two accumulators per CTA
+    bool batch_bf16 = true;   // PSX_STORE_BF16_MASTER: the batched GEMM reads the bf16 rows (kind::f16) instead of the fp32 master (kind::tf32)
     float* bq = nullptr;      // [256][ld] zero-padded query block
     float* btheta = nullptr;  // [256]
     int* bcount = nullptr;    // [256]
@@ -140,14 +141,15 @@ constexpr int PAIR_STAGES = 6;
 static int batch_bn(int mt, bool pair) { return mt == 2 ? (pair ? 256 : BatchCfg<2>::BN) : BatchCfg<1>::BN; }
 
 // cta_group::2 variant for 129..256 queries: grid = 2 * pairs, cluster (2,1,1) is a kernel attribute
+template <bool BF>
 static int launch_gemm_pair(psx_index* h, const CUtensorMap& mq, const CUtensorMap& mx, const GemmParams& gp, int pairs, cudaStream_t st) {
-    constexpr size_t smem = (size_t)PAIR_STAGES * (GEMM_M + 128) * GEMM_BK * 4 + 256;
+    constexpr size_t smem = (size_t)PAIR_STAGES * (GEMM_M + 128) * GEMM_KB_BYTES + 256;
     static std::atomic<bool> ready[64];
     if (h->device < 64 && !ready[h->device].load()) {
-        CU(cudaFuncSetAttribute(gemm_filter_pair_kernel<PAIR_STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CU(cudaFuncSetAttribute(gemm_filter_pair_kernel<PAIR_STAGES, BF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         ready[h->device].store(true);
     }
-    gemm_filter_pair_kernel<PAIR_STAGES><<<2 * pairs, GEMM_THREADS, smem, st>>>(mq, mx, gp);
+    gemm_filter_pair_kernel<PAIR_STAGES, BF><<<2 * pairs, GEMM_THREADS, smem, st>>>(mq, mx, gp);
     g_launches++;
     CU(cudaGetLastError());
     return PSX_OK;
@@ -687,15 +689,16 @@ static EncodeTiledFn encode_tiled_fn() {
     }();
     return fn;
 }
-// 2-D fp32 tensor [rows][cols] with row stride ld floats, box = 32 floats x box_rows, 128-byte swizzle
-static int make_map(CUtensorMap* map, const float* base, long long rows, int cols, int ld, int box_rows) {
+// 2-D fp32 (or bf16) tensor [rows][cols] with row stride ld elements, box = one 128-byte swizzle row x box_rows
+static int make_map(CUtensorMap* map, const void* base, bool bf16, long long rows, int cols, int ld, int box_rows) {
     EncodeTiledFn fn = encode_tiled_fn();
     if (!fn) return fail(PSX_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+    const size_t esz = bf16 ? 2 : 4;
     cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-    cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
-    cuuint32_t box[2] = {(cuuint32_t)GEMM_BK, (cuuint32_t)box_rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * esz};
+    cuuint32_t box[2] = {(cuuint32_t)(GEMM_KB_BYTES / esz), (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    CUresult r = fn(map, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(PSX_ERR_CUDA, "cuTensorMapEncodeTiled failed with %d", (int)r);
     return PSX_OK;
@@ -775,18 +778,18 @@ struct BatchTimer {
     }
 };
 
-template <int MT>
+template <int MT, bool BF>
 static int launch_gemm(psx_index* h, const CUtensorMap& mq, const CUtensorMap& mx, const GemmParams& gp, int grid, cudaStream_t st) {
     constexpr int STAGES = BatchCfg<MT>::STAGES;
     constexpr int BATCH_BN = BatchCfg<MT>::BN;
-    constexpr int STAGE_BYTES = (MT * GEMM_M + BATCH_BN) * GEMM_BK * 4;
+    constexpr int STAGE_BYTES = (MT * GEMM_M + BATCH_BN) * GEMM_KB_BYTES;
     constexpr size_t smem = (size_t)STAGES * STAGE_BYTES + 256;
     static std::atomic<bool> ready[64];
     if (h->device < 64 && !ready[h->device].load()) {
-        CU(cudaFuncSetAttribute(gemm_filter_kernel<MT, BATCH_BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CU(cudaFuncSetAttribute(gemm_filter_kernel<MT, BATCH_BN, STAGES, BF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         ready[h->device].store(true);
     }
-    gemm_filter_kernel<MT, BATCH_BN, STAGES><<<grid, GEMM_THREADS, smem, st>>>(mq, mx, gp);
+    gemm_filter_kernel<MT, BATCH_BN, STAGES, BF><<<grid, GEMM_THREADS, smem, st>>>(mq, mx, gp);
     g_launches++;
     CU(cudaGetLastError());
     return PSX_OK;
@@ -805,7 +808,8 @@ static int launch_batch(psx_index* h, const float* q_dev, int nq, int k, const p
     // number of rows above the sample's 16th score is ~ T * Gamma(16)/16: it undercuts k + (rows within eps of
     // the k-th) with probability ~3e-5 per query at k = 100 (8 sample scores and T = 3k+48 failed 2.7 % of the
     // queries of a 10M-row corpus, each of which costs a full scan).
-    const int T = 4 * k + 64;
+    // (bf16 operands: the wider error bound eps asks for ~60 more rows above theta; T = 4k+64 left 3e-4 of the queries unproven)
+    const int T = (h->dtype == PSX_STORE_BF16_MASTER && h->batch_bf16) ? 5 * k + 96 : 4 * k + 64;
     int tile_step = T / 16;
     if (tile_step < 1) tile_step = 1;
     const int sample_tiles = (num_tiles + tile_step - 1) / tile_step;
@@ -815,12 +819,24 @@ static int launch_batch(psx_index* h, const float* q_dev, int nq, int k, const p
     if (rc) return rc;
     // queries -> zero-padded [MT*128][ld] block (rows beyond nq and columns beyond d are zero)
     const int fld = fp32_ld(h);
-    CU(cudaMemsetAsync(h->bq, 0, (size_t)MT * GEMM_M * fld * sizeof(float), st));
-    CU(cudaMemcpy2DAsync(h->bq, (size_t)fld * sizeof(float), q_dev, (size_t)h->d * sizeof(float), (size_t)h->d * sizeof(float), nq,
-                         cudaMemcpyDeviceToDevice, st));
+    // bf16 + fp32 master: the GEMM streams the bf16 rows (half the HBM bytes, kind::f16 at twice the TF32 rate);
+    // the survivors are re-scored on the master exactly as in the TF32 form
+    const bool bf = h->dtype == PSX_STORE_BF16_MASTER && h->batch_bf16;
     CUtensorMap mq, mx;
-    if ((rc = make_map(&mq, h->bq, (long long)MT * GEMM_M, h->d, fld, GEMM_M))) return rc;
-    if ((rc = make_map(&mx, fp32_rows(h), h->n, h->d, fld, pair ? 128 : BATCH_BN))) return rc;
+    if (bf) {
+        CU(cudaMemsetAsync(h->bq, 0, (size_t)MT * GEMM_M * h->ld * sizeof(__nv_bfloat16), st));
+        pack_rows_kernel<__nv_bfloat16><<<(nq + 7) / 8, 256, 0, st>>>(q_dev, (__nv_bfloat16*)h->bq, nq, h->d, h->ld, 0, nullptr);
+        g_launches++;
+        CU(cudaGetLastError());
+        if ((rc = make_map(&mq, h->bq, true, (long long)MT * GEMM_M, h->d, h->ld, GEMM_M))) return rc;
+        if ((rc = make_map(&mx, h->x, true, h->n, h->d, h->ld, pair ? 128 : BATCH_BN))) return rc;
+    } else {
+        CU(cudaMemsetAsync(h->bq, 0, (size_t)MT * GEMM_M * fld * sizeof(float), st));
+        CU(cudaMemcpy2DAsync(h->bq, (size_t)fld * sizeof(float), q_dev, (size_t)h->d * sizeof(float), (size_t)h->d * sizeof(float), nq,
+                             cudaMemcpyDeviceToDevice, st));
+        if ((rc = make_map(&mq, h->bq, false, (long long)MT * GEMM_M, h->d, fld, GEMM_M))) return rc;
+        if ((rc = make_map(&mx, fp32_rows(h), false, h->n, h->d, fld, pair ? 128 : BATCH_BN))) return rc;
+    }
     GemmParams gp;
     memset(&gp, 0, sizeof gp);
     gp.n = h->n;
@@ -837,13 +853,19 @@ static int launch_batch(psx_index* h, const float* q_dev, int nq, int k, const p
         gp.attrs = h->attrs;
         gp.f = *f;
     }
+    auto run_gemm = [&](int grid) -> int {
+        if (bf)
+            return pair ? launch_gemm_pair<true>(h, mq, mx, gp, grid, st)
+                        : MT == 2 ? launch_gemm<2, true>(h, mq, mx, gp, grid, st) : launch_gemm<1, true>(h, mq, mx, gp, grid, st);
+        return pair ? launch_gemm_pair<false>(h, mq, mx, gp, grid, st)
+                    : MT == 2 ? launch_gemm<2, false>(h, mq, mx, gp, grid, st) : launch_gemm<1, false>(h, mq, mx, gp, grid, st);
+    };
     BatchTimer bt(st);
     // pass 1: sample
     gp.mode = GEMM_MODE_SAMPLE;
     gp.tile_step = tile_step;
     DBG_SYNC(st, "query staging");
-    rc = pair ? launch_gemm_pair(h, mq, mx, gp, grid_s, st)
-              : MT == 2 ? launch_gemm<2>(h, mq, mx, gp, grid_s, st) : launch_gemm<1>(h, mq, mx, gp, grid_s, st);
+    rc = run_gemm(grid_s);
     if (rc) return rc;
     DBG_SYNC(st, "gemm_filter_kernel(sample)");
     bt.mark("sample pass");
@@ -859,8 +881,7 @@ static int launch_batch(psx_index* h, const float* q_dev, int nq, int k, const p
     gp.mode = GEMM_MODE_FILTER;
     gp.tile_step = 1;
     const int grid_f = pair ? std::min(h->sm_count / 2, num_tiles) : std::min(h->sm_count, num_tiles);
-    rc = pair ? launch_gemm_pair(h, mq, mx, gp, grid_f, st)
-              : MT == 2 ? launch_gemm<2>(h, mq, mx, gp, grid_f, st) : launch_gemm<1>(h, mq, mx, gp, grid_f, st);
+    rc = run_gemm(grid_f);
     if (rc) return rc;
     DBG_SYNC(st, "gemm_filter_kernel(filter)");
     bt.mark("filter pass");
@@ -880,7 +901,8 @@ static int launch_batch(psx_index* h, const float* q_dev, int nq, int k, const p
         CU(cudaStreamSynchronize(st));
         h->max_norm = sqrtf(m2);
     }
-    const float eps = 2.2e-3f * (qnorm_max > 0.f ? qnorm_max : 1.0f) * (h->max_norm > 0.f ? h->max_norm : 1.0f);
+    // bf16 operands keep 8 significant bits each: |score_bf16 - score| <= (2^-9 + 2^-9) sum|q_i x_i| <= 2^-8 |q| |x|; 4.3e-3 adds 10 %
+    const float eps = (bf ? 4.3e-3f : 2.2e-3f) * (qnorm_max > 0.f ? qnorm_max : 1.0f) * (h->max_norm > 0.f ? h->max_norm : 1.0f);
     rescore_select_kernel<<<nq, 512, smem, st>>>(fp32_rows(h), fld, h->d, h->n, q_dev, k, kpad, h->bcand, h->bcount,
                                                  BATCH_CAND_CAP, h->btheta, eps, nullptr, id_base, out_scores, out_ids, out_keys, flags_dev);
     g_launches++;
@@ -1362,6 +1384,8 @@ extern "C" int psx_set_tunable(psx_index* h, const char* key, int value) {
         h->filter_mode = value < 0 || value > 2 ? 0 : value;
     } else if (!strcmp(key, "batch_pair")) {
         h->batch_pair = value > 0;
+    } else if (!strcmp(key, "batch_bf16")) {  // bf16+master indexes: 1 = bf16 GEMM over the bf16 rows (default), 0 = TF32 GEMM over the master
+        h->batch_bf16 = value > 0;
     } else if (!strcmp(key, "batch_min")) {  // smallest nq sent to the tensor-core path; 0 disables it
         h->batch_min = value < 0 ? 4 : value;
     } else {

@@ -27,8 +27,15 @@
 
 namespace psx {
 
-constexpr int GEMM_BK = 32;        // fp32 elements per k-block = one 128-byte swizzle row
-constexpr int GEMM_UMMA_K = 8;     // tf32
+// One k-block = one 128-byte swizzle row per operand row: 32 fp32 elements (kind::tf32, K = 8 per MMA) or
+// 64 bf16 elements (kind::f16, K = 16 per MMA) -- four MMAs per k-block either way, and the same bytes per
+// pipeline stage.  BF selects the bf16 form (PSX_STORE_BF16_MASTER: the GEMM streams the bf16 rows, half
+// the HBM bytes at twice the tensor rate; exactness still comes from the fp32 re-score).
+constexpr int GEMM_KB_BYTES = 128;
+constexpr int GEMM_MMAS_PER_KB = 4;
+constexpr int GEMM_BK = 32;        // fp32 elements per k-block
+template <bool BF>
+__host__ __device__ constexpr int gemm_bk() { return BF ? 64 : 32; }
 constexpr int GEMM_M = 128;        // queries per accumulator tile
 constexpr int GEMM_THREADS = 256;  // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warp3 idle, warps4-7 epilogue
 constexpr int GEMM_MODE_SAMPLE = 0, GEMM_MODE_FILTER = 1;
@@ -91,21 +98,31 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-// D[tmem] (+)= A[smem] * B[smem]^T, tf32 inputs, fp32 accumulate
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
-        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-        : "memory");
+// D[tmem] (+)= A[smem] * B[smem]^T, tf32 (or bf16) inputs, fp32 accumulate
+template <bool BF>
+__device__ __forceinline__ void umma_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    if constexpr (BF) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+            "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+            : "memory");
+    } else {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+            "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+            : "memory");
+    }
 }
 // shared-memory matrix descriptor: K-major, 128-byte swizzle, 8-row groups 1024 bytes apart
 __device__ __forceinline__ uint64_t umma_smem_desc(uint32_t smem_addr) {
     return (uint64_t)((smem_addr >> 4) & 0x3fffu) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
-// instruction descriptor: D fp32, A/B tf32, both K-major, M x N
-__host__ __device__ constexpr uint32_t umma_idesc_tf32(int m, int n) {
-    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+// instruction descriptor: D fp32, A/B tf32 (format 2 of kind::tf32) or bf16 (format 1 of kind::f16), both K-major, M x N
+template <bool BF>
+__host__ __device__ constexpr uint32_t umma_idesc(int m, int n) {
+    return (1u << 4) | ((BF ? 1u : 2u) << 7) | ((BF ? 1u : 2u) << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 // 32 consecutive fp32 columns of this warp's 32 TMEM lanes -> 32 registers per thread
 __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {
@@ -153,13 +170,14 @@ struct SampleTop {
 // ---- the GEMM + fused selection kernel ---------------------------------------------------------------
 // MT accumulator tiles of 128 queries each, BN corpus rows per tile.  TMEM columns: MT*BN per
 // accumulator stage, 512 in total.
-template <int MT, int BN, int STAGES>
+template <int MT, int BN, int STAGES, bool BF>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_x, const GemmParams p) {
     constexpr int ACC_COLS = MT * BN;
     constexpr int ACC_STAGES = 512 / ACC_COLS >= 2 ? 2 : 1;
-    constexpr int A_BYTES = MT * GEMM_M * GEMM_BK * 4;
-    constexpr int B_BYTES = BN * GEMM_BK * 4;
+    constexpr int A_BYTES = MT * GEMM_M * GEMM_KB_BYTES;
+    constexpr int B_BYTES = BN * GEMM_KB_BYTES;
+    constexpr int BK = gemm_bk<BF>();
     constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static_assert(ACC_COLS <= 512 && BN % 32 == 0 && BN <= 256, "bad tile");
 
@@ -172,7 +190,7 @@ gemm_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + ACC_STAGES);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int kblocks = (p.d + GEMM_BK - 1) / GEMM_BK;
+    const int kblocks = (p.d + BK - 1) / BK;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&map_q);
@@ -210,8 +228,8 @@ gemm_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
                     mbar_arrive_expect_tx(bar, STAGE_BYTES);
 #pragma unroll
                     for (int m = 0; m < MT; ++m)
-                        tma_load_2d(a_dst + m * (GEMM_M * GEMM_BK * 4), &map_q, bar, kb * GEMM_BK, m * GEMM_M);
-                    tma_load_2d(a_dst + A_BYTES, &map_x, bar, kb * GEMM_BK, row0);
+                        tma_load_2d(a_dst + m * (GEMM_M * GEMM_KB_BYTES), &map_q, bar, kb * BK, m * GEMM_M);
+                    tma_load_2d(a_dst + A_BYTES, &map_x, bar, kb * BK, row0);
                     if (++s == STAGES) {
                         s = 0;
                         ph ^= 1u;
@@ -222,7 +240,7 @@ gemm_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
     } else if (warp == 1) {
         // ===== MMA issuer (one thread) =====
         if (lane == 0) {
-            constexpr uint32_t idesc = umma_idesc_tf32(GEMM_M, BN);
+            constexpr uint32_t idesc = umma_idesc<BF>(GEMM_M, BN);
             int s = 0, a = 0;
             uint32_t ph = 0, aph = 0;
             for (int t = first; t < p.num_tiles; t += stride) {
@@ -235,13 +253,13 @@ gemm_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
                     const uint64_t b_desc = umma_smem_desc(a_addr + A_BYTES);
 #pragma unroll
                     for (int m = 0; m < MT; ++m) {
-                        const uint64_t a_desc = umma_smem_desc(a_addr + m * (GEMM_M * GEMM_BK * 4));
+                        const uint64_t a_desc = umma_smem_desc(a_addr + m * (GEMM_M * GEMM_KB_BYTES));
                         const uint32_t d_addr = tmem_base + (uint32_t)(a * ACC_COLS + m * BN);
 #pragma unroll
-                        for (int k = 0; k < GEMM_BK / GEMM_UMMA_K; ++k) {
+                        for (int k = 0; k < GEMM_MMAS_PER_KB; ++k) {
                             // advancing K inside the 128-byte swizzle row: +32 bytes = +2 in the
                             // (address >> 4) field of both descriptors
-                            umma_tf32(d_addr, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+                            umma_ss<BF>(d_addr, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
                         }
                     }
                     umma_commit(smem_u32(empty_bar + s));  // smem slot reusable once these MMAs retire
@@ -375,12 +393,21 @@ __device__ __forceinline__ void umma_commit_2sm(uint32_t bar, uint16_t mask) {
                  "h"(mask)
                  : "memory");
 }
-__device__ __forceinline__ void umma_tf32_2sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
-        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-        : "memory");
+template <bool BF>
+__device__ __forceinline__ void umma_ss_2sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    if constexpr (BF) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+            "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+            : "memory");
+    } else {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+            "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+            : "memory");
+    }
 }
 // TMA load whose completion bytes are credited to the LEADER CTA's mbarrier (peer bit of the address cleared)
 __device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
@@ -390,13 +417,14 @@ __device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap*
         : "memory");
 }
 
-template <int STAGES>
+template <int STAGES, bool BF>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm_filter_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_x, const GemmParams p) {
     constexpr int BN = 256;              // corpus rows per pair tile (128 per CTA)
     constexpr int ACC_STAGES = 2;        // 2 x 256 TMEM columns
-    constexpr int A_BYTES = GEMM_M * GEMM_BK * 4;        // this CTA's 128 queries
-    constexpr int B_BYTES = (BN / 2) * GEMM_BK * 4;      // this CTA's 128 corpus rows
+    constexpr int A_BYTES = GEMM_M * GEMM_KB_BYTES;        // this CTA's 128 queries
+    constexpr int B_BYTES = (BN / 2) * GEMM_KB_BYTES;      // this CTA's 128 corpus rows
+    constexpr int BK = gemm_bk<BF>();
     constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
 
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -410,7 +438,7 @@ gemm_filter_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t cta = cluster_ctarank();
     const bool leader = cta == 0;
-    const int kblocks = (p.d + GEMM_BK - 1) / GEMM_BK;
+    const int kblocks = (p.d + BK - 1) / BK;
     const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
 
     if (warp == 0 && lane == 0) {
@@ -457,8 +485,8 @@ gemm_filter_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
                     const uint32_t bar = smem_u32(full_bar + s);
                     const uint32_t a_dst = smem_u32(tiles + (size_t)s * STAGE_BYTES);
                     if (leader) mbar_arrive_expect_tx(bar, 2 * STAGE_BYTES);
-                    tma_load_2d_2sm(a_dst, &map_q, bar, kb * GEMM_BK, (int)cta * GEMM_M);
-                    tma_load_2d_2sm(a_dst + A_BYTES, &map_x, bar, kb * GEMM_BK, row0);
+                    tma_load_2d_2sm(a_dst, &map_q, bar, kb * BK, (int)cta * GEMM_M);
+                    tma_load_2d_2sm(a_dst + A_BYTES, &map_x, bar, kb * BK, row0);
                     if (!leader) mbar_arrive_cluster(mapa_shared(bar, 0));
                     if (++s == STAGES) {
                         s = 0;
@@ -473,7 +501,7 @@ gemm_filter_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
     } else if (warp == 1) {
         // ===== MMA issuer: one thread of the leader CTA drives both tensor cores =====
         if (leader && lane == 0) {
-            constexpr uint32_t idesc = umma_idesc_tf32(2 * GEMM_M, BN);
+            constexpr uint32_t idesc = umma_idesc<BF>(2 * GEMM_M, BN);
             int s = 0, a = 0;
             uint32_t ph = 0, aph = 0;
 #ifdef PSX_DEBUG_KERNELS
@@ -503,7 +531,7 @@ gemm_filter_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
                     const uint64_t b_desc = umma_smem_desc(a_addr + A_BYTES);
                     const uint32_t d_addr = tmem_base + (uint32_t)(a * BN);
 #pragma unroll
-                    for (int k = 0; k < GEMM_BK / GEMM_UMMA_K; ++k) umma_tf32_2sm(d_addr, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+                    for (int k = 0; k < GEMM_MMAS_PER_KB; ++k) umma_ss_2sm<BF>(d_addr, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
                     umma_commit_2sm(smem_u32(empty_bar + s), 3);
                     if (++s == STAGES) {
                         s = 0;

@@ -147,3 +147,32 @@ def test_batch_device_api_flags():
     assert np.array_equal(ids.cpu().numpy()[ok], Is[ok] + 1000)
     assert np.array_equal(sc.cpu().numpy()[ok], Ds[ok])
     ix.close()
+
+
+@pytest.mark.parametrize("n,d,nq,k", [(150_000, 1024, 200, 100), (100_000, 768, 64, 50), (70_000, 100, 256, 10), (90_000, 200, 5, 100)])
+def test_bf16_master_batch_uses_bf16_gemm_and_stays_exact(n, d, nq, k):
+    """bf16 + fp32 master index: the batched GEMM streams the bf16 rows (kind::f16, operands rounded to 8 bits),
+    the survivors are re-scored on the fp32 master -- every certified result is bit-identical to an fp32 index,
+    with the bf16 GEMM (default) and with the TF32 GEMM over the master (batch_bf16 = 0)."""
+    rng = np.random.default_rng(n + d + nq + 7)
+    x = unit_rows(rng, n, d)
+    q = unit_rows(rng, nq, d)
+    q[0] = x[4242]
+    exact = N().NativeIndex(d)
+    exact.add(x)
+    exact.set_tunable("batch_min", 0)
+    De, Ie = exact.search(q, k)
+    exact.close()
+    ix = N().NativeIndex(d, 0, N().STORE_BF16_MASTER, 0)
+    ix.add(x)
+    for bf in (1, 0):
+        ix.set_tunable("batch_bf16", bf)
+        ix.set_tunable("batch_min", 2)
+        before = ix.batch_stats()
+        Db, Ib = ix.search(q, k)
+        served, fallbacks = (a - b for a, b in zip(ix.batch_stats(), before))
+        assert served == nq
+        assert np.array_equal(Ib, Ie) and np.array_equal(Db, De), bf
+        assert Ib[0, 0] == 4242
+        assert fallbacks <= max(1, nq // 10), (bf, fallbacks)
+    ix.close()

@@ -22,13 +22,20 @@ def main():
     ap.add_argument("--k", type=int, default=100)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--clustered", action="store_true")
+    ap.add_argument("--seed", type=int, default=1)
+    ap.add_argument("--trials", type=int, default=0, help="extra batches of fresh random queries: count unproven queries")
     ap.add_argument("--pair", action="store_true", help="cta_group::2 kernel for nq > 128")
+    ap.add_argument("--store", default="fp32", choices=["fp32", "mixed"], help="mixed = bf16 rows + fp32 master (bf16 GEMM)")
+    ap.add_argument("--tunable", action="append", default=[], help="key=value, repeatable")
     a = ap.parse_args()
-    ix = _native.NativeIndex(a.dim)
+    ix = _native.NativeIndex(a.dim, 0, _native.STORE_BF16_MASTER if a.store == "mixed" else _native.STORE_F32, 0)
+    for kv in a.tunable:
+        key, val = kv.split("=")
+        ix.set_tunable(key, int(val))
     ix.reserve(a.rows)
     if a.pair:
         ix.set_tunable("batch_pair", 1)
-    g = torch.Generator(device="cuda").manual_seed(1)
+    g = torch.Generator(device="cuda").manual_seed(a.seed)
     done = 0
     cent = torch.randn((4096, a.dim), generator=g, device="cuda")
     while done < a.rows:
@@ -60,9 +67,22 @@ def main():
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / a.steps
     flops = 2.0 * a.rows * a.dim * a.nq
-    print(json.dumps({"rows": a.rows, "dim": a.dim, "nq": a.nq, "k": a.k, "ms_per_batch": ms, "queries_per_s": a.nq / ms * 1e3,
+    print(json.dumps({"rows": a.rows, "dim": a.dim, "nq": a.nq, "k": a.k, "store": a.store, "ms_per_batch": ms, "queries_per_s": a.nq / ms * 1e3,
                       "TFLOPs": flops / ms / 1e9, "GBps_corpus": a.rows * a.dim * 4 / ms / 1e6,
-                      "unproven": int((flags != 0).sum())}))
+                      "unproven": int((flags != 0).sum()),
+                      "unproven_detail": [(int(i), int(flags[i])) for i in flags.nonzero().flatten().tolist()][:8]}))
+    if a.trials:
+        bad = {}
+        for t in range(a.trials):
+            q2 = torch.randn((a.nq, a.dim), generator=g, device="cuda")
+            q2 /= q2.norm(dim=1, keepdim=True)
+            ix.search_batch_device(q2.data_ptr(), a.nq, a.k, sc.data_ptr(), ids.data_ptr(), flags.data_ptr(), stream=stream.cuda_stream)
+            torch.cuda.synchronize()
+            for i in flags.nonzero().flatten().tolist():
+                bad[int(flags[i])] = bad.get(int(flags[i]), 0) + 1
+        print(json.dumps({"trials": a.trials, "queries": a.trials * a.nq, "unproven_by_code": bad}))
+        run()
+        torch.cuda.synchronize()
     # correctness spot check vs the streaming scan
     ix.set_tunable("batch_min", 0)
     Ds, Is = ix.search(q[:8].cpu().numpy(), a.k)
