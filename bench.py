@@ -799,8 +799,8 @@ def run_config5(args):
         hi_p.add_device(blk.data_ptr(), take, stream=st)
         done += take
         del blk
-    lo_s = ShardedIndex(lo_p, lo, exchange=args.exchange)
-    hi_s = ShardedIndex(hi_p, lo, exchange=args.exchange)
+    lo_s = ShardedIndex(lo_p, lo, exchange=args.exchange, bounds=bounds)
+    hi_s = ShardedIndex(hi_p, lo, exchange=args.exchange, bounds=bounds)
     gen = torch.Generator().manual_seed(99)
     ids = torch.randint(0, rows, (nq,), generator=gen).tolist()
     hits = 0
@@ -826,6 +826,8 @@ def run_config5(args):
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     stream = torch.cuda.current_stream()
+    clocks = ClockSampler(local_rank).start() if rank == 0 else None
+    launches0 = _native.launch_count()
     e0.record(stream)
     for i in range(args.steps):
         lo_s.search_device(qs[i % 16], k + 1)
@@ -833,6 +835,8 @@ def run_config5(args):
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
+    launches = (_native.launch_count() - launches0) * world
+    clock_info = clocks.stop() if clocks else None
     ms = e0.elapsed_time(e1) / args.steps
     t = torch.tensor([ms], device=device, dtype=torch.float64)
     if world > 1:
@@ -861,7 +865,7 @@ def run_config5(args):
                            "algorithmic_bytes_per_launch": (hi - lo) * d * 2},
               "e2e": {"value": e2e, "unit": "queries/s", "h2d_bytes_per_step": d * 4, "d2h_bytes_per_step": d * 4 + world * k * 12,
                       "api": "ShardedIndex.search_by_id(global id)"},
-              "cpu_baseline": None, "gpu_launches": None})
+              "cpu_baseline": None, "gpu_launches": launches, "clocks": clock_info})
     lo_p.close()
     hi_p.close()
     if world > 1:

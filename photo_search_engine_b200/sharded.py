@@ -33,7 +33,8 @@ class ShardedIndex:
     """
 
     def __init__(self, local, row0: int, k_max: int = 128, group=None,
-                 local_search: Optional[Callable] = None, merge: Optional[Callable] = None, exchange: str = "auto") -> None:
+                 local_search: Optional[Callable] = None, merge: Optional[Callable] = None, exchange: str = "auto",
+                 bounds: Optional[List[int]] = None) -> None:
         import torch
         import torch.distributed as dist
 
@@ -47,6 +48,9 @@ class ShardedIndex:
         self._merge = merge
         self.device = torch.device("cuda", local.device) if local_search is None else torch.device("cpu")
         self._bufs = {}
+        # first row of every shard (+ the total), when the caller knows it (``shard_bounds``): lets
+        # ``search_by_id`` name the owner of a row without a collective
+        self.bounds = list(bounds) if bounds is not None else None
         # exchange: "p2p" = fused into the kernels over NVLink peer mappings (torch symmetric memory
         # provides the mappings), "nccl" = all_gather_into_tensor + merge kernel, "auto" = p2p if it can
         # be set up.  The CPU (gloo) test path always uses the collective.
@@ -154,9 +158,14 @@ class ShardedIndex:
         if owner_mine:
             q.copy_(t.from_numpy(self.local.reconstruct(global_id - self.row0))[None, :])
         if self.world > 1:
-            owner = t.tensor([self.rank if owner_mine else -1], device=self.device)
-            self.dist.all_reduce(owner, op=self.dist.ReduceOp.MAX, group=self.group)
-            self.dist.broadcast(q, src=int(owner.item()), group=self.group)
+            if self.bounds is not None:  # contiguous shards: the owner follows from the id, no collective, no host sync
+                owner_rank = int(np.searchsorted(np.asarray(self.bounds[1:]), global_id, side="right"))
+            else:
+                owner = t.tensor([self.rank if owner_mine else -1], device=self.device)
+                self.dist.all_reduce(owner, op=self.dist.ReduceOp.MAX, group=self.group)
+                owner_rank = int(owner.item())
+            src = owner_rank if self.group is None else self.dist.get_global_rank(self.group, owner_rank)
+            self.dist.broadcast(q, src=src, group=self.group)
         s, i = self.search_device(q, k + 1, flt)
         keep = i[0] != global_id
         # the row itself is the best hit unless an exact duplicate with a lower id exists: drop it wherever it is

@@ -46,15 +46,22 @@ def _worker(rank: int, world: int, port: int, out_dir: str) -> None:
 
     class Local:
         device, metric, d = 0, 0, 24
+        ntotal = hi - lo
+
+        @staticmethod
+        def reconstruct(i):
+            return x[lo + i].copy()
 
     local = Local()
     kp = _native.kpad(k)
 
     def local_search(q_dev, kk, row0, flt):
-        D = np.full((nq, kk), -np.inf, np.float32)
-        I = np.full((nq, kk), -1, np.int64)
-        for j in range(nq):
-            s_sel, i_sel = O._topk_desc(table[j, lo:hi], kk)
+        m = q_dev.shape[0]
+        tbl = table if m == nq else np.stack([whole.scores(row) for row in q_dev.numpy()])  # by-id queries
+        D = np.full((m, kk), -np.inf, np.float32)
+        I = np.full((m, kk), -1, np.int64)
+        for j in range(m):
+            s_sel, i_sel = O._topk_desc(tbl[j, lo:hi], kk)
             D[j, : len(s_sel)], I[j, : len(i_sel)] = s_sel, i_sel
         gids = np.where(I >= 0, I + row0, -1)
         out = np.zeros((q_dev.shape[0], kp), np.uint64)
@@ -76,6 +83,13 @@ def _worker(rank: int, world: int, port: int, out_dir: str) -> None:
     Dw = np.stack([O._topk_desc(table[j], k)[0] for j in range(nq)])
     Iw = np.stack([O._topk_desc(table[j], k)[1] for j in range(nq)])
     ok = np.array_equal(I, Iw) and np.allclose(S, Dw, rtol=0, atol=0) and I[0, 0] == 3 and I[0, 1] == 700
+    # image -> image by stored id: the owner is found by a collective, or from the shard bounds without one
+    with_bounds = ShardedIndex(local, lo, local_search=local_search, merge=merge, bounds=bounds)
+    for gid in (0, 700, n - 1, bounds[1]):
+        want = [i for i in O._topk_desc(whole.scores(x[gid]), k + 1)[1].tolist() if i != gid][:k]
+        for handle in (sh, with_bounds):
+            _, got = handle.search_by_id(gid, k)
+            ok = ok and got.tolist() == want
     np.save(os.path.join(out_dir, f"ids_{rank}.npy"), I)
     with open(os.path.join(out_dir, f"ok_{rank}"), "w") as f:
         f.write("1" if ok else "0")
