@@ -98,13 +98,16 @@ class ShardedIndex:
                 ids=t.empty((nq, k), dtype=t.int64, device=self.device),
                 scores_host=t.empty((nq, k), dtype=t.float32, pin_memory=pin),
                 ids_host=t.empty((nq, k), dtype=t.int64, pin_memory=pin),
+                flags=t.zeros((nq,), dtype=t.int32, device=self.device),
+                flags_host=t.zeros((nq,), dtype=t.int32, pin_memory=pin),
             )
         return self._bufs[key]
 
     def search_device(self, q_dev, k: int, flt=None):
         """``q_dev``: float32 ``[nq, d]`` tensor on this rank's device (same on every rank).
         Returns device tensors ``(scores [nq,k], ids [nq,k])`` -- identical on every rank.
-        Everything is enqueued on the current torch stream; no host synchronisation."""
+        Everything is enqueued on the current torch stream; single queries need no host synchronisation,
+        batches of ``BATCH_MIN`` or more read their certificate flags back once."""
         t = self.torch
         nq = int(q_dev.shape[0])
         b = self._buffers(nq, k)
@@ -117,7 +120,11 @@ class ShardedIndex:
                 self.local.search_device(q_dev.data_ptr(), nq, k, b["scores"].data_ptr(), b["ids"].data_ptr(), 0,
                                          flt=flt, id_base=self.row0, stream=stream)
                 return b["scores"], b["ids"]
-            if self.exchange == "p2p":
+            if nq >= self.BATCH_MIN:
+                # query batches: every rank produces its shard's keys (tensor-core GEMM + exact re-score where the
+                # shard qualifies, scans otherwise), ONE all-gather of nq x k keys, one merge CTA per query
+                self._local_batch_keys(q_dev, nq, k, flt, b, stream)
+            elif self.exchange == "p2p":
                 d = self.local.d
                 for qi in range(nq):  # one fused scan+publish / wait+merge pair per query
                     self._seq += 1
@@ -125,8 +132,9 @@ class ShardedIndex:
                                                       self._seq, b["scores"].data_ptr() + qi * k * 4, b["ids"].data_ptr() + qi * k * 8,
                                                       flt=flt, id_base=self.row0, stream=stream)
                 return b["scores"], b["ids"]
-            self.local.search_device(q_dev.data_ptr(), nq, k, 0, 0, b["mine"].data_ptr(), flt=flt,
-                                     id_base=self.row0, stream=stream)
+            else:
+                self.local.search_device(q_dev.data_ptr(), nq, k, 0, 0, b["mine"].data_ptr(), flt=flt,
+                                         id_base=self.row0, stream=stream)
         if self.world > 1:
             self.dist.all_gather_into_tensor(b["gathered"], b["mine"], group=self.group)
             if nq == 1:
@@ -145,6 +153,27 @@ class ShardedIndex:
             _native.merge_keys_device(self.local.device, lists.data_ptr(), nq, self.world, k, self.local.metric,
                                       b["scores"].data_ptr(), b["ids"].data_ptr(), stream)
         return b["scores"], b["ids"]
+
+    BATCH_MIN = 4  # batches of at least this many queries take the all-gather path on every rank
+
+    def _local_batch_keys(self, q_dev, nq: int, k: int, flt, b, stream: int) -> None:
+        """This shard's sorted key lists for a batch into ``b["mine"]``: the tensor-core path
+        (``psx_search_batch_device``) when the shard qualifies, with the unproven queries re-run on the scan
+        (one host synchronisation to read the certificate flags), else one scan per query."""
+        local = self.local
+        mine, d = b["mine"], local.d
+        eligible = (local.metric == _native.METRIC_IP and getattr(local, "store_dtype", 0) != _native.STORE_BF16
+                    and local.ntotal >= 65536 and d >= 32 and k <= 512)
+        if not eligible:
+            local.search_device(q_dev.data_ptr(), nq, k, 0, 0, mine.data_ptr(), flt=flt, id_base=self.row0, stream=stream)
+            return
+        local.search_batch_device(q_dev.data_ptr(), nq, k, b["scores"].data_ptr(), b["ids"].data_ptr(), b["flags"].data_ptr(),
+                                  out_keys_ptr=mine.data_ptr(), id_base=self.row0, stream=stream, flt=flt)
+        b["flags_host"].copy_(b["flags"], non_blocking=True)
+        self.torch.cuda.current_stream(self.device).synchronize()
+        for qi in b["flags_host"].nonzero().flatten().tolist():
+            local.search_device(q_dev.data_ptr() + qi * d * 4, 1, k, 0, 0, mine.data_ptr() + qi * b["kp"] * 8, flt=flt,
+                                id_base=self.row0, stream=stream)
 
     def search_by_id(self, global_id: int, k: int, flt=None, n_total: Optional[int] = None):
         """Image -> image (core/searcher.py:1751-1814): the stored vector of row ``global_id`` is the
