@@ -582,9 +582,36 @@ def run_vector_store_call(index, queries, rows, k):
     for i in range(n):
         hits = store.search(qs[i % 8], k)
     ms = (time.perf_counter() - t0) / n * 1e3
+    out = {"vector_store_search": {"ms_per_call": ms, "qps": 1e3 / ms, "hits": len(hits),
+                                   "note": "drop-in VectorStore.search: list->fp32, normalise, psx_search (H2D, scan, D2H), k result dicts"}}
+    # the threaded server (main.py:353): 16 request threads on the one shared instance, without and with coalescing
+    from photo_search_engine_b200.coalesce import SearchCoalescer
+
+    def hammer(threads=16, per_thread=6):
+        def worker(t):
+            for j in range(per_thread):
+                store.search(qs[(t + j) % 8], k)
+
+        ts = [threading.Thread(target=worker, args=(t,)) for t in range(threads)]
+        t0 = time.perf_counter()
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join()
+        return threads * per_thread / (time.perf_counter() - t0)
+
+    hammer(4, 2)
+    serial_qps = hammer()
+    store._coalescer = SearchCoalescer(store._run_search)
+    hammer(4, 2)
+    coalesced_qps = hammer()
+    out["vector_store_search/16_threads"] = {
+        "qps_serialised": serial_qps, "qps_coalesced": coalesced_qps, "largest_batch": store._coalescer.largest_batch,
+        "note": "concurrent VectorStore.search calls: one after the other (reference behaviour) vs coalesce=True "
+                "(whatever queued while the GPU was busy runs as one batched search; identical results)"}
+    store._coalescer = None
     store.index = None  # the bench owns the index
-    return {"vector_store_search": {"ms_per_call": ms, "qps": 1e3 / ms, "hits": len(hits),
-                                    "note": "drop-in VectorStore.search: list->fp32, normalise, psx_search (H2D, scan, D2H), k result dicts"}}
+    return out
 
 
 def run_config1(torch, _native, device):

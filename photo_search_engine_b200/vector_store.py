@@ -19,7 +19,9 @@ Additive, optional surface (defaults reproduce the reference):
   streamed per query);
 * ``search(..., constraints=None)``: fused pre-filter with the semantics of
   ``Searcher._check_time_match_v2`` (core/searcher.py:1884-1950);
-* ``search_batch`` / ``add_batch``: arrays in, arrays out, no per-hit Python objects.
+* ``search_batch`` / ``add_batch``: arrays in, arrays out, no per-hit Python objects;
+* ``coalesce=True`` (env ``PSX_COALESCE=1``): concurrent ``search`` calls of the threaded server share one
+  batched search while the GPU is busy (``coalesce.py``); same results, no added latency when idle.
 """
 from __future__ import annotations
 
@@ -30,6 +32,7 @@ from typing import Any, Callable, Dict, List, Optional, Sequence, Tuple
 import numpy as np
 
 from . import _native, faiss_io
+from .coalesce import SearchCoalescer
 from .exif_attrs import attr_words, build_filter
 
 _native.load_library()
@@ -87,6 +90,7 @@ class VectorStore:
         *,
         device: Optional[int] = None,
         store_dtype: Optional[str] = None,
+        coalesce: Optional[bool] = None,
     ) -> None:
         # argument handling of utils/vector_store.py:44-62
         metric_name = metric.lower().strip() if metric else "l2"
@@ -118,6 +122,10 @@ class VectorStore:
         self._attrs_built = 0  # rows whose attribute word is already on the device
         self._attr_words = np.zeros(0, np.uint64)  # host copy of those words (persisted by save())
         self.index = self._create_index(dimension) if dimension else None
+        # opt-in: concurrent search() calls (Flask's request threads) share one batched search
+        if coalesce is None:
+            coalesce = os.environ.get("PSX_COALESCE", "0").strip() not in ("", "0", "false", "no")
+        self._coalescer = SearchCoalescer(self._run_search) if coalesce else None
 
     # ------------------------------------------------------------------------------------
     # helpers
@@ -244,11 +252,15 @@ class VectorStore:
         if never:
             return []
         query = np.array([self._normalize_vector(query_embedding)], dtype="float32")
-        distances, labels = self._run_search(query, k, flt)
+        if self._coalescer is not None:
+            row_scores, row_labels = self._coalescer.submit(query[0], k, None if flt is None else bytes(flt), flt)
+        else:
+            distances, labels = self._run_search(query, k, flt)
+            row_scores, row_labels = distances[0], labels[0]
         records = self.metadata
         return [
             {"metadata": records[label], "distance": float(distance)}
-            for distance, label in zip(distances[0].tolist(), labels[0].tolist())
+            for distance, label in zip(row_scores.tolist(), row_labels.tolist())
             if label != -1
         ]
 

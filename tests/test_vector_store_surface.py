@@ -392,3 +392,62 @@ def test_exif_sidecar_round_trip(VS, tmp_path):
     t3 = VS(4, ip, mp)
     assert t3.load() and t3._attrs_built == 0
     assert len(t3.search([1, 0, 0, 0], 6, constraints={"year": 2023})) == 1
+
+
+def test_coalesced_concurrent_searches_equal_sequential(fake_backend, tmp_path, monkeypatch):
+    """coalesce=True: request threads that arrive while a search is running are served by ONE batched backend
+    call; every caller gets exactly what the plain store returns, filters are never mixed in a batch, and a
+    backend failure reaches every waiter of that batch."""
+    import threading
+    import time
+
+    from photo_search_engine_b200.vector_store import VectorStore
+
+    d, n = 16, 300
+    rng = np.random.default_rng(4)
+    rows = rng.standard_normal((n, d)).astype(np.float32)
+    metas = [{"photo_path": f"/p/{i}.jpg", "exif_data": {"datetime": f"20{20 + i % 4}-0{1 + i % 9}-10T10:00:00"},
+              "time_info": {"year": 2020 + i % 4, "month": 1 + i % 9, "season": None, "time_period": None,
+                            "datetime_str": f"20{20 + i % 4}-0{1 + i % 9}-10T10:00:00"}} for i in range(n)]
+    plain = VectorStore(d, str(tmp_path / "a.index"), str(tmp_path / "a.json"))
+    shared = VectorStore(d, str(tmp_path / "b.index"), str(tmp_path / "b.json"), coalesce=True)
+    for store in (plain, shared):
+        store.add_batch(rows, metas)
+    calls = []
+    real = fake_backend.search
+
+    def slow_search(self, q, k, flt=None):
+        calls.append(np.asarray(q).shape[0] if np.asarray(q).ndim == 2 else 1)
+        time.sleep(0.02)  # long enough for the other threads to queue up behind the running search
+        return real(self, q, k, flt)
+
+    monkeypatch.setattr(fake_backend, "search", slow_search)
+    queries = [rng.standard_normal(d).astype(np.float32).tolist() for _ in range(24)]
+    cons = [None, {"year": 2021}, None, {"start_date": "2022-01-01", "end_date": "2023-12-31"}]
+    want = [plain.search(q, 5 + i % 7, constraints=cons[i % 4]) for i, q in enumerate(queries)]
+    calls.clear()
+    got = [None] * len(queries)
+
+    def worker(i):
+        got[i] = shared.search(queries[i], 5 + i % 7, constraints=cons[i % 4])
+
+    threads = [threading.Thread(target=worker, args=(i,)) for i in range(len(queries))]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(30)
+    assert all(not t.is_alive() for t in threads)
+    for g, w in zip(got, want):
+        assert [h["metadata"]["photo_path"] for h in g] == [h["metadata"]["photo_path"] for h in w]
+        assert [h["distance"] for h in g] == [h["distance"] for h in w]
+    co = shared._coalescer
+    assert co.requests == len(queries) and co.batches == len(calls) < len(queries) and co.largest_batch > 1
+    # a failing backend call fails every request of its batch, and the coalescer keeps working afterwards
+    def broken(self, q, k, flt=None):
+        raise RuntimeError("boom")
+
+    monkeypatch.setattr(fake_backend, "search", broken)
+    with pytest.raises(RuntimeError):
+        shared.search(queries[0], 3)
+    monkeypatch.setattr(fake_backend, "search", real)
+    assert len(shared.search(queries[0], 3)) == 3
