@@ -26,7 +26,10 @@ def main():
     ap.add_argument("--steps", type=int, default=6)
     ap.add_argument("--pass-frac", type=float, default=0.0, help="> 0: EXIF window predicate passing this fraction of the rows")
     ap.add_argument("--tunable", action="append", default=[], help="key=value, repeatable")
+    ap.add_argument("--ballast-gb", type=float, default=0.0, help="allocate this much HBM first (placement experiment)")
+    ap.add_argument("--queries", type=int, default=8)
     a = ap.parse_args()
+    ballast = torch.empty(int(a.ballast_gb * (1 << 30)), dtype=torch.uint8, device="cuda") if a.ballast_gb > 0 else None
     dt = _native.STORE_BF16 if a.store == "bf16" else _native.STORE_F32
     esize = 2 if a.store == "bf16" else 4
     ix = _native.NativeIndex(a.dim, 0, dt, 0)
@@ -42,7 +45,7 @@ def main():
         blk /= blk.norm(dim=1, keepdim=True)
         ix.add_device(blk.data_ptr(), m)
         done += m
-    q = torch.randn((8, a.dim), generator=g, device="cuda")
+    q = torch.randn((a.queries, a.dim), generator=g, device="cuda")
     q /= q.norm(dim=1, keepdim=True)
     flt = None
     passing = a.rows
@@ -57,11 +60,11 @@ def main():
     st = torch.cuda.current_stream()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     for i in range(3):
-        ix.search_device(q[i].data_ptr(), 1, a.k, sc.data_ptr(), ids.data_ptr(), 0, flt=flt, stream=st.cuda_stream)
+        ix.search_device(q[i % a.queries].data_ptr(), 1, a.k, sc.data_ptr(), ids.data_ptr(), 0, flt=flt, stream=st.cuda_stream)
     torch.cuda.synchronize()
     e0.record(st)
     for i in range(a.steps):
-        ix.search_device(q[i % 8].data_ptr(), 1, a.k, sc.data_ptr(), ids.data_ptr(), 0, flt=flt, stream=st.cuda_stream)
+        ix.search_device(q[i % a.queries].data_ptr(), 1, a.k, sc.data_ptr(), ids.data_ptr(), 0, flt=flt, stream=st.cuda_stream)
     e1.record(st)
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / a.steps
