@@ -218,7 +218,8 @@ int psx_storage_device(psx_index* h, const void** rows_dev, int64_t* ld_elems, i
  * for 129..256 queries, default 1), "filter_mode" (0 = default, 1 = EXIF predicate evaluated inside
  * the scan, 2 = predicate compacted into a row list that the scan then streams), "deal" (1 = rows
  * dealt to the warps as units with a dynamically scheduled tail, the default; 0 = static groups),
- * "dyn_tail" (0 = deal everything statically), "static_batch" (units per dealt batch, default 8).
+ * "dyn_tail" (0 = deal everything statically), "static_batch" (units per dealt batch, default 8), "pdl"
+ * (1 = back-to-back scans overlap through programmatic dependent launch, the default; 0 = plain stream order).
  * Tunables change launch geometry only, never results. */
 int psx_set_tunable(psx_index* h, const char* key, int value);
 /* Diagnostics: while `trace_dev` is non-NULL every scan launch writes, per CTA, 8 uint64 into

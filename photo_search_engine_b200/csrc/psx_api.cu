@@ -83,7 +83,9 @@ struct psx_index {
 
     uint64_t* lists = nullptr;  // [grid][kpad]
     size_t lists_cap = 0;
-    unsigned int* counter = nullptr;  // [0] merge tickets, [1] dynamic-tail tickets, [2] entries of rowlist
+    unsigned int* counter = nullptr;  // [0] merge tickets, [1] / [3] dynamic-tail tickets of even / odd launches, [2] entries of rowlist
+    unsigned long long scan_seq = 0;  // launches so far (alternates the dynamic-tail ticket word)
+    bool pdl = true;         // back-to-back scans overlap: the next one starts streaming while this one sorts and merges
     uint32_t* rowlist = nullptr;      // [cap] ids of the rows that pass the current query's predicate
     long long rowlist_cap = 0;
     bool deal = true;        // unfiltered scans: dealt units with a dynamic tail (false: static predicate groups)
@@ -338,6 +340,8 @@ static int ensure_capacity(psx_index* h, long long need, bool exact) {
         if (nm) CU(cudaMemcpyAsync(nm, h->xm, (size_t)h->n * h->mrow_bytes, cudaMemcpyDeviceToDevice, h->stream));
     }
     CU(cudaStreamSynchronize(h->stream));
+    // a search enqueued earlier on a caller's stream may still be reading the old arena
+    if (h->has_last) CU(cudaEventSynchronize(h->last_ev));
     cudaFree(h->x);
     cudaFree(h->xm);
     cudaFree(h->attrs);
@@ -484,6 +488,7 @@ extern "C" int psx_set_attrs_device(psx_index* h, int64_t row0, const uint64_t* 
 struct ScanPlan {
     ScanParams p;
     int grid, block, mode;
+    bool pdl;
     size_t smem;
 };
 
@@ -571,7 +576,7 @@ static int plan_scan_with(psx_index* h, bool master, int k, int W, int mode, boo
 }
 
 static int launch_scan_variant(int device, int dtype, int metric, int ppl, bool qreg, const ScanPlan& plan, cudaStream_t st) {
-    const ScanLaunch l{plan.grid, plan.block, plan.smem};
+    const ScanLaunch l{plan.grid, plan.block, plan.smem, plan.pdl};
     cudaError_t e;
     if (dtype == PSX_STORE_F32)
         e = metric == PSX_METRIC_IP ? launch_scan_shape<float, PSX_METRIC_IP>(device, ppl, qreg, plan.mode, plan.p, l, st)
@@ -618,7 +623,11 @@ static int launch_scan(psx_index* h, const float* q_dev, int k, const psx_filter
         p.rowlist = h->rowlist;
     }
     p.list_count = h->counter + 2;
-    p.work = h->counter + 1;
+    p.work = h->counter + ((h->scan_seq++ & 1ull) ? 3 : 1);
+    // the overlap is for back-to-back queries (also behind the merge kernel of a sharded query); launches that consume
+    // what the kernel right before them wrote (a row list, a condition flag, a page ceiling) or that are traced keep
+    // full stream order
+    plan.pdl = h->pdl && !listed && !cond_flag && !ceil_ptr && !h->trace;
     const size_t need_lists = (size_t)plan.grid * p.kpad;
     if (need_lists > h->lists_cap) {
         CU(cudaStreamSynchronize(st));
@@ -1374,6 +1383,8 @@ extern "C" int psx_set_tunable(psx_index* h, const char* key, int value) {
         h->stages_auto = value <= 0;
     } else if (!strcmp(key, "ctas_per_sm")) {
         h->ctas_per_sm = value <= 0 ? 1 : std::min(value, 8);
+    } else if (!strcmp(key, "pdl")) {  // 1 = consecutive scans overlap via programmatic dependent launch (default)
+        h->pdl = value != 0;
     } else if (!strcmp(key, "deal")) {  // unfiltered scans: 1 = dealt units (default), 0 = static groups
         h->deal = value != 0;
     } else if (!strcmp(key, "dyn_tail")) {  // dealt units: 1 = dynamic tail (default), 0 = all static

@@ -78,6 +78,9 @@ merge_wait_kernel(const uint64_t* __restrict__ recv, const uint32_t* flags, int 
                   int metric, float* out_scores, long long* out_ids) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     uint64_t* buf = reinterpret_cast<uint64_t*>(smem_raw);
+    // the next query's scan may start streaming now: it touches nothing this merge reads, and it publishes only
+    // after its own pdl_wait(), i.e. after this kernel has completed
+    pdl_launch_dependents();
     const int slot = (int)(seq & 1u);
     if ((int)threadIdx.x < world) {
         const uint32_t* f = flags + slot * PSX_XCHG_MAX_WORLD + threadIdx.x;
@@ -111,6 +114,7 @@ merge_keys_kernel(const uint64_t* __restrict__ keys, int nlists, int k, int kpad
                   float* out_scores, long long* out_ids) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     uint64_t* buf = reinterpret_cast<uint64_t*>(smem_raw);
+    pdl_launch_dependents();  // see merge_wait_kernel
     const size_t qi = blockIdx.x;
     block_select_from_lists(keys + qi * (size_t)nlists * kpad, nlists, k, kpad, buf, cap_lists * kpad);
     block_emit_results(buf, k, kpad, metric, out_scores + qi * k, out_ids + qi * k, nullptr);

@@ -90,6 +90,15 @@ __device__ __forceinline__ void trace_stamp(unsigned long long* trace, int i) {
     if (trace && threadIdx.x == 0) trace[(size_t)blockIdx.x * 8 + i] = globaltimer_ns();
 }
 
+// Programmatic dependent launch.  A scan launched with programmaticStreamSerialization may become resident
+// while the scan before it is still finishing.  Everything up to the end of the row stream only reads the
+// corpus / the query and uses this launch's own ticket word (two alternate), so it may overlap the previous
+// scan's final sorts; pdl_wait() -- "the previous grid has completed and its writes are visible" -- comes
+// before the first write to the scratch both launches share (candidate lists, merge tickets, outputs), and
+// only then does the CTA let the NEXT launch go, which bounds the overlap to two scans in flight.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ bool attr_pass(uint64_t a, const psx_filter& f) {
     const uint32_t fl = f.flags;
     if (fl & (PSX_F_SEASON | PSX_F_PERIOD | PSX_F_YEAR | PSX_F_MONTH)) {
@@ -633,6 +642,8 @@ __global__ void __launch_bounds__(PSX_MAX_THREADS, 1) scan_topk_kernel(const Sca
         if (!alive) break;
     }
 
+    pdl_wait();
+    pdl_launch_dependents();
     trace_stamp(p.trace, 2);
     if (p.trace && threadIdx.x == 0) p.trace[(size_t)blockIdx.x * 8 + 6] = (unsigned long long)n_compact;
     // ---- publish this CTA's k best -------------------------------------------------------------

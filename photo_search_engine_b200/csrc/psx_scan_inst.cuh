@@ -16,8 +16,17 @@ static cudaError_t launch_scan_one(int device, const ScanParams& p, const ScanLa
         if (e != cudaSuccess) return e;
         ready[device].store(true);
     }
-    scan_topk_kernel<T, METRIC, PPL, QREG, MODE><<<l.grid, l.block, l.smem, st>>>(p);
-    return cudaGetLastError();
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)l.grid);
+    cfg.blockDim = dim3((unsigned)l.block);
+    cfg.dynamicSmemBytes = l.smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = l.pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, scan_topk_kernel<T, METRIC, PPL, QREG, MODE>, p);
 }
 
 template <typename T, int METRIC, int MODE>

@@ -9,6 +9,7 @@ namespace psx {
 struct ScanLaunch {
     int grid, block;
     size_t smem;
+    bool pdl;  // launch with programmatic stream serialization (may start before the previous kernel has drained)
 };
 
 // ppl: 16-byte pieces per lane of a row/chunk when the row shape allows the unrolled dot (0 = generic loop);

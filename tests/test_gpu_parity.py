@@ -403,7 +403,8 @@ def test_determinism_and_tunables():
     ix = make_index(x)
     D0, I0 = ix.search(q, 100)
     for key, val in (("warps", 4), ("stages", 2), ("warps", 16), ("stages", 3), ("ctas_per_sm", 2), ("warps", 8),
-                     ("deal", 0), ("warps", 16), ("deal", 1), ("static_batch", 3), ("dyn_tail", 0), ("static_batch", 32)):
+                     ("deal", 0), ("warps", 16), ("deal", 1), ("static_batch", 3), ("dyn_tail", 0), ("static_batch", 32),
+                     ("pdl", 0), ("pdl", 1)):
         ix.set_tunable(key, val)
         D, I = ix.search(q, 100)
         # same reduction tree per row -> bit-identical scores whatever the launch geometry
@@ -471,6 +472,39 @@ def test_dynamic_tail_and_row_list_geometry(d):
     D, I = ix.search(q, 300, flt)
     assert np.array_equal(I, ref["filtered", 300][1]) and np.array_equal(D, ref["filtered", 300][0])
     ix.close()
+
+
+def test_back_to_back_scans_overlap_safely():
+    """Programmatic dependent launch: scan i+1 starts streaming while scan i sorts and merges.  Many short
+    launches back to back into separate output slots (and, harder, into the SAME slot) must give exactly the
+    results of the same launches in plain stream order."""
+    import torch
+
+    rng = np.random.default_rng(77)
+    for n, d, k in ((3000, 128, 10), (20000, 1024, 100), (300, 64, 300), (150_000, 256, 64)):
+        x = unit_rows(rng, n, d)
+        nq = 48
+        q = torch.from_numpy(unit_rows(rng, nq, d)).cuda()
+        ix = make_index(x)
+        kk = min(k, n)
+        st = torch.cuda.current_stream().cuda_stream
+        res = {}
+        for pdl in (0, 1):
+            ix.set_tunable("pdl", pdl)
+            sc = torch.zeros((nq, kk), device="cuda")
+            ids = torch.zeros((nq, kk), dtype=torch.int64, device="cuda")
+            one_s = torch.zeros((1, kk), device="cuda")
+            one_i = torch.zeros((1, kk), dtype=torch.int64, device="cuda")
+            for rep in range(3):
+                ix.search_device(q.data_ptr(), nq, kk, sc.data_ptr(), ids.data_ptr(), 0, stream=st)  # nq launches back to back
+            for qi in range(nq):  # every launch writes the same slot; the last one must win
+                ix.search_device(q[qi: qi + 1].data_ptr(), 1, kk, one_s.data_ptr(), one_i.data_ptr(), 0, stream=st)
+            torch.cuda.synchronize()
+            res[pdl] = (sc.cpu().numpy(), ids.cpu().numpy(), one_s.cpu().numpy(), one_i.cpu().numpy())
+        for a, b in zip(res[0], res[1]):
+            assert np.array_equal(a, b), (n, d, k)
+        assert np.array_equal(res[1][3][0], res[1][1][nq - 1])
+        ix.close()
 
 
 def test_concurrent_searches_one_handle():

@@ -92,6 +92,10 @@ def main():
             ix.set_tunable("deal", deal)
             us = timed(ix, qs, a.k, a.steps)
             out.setdefault(f"deal={deal}", []).append([round(us, 1), round(rows * a.dim * 4 / us / 1e3)])
+        for pdl in (0, 1, 0, 1):
+            ix.set_tunable("pdl", pdl)
+            us = timed(ix, qs, a.k, a.steps)
+            out.setdefault(f"pdl={pdl}", []).append([round(us, 1), round(rows * a.dim * 4 / us / 1e3)])
         out["trace"] = trace_once(ix, qs[0], a.k)
         print(json.dumps(out), flush=True)
         if a.filters:
