@@ -258,37 +258,45 @@ def run_ours(args):
     barrier()
     clocks = ClockSampler(local_rank).start() if rank == 0 else None
     launches0 = _native.launch_count()
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * args.steps + 2)]
+    # Every EVERY-th scan launch is bracketed by its own pair of events (on the stream it is launched on), so the
+    # kernel's duration is measured live inside the timed region; the launches in between run back to back, as
+    # they do in service (an event record between two kernels also keeps the next scan from starting early).
+    EVERY = 8
+    sampled = [i for i in range(args.steps) if i % EVERY == EVERY - 1] or [args.steps - 1]
+    ev = {i: (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for i in sampled}
+    ev_all = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
     stream = torch.cuda.current_stream()
-    ev[0].record(stream)
+    ev_all[0].record(stream)
     b = sharded._buffers(1, k)
     for i in range(args.steps):
-        # events bracket the scan launch inside each step so the kernel's own duration is measured
-        # live, on the stream it is launched on
         qptr = queries[i % N_QUERIES: i % N_QUERIES + 1].data_ptr()
-        ev[2 * i + 1].record(stream)
+        if i in ev:
+            ev[i][0].record(stream)
         if world == 1:  # the scan's fused merge already emits the final scores / ids
             index.search_device(qptr, 1, k, b["scores"].data_ptr(), b["ids"].data_ptr(), b["mine"].data_ptr(),
                                 id_base=lo, stream=stream.cuda_stream)
-            ev[2 * i + 2].record(stream)
+            if i in ev:
+                ev[i][1].record(stream)
         elif sharded.exchange == "p2p":  # scan publishes its keys into every peer's buffer; wait + merge kernel
             sharded._seq += 1
             index.search_exchange_device(qptr, k, rank, world, sharded._xchg_bases, sharded._seq, 0, 0, id_base=lo,
                                          stream=stream.cuda_stream, phases=1)
-            ev[2 * i + 2].record(stream)
+            if i in ev:
+                ev[i][1].record(stream)
             index.search_exchange_device(0, k, rank, world, sharded._xchg_bases, sharded._seq, b["scores"].data_ptr(),
                                          b["ids"].data_ptr(), stream=stream.cuda_stream, phases=2)
         else:  # keys only, then ONE all-gather and the integer merge on every rank
             index.search_device(qptr, 1, k, 0, 0, b["mine"].data_ptr(), id_base=lo, stream=stream.cuda_stream)
-            ev[2 * i + 2].record(stream)
+            if i in ev:
+                ev[i][1].record(stream)
             dist.all_gather_into_tensor(b["gathered"], b["mine"])
             _native.merge_keys_device(local_rank, b["gathered"].data_ptr(), 1, world, k, _native.METRIC_IP,
                                       b["scores"].data_ptr(), b["ids"].data_ptr(), stream.cuda_stream)
-    ev[-1].record(stream)
+    ev_all[1].record(stream)
     barrier()
     launches = _native.launch_count() - launches0
-    total_ms = ev[0].elapsed_time(ev[-1])
-    scan_ms = sum(ev[2 * i + 1].elapsed_time(ev[2 * i + 2]) for i in range(args.steps)) / args.steps
+    total_ms = ev_all[0].elapsed_time(ev_all[1])
+    scan_ms = sum(a.elapsed_time(z) for a, z in ev.values()) / len(ev)
     t = torch.tensor([total_ms, scan_ms, float(launches)], device=device, dtype=torch.float64)
     if world > 1:
         tmax = t.clone()
@@ -401,7 +409,8 @@ def run_ours(args):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "traffic_source": rec.get("source"),
                          "kernel": "psx::scan_topk_kernel", "algorithmic_bytes_per_launch": algo_bytes,
-                         "kernel_ms": scan_ms, "peak_source": peak_src, "frac_of_8TBps_spec": achieved / 8000.0},
+                         "kernel_ms": scan_ms, "kernel_ms_note": f"CUDA events around every {EVERY}th scan launch of the timed region ({len(ev)} launches)",
+                         "peak_source": peak_src, "frac_of_8TBps_spec": achieved / 8000.0},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_qps, "unit": "queries/s", "h2d_bytes_per_step": world * d * 4, "d2h_bytes_per_step": world * k * 12,
                     "api": "ShardedIndex.search(host query) -> (scores, ids) on host"},
