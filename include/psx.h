@@ -219,7 +219,10 @@ int psx_storage_device(psx_index* h, const void** rows_dev, int64_t* ld_elems, i
  * the scan, 2 = predicate compacted into a row list that the scan then streams), "deal" (1 = rows
  * dealt to the warps as units with a dynamically scheduled tail, the default; 0 = static groups),
  * "dyn_tail" (0 = deal everything statically), "static_batch" (units per dealt batch, default 8), "pdl"
- * (1 = back-to-back scans overlap through programmatic dependent launch, the default; 0 = plain stream order).
+ * (programmatic dependent launch: the next scan starts streaming while the previous one sorts and merges.  0 = plain
+ * stream order; 1 = between the scans of ONE call, the default; 2 = also across calls: only valid when the query of a
+ * call is never written by the kernel enqueued right before that call on its stream -- queries already resident on
+ * the device or delivered by a memcpy).
  * Tunables change launch geometry only, never results. */
 int psx_set_tunable(psx_index* h, const char* key, int value);
 /* Diagnostics: while `trace_dev` is non-NULL every scan launch writes, per CTA, 8 uint64 into

@@ -85,7 +85,13 @@ struct psx_index {
     size_t lists_cap = 0;
     unsigned int* counter = nullptr;  // [0] merge tickets, [1] / [3] dynamic-tail tickets of even / odd launches, [2] entries of rowlist
     unsigned long long scan_seq = 0;  // launches so far (alternates the dynamic-tail ticket word)
-    bool pdl = true;         // back-to-back scans overlap: the next one starts streaming while this one sorts and merges
+    // Programmatic dependent launch of the scans: 0 = never; 1 = the 2nd, 3rd ... scan of ONE API call overlaps its
+    // predecessor (default: the call's first launch is in plain stream order, so whatever produced the queries is
+    // complete and visible before any of the call's kernels starts); 2 = also the first scan of a call -- the caller
+    // guarantees that the query of a call is never written by the kernel enqueued right before the call on that stream
+    // (queries resident on the device, or delivered by a memcpy).
+    int pdl = 1;
+    bool call_first = true;  // no scan launched yet in the current API call
     uint32_t* rowlist = nullptr;      // [cap] ids of the rows that pass the current query's predicate
     long long rowlist_cap = 0;
     bool deal = true;        // unfiltered scans: dealt units with a dynamic tail (false: static predicate groups)
@@ -627,7 +633,8 @@ static int launch_scan(psx_index* h, const float* q_dev, int k, const psx_filter
     // the overlap is for back-to-back queries (also behind the merge kernel of a sharded query); launches that consume
     // what the kernel right before them wrote (a row list, a condition flag, a page ceiling) or that are traced keep
     // full stream order
-    plan.pdl = h->pdl && !listed && !cond_flag && !ceil_ptr && !h->trace;
+    plan.pdl = (h->pdl >= 2 || (h->pdl == 1 && !h->call_first)) && !listed && !cond_flag && !ceil_ptr && !h->trace;
+    h->call_first = false;
     const size_t need_lists = (size_t)plan.grid * p.kpad;
     if (need_lists > h->lists_cap) {
         CU(cudaStreamSynchronize(st));
@@ -973,6 +980,7 @@ static int launch_query(psx_index* h, const float* q_dev, int k, const psx_filte
 
 // scratch is per index: order this search after the previous one if it ran on another stream
 static int enter_stream(psx_index* h, cudaStream_t st) {
+    h->call_first = true;
     if (h->has_last && h->last_stream != st) CU(cudaStreamWaitEvent(st, h->last_ev, 0));
     return PSX_OK;
 }
@@ -1383,8 +1391,8 @@ extern "C" int psx_set_tunable(psx_index* h, const char* key, int value) {
         h->stages_auto = value <= 0;
     } else if (!strcmp(key, "ctas_per_sm")) {
         h->ctas_per_sm = value <= 0 ? 1 : std::min(value, 8);
-    } else if (!strcmp(key, "pdl")) {  // 1 = consecutive scans overlap via programmatic dependent launch (default)
-        h->pdl = value != 0;
+    } else if (!strcmp(key, "pdl")) {  // 0 never, 1 within one call (default), 2 also across calls (see psx_index::pdl)
+        h->pdl = value < 0 ? 1 : std::min(value, 2);
     } else if (!strcmp(key, "deal")) {  // unfiltered scans: 1 = dealt units (default), 0 = static groups
         h->deal = value != 0;
     } else if (!strcmp(key, "dyn_tail")) {  // dealt units: 1 = dynamic tail (default), 0 = all static

@@ -404,7 +404,7 @@ def test_determinism_and_tunables():
     D0, I0 = ix.search(q, 100)
     for key, val in (("warps", 4), ("stages", 2), ("warps", 16), ("stages", 3), ("ctas_per_sm", 2), ("warps", 8),
                      ("deal", 0), ("warps", 16), ("deal", 1), ("static_batch", 3), ("dyn_tail", 0), ("static_batch", 32),
-                     ("pdl", 0), ("pdl", 1)):
+                     ("pdl", 0), ("pdl", 2), ("pdl", 1)):
         ix.set_tunable(key, val)
         D, I = ix.search(q, 100)
         # same reduction tree per row -> bit-identical scores whatever the launch geometry
@@ -489,7 +489,7 @@ def test_back_to_back_scans_overlap_safely():
         kk = min(k, n)
         st = torch.cuda.current_stream().cuda_stream
         res = {}
-        for pdl in (0, 1):
+        for pdl in (0, 1, 2):  # 1: overlap inside one multi-query call; 2: also across calls (queries are resident here)
             ix.set_tunable("pdl", pdl)
             sc = torch.zeros((nq, kk), device="cuda")
             ids = torch.zeros((nq, kk), dtype=torch.int64, device="cuda")
@@ -501,9 +501,10 @@ def test_back_to_back_scans_overlap_safely():
                 ix.search_device(q[qi: qi + 1].data_ptr(), 1, kk, one_s.data_ptr(), one_i.data_ptr(), 0, stream=st)
             torch.cuda.synchronize()
             res[pdl] = (sc.cpu().numpy(), ids.cpu().numpy(), one_s.cpu().numpy(), one_i.cpu().numpy())
-        for a, b in zip(res[0], res[1]):
-            assert np.array_equal(a, b), (n, d, k)
-        assert np.array_equal(res[1][3][0], res[1][1][nq - 1])
+        for level in (1, 2):
+            for a, b in zip(res[0], res[level]):
+                assert np.array_equal(a, b), (n, d, k, level)
+        assert np.array_equal(res[2][3][0], res[2][1][nq - 1])
         ix.close()
 
 

@@ -92,7 +92,7 @@ def main():
             ix.set_tunable("deal", deal)
             us = timed(ix, qs, a.k, a.steps)
             out.setdefault(f"deal={deal}", []).append([round(us, 1), round(rows * a.dim * 4 / us / 1e3)])
-        for pdl in (0, 1, 0, 1):
+        for pdl in (0, 2, 0, 2):  # 2 = overlap also across calls (one query per call here, queries resident)
             ix.set_tunable("pdl", pdl)
             us = timed(ix, qs, a.k, a.steps)
             out.setdefault(f"pdl={pdl}", []).append([round(us, 1), round(rows * a.dim * 4 / us / 1e3)])
