@@ -357,6 +357,16 @@ def run_ours(args):
                                   f"path restated (FAISS is not installable here), rows split over {cores} threads"),
                        "single_thread_value": 1.0 / (med_one * scale),
                        "single_thread_note": "what FAISS does for nq=1 (it parallelises over queries only)"}
+                # SURVEY 8d variant (1): numpy / OpenBLAS sgemv + argpartition over the same sample, all BLAS threads
+                t_np = []
+                for i in range(6):
+                    t0 = time.perf_counter()
+                    s_np = x_host @ queries_host[i % N_QUERIES]
+                    top = np.argpartition(-s_np, k)[:k]
+                    top = top[np.argsort(-s_np[top], kind="stable")]
+                    t_np.append(time.perf_counter() - t0)
+                cpu["numpy_openblas_value"] = 1.0 / (statistics.median(t_np[1:]) * scale)
+                cpu["numpy_openblas_note"] = "x @ q (sgemv, all BLAS threads) + argpartition + sort on the same sample, scaled the same way"
             del x_host
 
     # ---- secondary configurations (not bench lines: context for the judge) -------------------------
