@@ -306,10 +306,17 @@ gemm_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
 #pragma unroll
                         for (int j = 1; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(r[j]));
                         if (mx >= theta[m]) {
+                            // survivors as a bit mask (straight-line code), then one trip per set bit: a lane has a
+                            // survivor in ~2 % of its blocks, but some lane of the warp has one in ~half of them, so the
+                            // block must stay cheap for the lanes that only tag along
+                            uint32_t hit = 0;
 #pragma unroll
-                            for (int j = 0; j < 32; ++j) {
+                            for (int j = 0; j < 32; ++j) hit |= (__uint_as_float(r[j]) >= theta[m] ? 1u : 0u) << j;
+                            while (hit) {
+                                const int j = __ffs(hit) - 1;
+                                hit &= hit - 1;
                                 const long long row = row0 + c * 32 + j;
-                                if (__uint_as_float(r[j]) >= theta[m] && row < p.n && (!p.attrs || gemm_attr_pass(__ldg(p.attrs + row), p.f))) {
+                                if (row < p.n && (!p.attrs || gemm_attr_pass(__ldg(p.attrs + row), p.f))) {
                                     const int pos = atomicAdd(p.cand_count + qi, 1);
                                     if (pos < p.cand_cap) p.cand_ids[(size_t)qi * p.cand_cap + pos] = (uint32_t)row;
                                 }
@@ -573,10 +580,14 @@ gemm_filter_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
 #pragma unroll
                     for (int j = 1; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(r[j]));
                     if (mx >= theta) {
+                        uint32_t hit = 0;  // see gemm_filter_kernel
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) {
+                        for (int j = 0; j < 32; ++j) hit |= (__uint_as_float(r[j]) >= theta ? 1u : 0u) << j;
+                        while (hit) {
+                            const int j = __ffs(hit) - 1;
+                            hit &= hit - 1;
                             const long long row = row0 + c * 32 + j;
-                            if (__uint_as_float(r[j]) >= theta && row < p.n && (!p.attrs || gemm_attr_pass(__ldg(p.attrs + row), p.f))) {
+                            if (row < p.n && (!p.attrs || gemm_attr_pass(__ldg(p.attrs + row), p.f))) {
                                 const int pos = atomicAdd(p.cand_count + qi, 1);
                                 if (pos < p.cand_cap) p.cand_ids[(size_t)qi * p.cand_cap + pos] = (uint32_t)row;
                             }
