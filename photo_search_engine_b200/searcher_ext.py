@@ -48,6 +48,11 @@ class _PrefetchingStore:
         setattr(self._store, name, value)
 
     def search(self, query_embedding: List[float], top_k: int, *args: Any, **kwargs: Any) -> List[Dict]:
+        # FusedPrefilterMixin: the round's EXIF constraints ride along, so that the scan itself only considers
+        # rows passing Searcher._check_time_match_v2 (core/searcher.py:1884-1950)
+        fused = getattr(self._local, "constraints", None)
+        if fused and not args and "constraints" not in kwargs:
+            return self._store.search(query_embedding, top_k, constraints=fused)
         prefetched = getattr(self._local, "prefetch", None)
         if prefetched and not args and not kwargs and query_embedding is not None:
             got = prefetched.get(_embedding_key(query_embedding))
@@ -88,11 +93,13 @@ class BatchedExpansionMixin:
 
     def __init__(self, *args: Any, **kwargs: Any) -> None:
         super().__init__(*args, **kwargs)
-        self._psx_local = threading.local()
+        if not hasattr(self, "_psx_local"):
+            self._psx_local = threading.local()
         self.psx_batch_stats = {"batches": 0, "batched_queries": 0, "served_from_batch": 0}
         if getattr(self, "query_formatter", None) is not None:
             self.query_formatter = _PrefetchingFormatter(self.query_formatter, self)
-        self.vector_store = _PrefetchingStore(self.vector_store, self._psx_local)
+        if not isinstance(self.vector_store, _PrefetchingStore):
+            self.vector_store = _PrefetchingStore(self.vector_store, self._psx_local)
 
     # -- request scope ---------------------------------------------------------------------------
     def _maybe_expand_query_results(self, *, query, base_intent, normalized_top_k, has_filter, **kwargs):
@@ -191,3 +198,34 @@ class BatchedExpansionMixin:
             # batching is an optimisation: on any surprise the unmodified loop simply runs unbatched
             local.prefetch = {}
             local.embeddings = {}
+
+
+class FusedPrefilterMixin:
+    """Opt-in: hand the round's EXIF constraints to the vector store so that the predicate
+    runs on the device BEFORE the top-k selection.  The reference post-filters the top ``candidate_k`` hits
+    (core/searcher.py:1477-1480) and can come back with fewer than ``top_k`` photos although more match; with
+    the pre-filter the k best *matching* rows are recalled.  This changes results (strictly more complete for
+    filtered queries), hence a separate opt-in::
+
+        class MySearcher(FusedPrefilterMixin, Searcher): ...
+
+    Only the pure vector branch is affected (``keyword_store is None``: the branch in which the reference applies
+    ``_check_time_match_v2`` itself); with Elasticsearch the filter already runs there.  The reference's own
+    post-filter still runs afterwards and is a no-op on rows that passed.  May be combined with
+    ``BatchedExpansionMixin`` (list this one first); expansion rounds under a predicate then search unbatched.
+    """
+
+    def __init__(self, *args: Any, **kwargs: Any) -> None:
+        super().__init__(*args, **kwargs)
+        if not hasattr(self, "_psx_local"):
+            self._psx_local = threading.local()
+        if not isinstance(self.vector_store, _PrefetchingStore):
+            self.vector_store = _PrefetchingStore(self.vector_store, self._psx_local)
+
+    def _run_single_search_round(self, *, constraints, has_filter, **kwargs):
+        use = bool(has_filter) and bool(constraints) and self.keyword_store is None
+        self._psx_local.constraints = dict(constraints) if use else None
+        try:
+            return super()._run_single_search_round(constraints=constraints, has_filter=has_filter, **kwargs)
+        finally:
+            self._psx_local.constraints = None

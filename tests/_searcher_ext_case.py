@@ -14,7 +14,7 @@ import ref_inject_plugin  # noqa: F401  (installs utils.vector_store -> the drop
 from core.searcher import Searcher  # the reference, unmodified
 from tests.helpers import FakeQueryFormatter, FakeTimeParser  # the reference's own fakes
 
-from photo_search_engine_b200.searcher_ext import BatchedExpansionMixin
+from photo_search_engine_b200.searcher_ext import BatchedExpansionMixin, FusedPrefilterMixin
 from photo_search_engine_b200.vector_store import VectorStore
 
 D = 16
@@ -57,6 +57,46 @@ class CountingStore(VectorStore):
 
 class BatchedSearcher(BatchedExpansionMixin, Searcher):
     pass
+
+
+class PrefilterSearcher(FusedPrefilterMixin, BatchedExpansionMixin, Searcher):
+    pass
+
+
+def prefilter_case(tmp):
+    """A year filter that only 1 photo in 12 passes: the reference recalls candidate_k hits and post-filters them,
+    the fused pre-filter recalls the best *passing* rows."""
+    out = {}
+    rng = np.random.default_rng(11)
+    rows = rng.standard_normal((600, D)).astype(np.float32)
+    metas = []
+    for i in range(600):
+        year = 2019 if i % 12 == 0 else 2021
+        stamp = f"{year}-06-15T12:00:00"
+        metas.append({"photo_path": f"/photos/{i}.jpg", "description": f"photo {i}", "exif_data": {"datetime": stamp},
+                      "time_info": {"year": year, "month": 6, "season": "夏天", "time_period": "中午", "datetime_str": stamp}})
+    constraints = {"start_date": "2019-01-01", "end_date": "2019-12-31", "precision": "year"}
+    qvec = rng.standard_normal(D).astype(np.float32).tolist()
+    for tag, cls in (("plain", Searcher), ("prefilter", PrefilterSearcher)):
+        store = CountingStore(D, os.path.join(tmp, tag + "_pf.index"), os.path.join(tmp, tag + "_pf.json"))
+        for r, m in zip(rows, metas):
+            store.add_item(r.tolist(), m)
+        emb = CountingEmbedding()
+        emb._vec = lambda text: list(qvec)
+        s = cls(embedding=emb, time_parser=FakeTimeParser(), vector_store=store, keyword_store=None, query_formatter=None)
+        s.index_loaded = True
+        res = s._run_single_search_round(query="q", intent={"search_text": "q"}, embedding_query="q", media_terms=[],
+                                         identity_terms=[], strict_identity_filter=False, constraints=constraints,
+                                         normalized_top_k=10, has_filter=True)
+        out[tag] = [[r["photo_path"], r.get("score")] for r in res]
+    # ground truth: the 10 best rows of year 2019 by cosine
+    unit = rows / np.linalg.norm(rows, axis=1, keepdims=True)
+    qn = np.asarray(qvec, np.float32) / np.linalg.norm(qvec)
+    s_all = unit @ qn
+    passing = [i for i in range(600) if i % 12 == 0]
+    best = sorted(passing, key=lambda i: -s_all[i])[:10]
+    out["truth"] = [f"/photos/{i}.jpg" for i in best]
+    return out
 
 
 def alt(text, terms=()):
@@ -104,6 +144,7 @@ def main():
                         "after_direct": after_direct, "total": (store.n_search, store.n_batch, emb.single, emb.batch),
                         "stats": getattr(s, "psx_batch_stats", None),
                         "expansion_triggered_full": bool(s._last_search_debug.get("expansion_triggered"))}
+        out["prefilter_case"] = prefilter_case(tmp)
     print("RESULT " + json.dumps(out))
 
 

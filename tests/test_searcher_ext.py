@@ -38,6 +38,15 @@ def _check(out):
     assert batched["stats"]["batches"] >= 1 and batched["stats"]["batched_queries"] >= 3
     assert batched["stats"]["served_from_batch"] >= 4
     assert plain["expansion_triggered_full"] == batched["expansion_triggered_full"]
+    # FusedPrefilterMixin: every returned photo passes the filter in both variants; the pre-filtered recall contains
+    # every passing photo the reference found, finds the true 10 best passing rows, and is never smaller
+    pf = out["prefilter_case"]
+    truth = pf["truth"]
+    got_plain = [p for p, _ in pf["plain"]]
+    got_pre = [p for p, _ in pf["prefilter"]]
+    assert set(got_plain) <= set(truth) | set(got_pre)
+    assert set(got_pre) == set(truth) and len(got_pre) == 10
+    assert len(got_plain) <= len(got_pre)
 
 
 @pytest.mark.skipif(not os.path.isdir(os.path.join(REFERENCE, "core")), reason="reference checkout not present")
