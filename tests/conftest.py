@@ -17,7 +17,17 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 GOLDEN = os.path.join(ROOT, "tests", "golden")
-REFERENCE = os.environ.get("PSX_REFERENCE", "/root/reference")
+
+
+def _locate_reference() -> str:
+    """The reference checkout (build container), else the unmodified copy of its hot-path suites that
+    ``__graft_entry__.build()`` staged under oracle/_ref/ (git-ignored, travels to the GPU box)."""
+    from oracle.stage_reference import DEFAULT_SOURCE, locate
+
+    return locate() or DEFAULT_SOURCE
+
+
+REFERENCE = _locate_reference()
 
 
 def pytest_configure(config):

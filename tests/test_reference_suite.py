@@ -1,7 +1,9 @@
 """Run the reference's own, unmodified hot-path test files against the drop-in class.
 
-Only possible where the reference checkout exists (the build container); on the GPU box the
-same cases run as restated tests in test_gpu_vector_store.py.
+In the build container they run from the checkout (/root/reference); on the GPU box from the
+unmodified copy that ``__graft_entry__.build()`` staged under oracle/_ref/reference_suite/ (git-ignored,
+see oracle/stage_reference.py).  ``test_staged_reference_suite_is_unmodified`` pins the staged files to
+the committed SHA-256 digests.
 """
 from __future__ import annotations
 
@@ -26,6 +28,21 @@ def _run(backend: str):
     return subprocess.run(cmd, cwd=tempfile.gettempdir(), env=env, capture_output=True, text=True, timeout=900)
 
 
+def test_staged_reference_suite_is_unmodified():
+    """What travels to the GPU box is byte-identical to the reference's files (digests committed under
+    tests/golden/; regenerate with ``python -m oracle.stage_reference`` if the reference ever changes)."""
+    from oracle import stage_reference as sr
+
+    folder = sr.stage()
+    if folder is None:
+        pytest.skip("neither a reference checkout nor a staged copy is present")
+    pinned = sr.pinned_manifest()
+    assert sorted(pinned) == sorted(sr.FILES)
+    assert sr.manifest_of(folder) == pinned
+    if os.path.isdir(os.path.join(sr.DEFAULT_SOURCE, "tests")):
+        assert sr.manifest_of(sr.DEFAULT_SOURCE) == pinned
+
+
 @pytest.mark.skipif(not os.path.isdir(os.path.join(REFERENCE, "tests")), reason="reference checkout not present")
 def test_reference_tests_pass_on_host_logic():
     proc = _run("fake")
@@ -40,4 +57,6 @@ def test_reference_tests_pass_on_gpu():
     if not has_gpu():
         pytest.skip("no GPU")
     proc = _run("gpu")
-    assert proc.returncode == 0, (proc.stdout + proc.stderr)[-3000:]
+    tail = (proc.stdout + proc.stderr)[-3000:]
+    assert proc.returncode == 0, tail
+    assert "52 passed" in proc.stdout, tail
