@@ -59,6 +59,21 @@ def parse_args():
     return ap.parse_args()
 
 
+def workload_name(rows, d, k, store="fp32"):
+    """ONE spelling of the workload for both arms (the driver compares the strings)."""
+    return f"{rows}x{d} {store} flat-IP top-{k}, nq=1 (BASELINE.json configs[3]; the metric's own shape)"
+
+
+def mem_available_bytes():
+    try:
+        for line in open("/proc/meminfo"):
+            if line.startswith("MemAvailable:"):
+                return int(line.split()[1]) * 1024
+    except Exception:
+        pass
+    return 0
+
+
 def measured_peak():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -144,42 +159,55 @@ def cpu_time_queries(x, queries, k, nthreads, budget_s, max_queries):
 
 
 def run_reference(args):
-    """--impl reference: rank 0 only; bounded sample, scaled linearly to the full row count."""
+    """--impl reference: rank 0 only.  The reference's algorithm (oracle/flat_scan.c) on the host cores, thread
+    count pinned explicitly (never taken from OMP_NUM_THREADS).  A step is one query over the rows that fit: the
+    whole corpus when the host has the RAM for it (41 GB at 10M x 1024), else the largest sample that does --
+    ms_per_step is always the MEASURED time of such a step, the row scale is stated in config."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     from oracle import c_oracle
 
-    cores = c_oracle.max_threads()
+    cores = c_oracle.host_cores()
+    c_oracle.set_threads(cores)
     rows, d, k = args.rows, args.dim, args.k
-    # calibrate the sample so that (steps + warmup) queries end within ~2 minutes
-    probe = c_oracle.fill_unit_rows(1 << 17, d, CORPUS_SEED)
     q = c_oracle.fill_unit_rows(N_QUERIES, d, QUERY_SEED)
-    t = min(cpu_time_queries(probe, q, k, cores, 1.0, 5))
-    per_row = t / probe.shape[0]
-    budget = 120.0
-    sample_rows = int(min(rows, max(1 << 17, budget / max(per_row * (args.steps + args.warmup), 1e-12))))
-    sample_rows = min(sample_rows, 1 << 21)  # <= 8 GB of host memory at d=1024
+    # rows that fit the host: leave 6 GB of head room; and keep (steps + warmup) queries within ~2.5 minutes
+    probe = c_oracle.fill_unit_rows(1 << 17, d, CORPUS_SEED)
+    per_row = min(cpu_time_queries(probe, q, k, cores, 1.0, 5)) / probe.shape[0]
+    del probe
+    by_ram = max(1 << 17, (mem_available_bytes() - (6 << 30)) // (d * 4))
+    by_time = int(150.0 / max(per_row * (args.steps + max(args.warmup, 1) + 3), 1e-12))
+    sample_rows = int(max(1 << 17, min(rows, by_ram, by_time)))
     x = c_oracle.fill_unit_rows(sample_rows, d, CORPUS_SEED)
+    scale = rows / sample_rows
     for i in range(args.warmup):
         c_oracle.search(x, q[i % N_QUERIES][None], k, nthreads=cores)
     t0 = time.perf_counter()
     for i in range(args.steps):
         c_oracle.search(x, q[i % N_QUERIES][None], k, nthreads=cores)
     elapsed = time.perf_counter() - t0
-    ms_sample = elapsed / args.steps * 1e3
-    ms_full = ms_sample * rows / sample_rows
-    qps = 1e3 / ms_full
-    sample = (f"{sample_rows} of {rows} rows x {d} fp32 per step (host RAM / time bound), time scaled linearly x"
-              f"{rows / sample_rows:.2f}; C restatement of FAISS IndexFlatIP small-batch path (AVX dot + heap), rows split over "
-              f"{cores} OpenMP threads (FAISS itself would use 1 thread for nq=1)")
+    ms_step = elapsed / args.steps * 1e3          # measured: one query over sample_rows rows
+    qps = 1e3 / (ms_step * scale)                 # the metric: queries/s over the full corpus
+    # FAISS itself runs nq=1 on ONE thread (it parallelises over queries): time that too, on a slice
+    one_rows = min(sample_rows, 1 << 20)
+    t_one = statistics.median(cpu_time_queries(x[:one_rows], q, k, 1, 6.0, 4))
+    qps_one = 1.0 / (t_one * rows / one_rows)
+    sample = (f"{sample_rows} of {rows} rows x {d} fp32 per step"
+              + ("" if sample_rows == rows else f" (host RAM / time bound; value = measured step time x {scale:.3f})")
+              + f"; C restatement of FAISS IndexFlatIP small-batch path (AVX dot + heap), rows split over {cores} OpenMP "
+                f"threads pinned with omp_set_num_threads (OMP_NUM_THREADS={os.environ.get('OMP_NUM_THREADS', 'unset')} ignored)")
     line = {
         "impl": "reference", "metric": METRIC, "value": qps, "unit": "queries/s", "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms_full, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{rows}x{d} fp32 flat-IP top-{k}, nq=1", "rows": rows, "dim": d, "k": k,
-                   "scanned_GBps": rows * d * 4 / (ms_full * 1e-3) / 1e9},
-        "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": cores, "kind": "port", "sample": sample},
+        "config": {"workload": workload_name(rows, d, k), "rows": rows, "dim": d, "k": k,
+                   "rows_per_step": sample_rows, "row_scale": scale,
+                   "ms_per_query_full_corpus": ms_step * scale,
+                   "scanned_GBps": sample_rows * d * 4 / (ms_step * 1e-3) / 1e9},
+        "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": cores, "kind": "port", "sample": sample,
+                         "single_thread_value": qps_one,
+                         "single_thread_note": f"1 thread, what FAISS does for nq=1; measured on {one_rows} rows, scaled linearly"},
         "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -240,10 +268,9 @@ def run_ours(args):
         if val:
             index.set_tunable(key, val)
     build_corpus(torch, index, lo, hi - lo, d, device)
-    # the timed loops below issue one query per call from queries that are resident on the device: consecutive scans
-    # may overlap (include/psx.h, tunable "pdl" = 2).  The end-to-end loop copies every query from the host first, so
-    # nothing overlaps there.
-    index.set_tunable("pdl", 2)
+    # The headline runs with the library's DEFAULT launch policy (tunable "pdl" = 1: consecutive calls are in plain
+    # stream order).  "pdl" = 2 lets scan i+1 start streaming while scan i sorts/merges; it is only valid for callers
+    # whose queries are already resident on the device, so it is reported beside the headline, not as the headline.
     sharded = ShardedIndex(index, lo, exchange=args.exchange)
     queries = make_queries(torch, N_QUERIES, d, device)
     queries_host = queries.cpu().numpy()
@@ -256,51 +283,55 @@ def run_ours(args):
     def step_device(i):
         return sharded.search_device(queries[i % N_QUERIES: i % N_QUERIES + 1], k)
 
+    stream = torch.cuda.current_stream()
+    b = sharded._buffers(1, k)
+
+    def timed_loop(steps, every):
+        """`steps` back-to-back queries; every `every`-th scan launch is bracketed by its own pair of events (on the
+        stream it is launched on), so the kernel's duration is measured live inside the timed region.  Returns
+        (total ms, mean bracketed scan ms, number of bracketed launches)."""
+        sampled = [i for i in range(steps) if i % every == every - 1] or [steps - 1]
+        ev = {i: (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for i in sampled}
+        ev_all = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        ev_all[0].record(stream)
+        for i in range(steps):
+            qptr = queries[i % N_QUERIES: i % N_QUERIES + 1].data_ptr()
+            if i in ev:
+                ev[i][0].record(stream)
+            if world == 1:  # the scan's fused merge already emits the final scores / ids
+                index.search_device(qptr, 1, k, b["scores"].data_ptr(), b["ids"].data_ptr(), b["mine"].data_ptr(),
+                                    id_base=lo, stream=stream.cuda_stream)
+                if i in ev:
+                    ev[i][1].record(stream)
+            elif sharded.exchange == "p2p":  # scan publishes its keys into every peer's buffer; wait + merge kernel
+                sharded._seq += 1
+                index.search_exchange_device(qptr, k, rank, world, sharded._xchg_bases, sharded._seq, 0, 0, id_base=lo,
+                                             stream=stream.cuda_stream, phases=1)
+                if i in ev:
+                    ev[i][1].record(stream)
+                index.search_exchange_device(0, k, rank, world, sharded._xchg_bases, sharded._seq, b["scores"].data_ptr(),
+                                             b["ids"].data_ptr(), stream=stream.cuda_stream, phases=2)
+            else:  # keys only, then ONE all-gather and the integer merge on every rank
+                index.search_device(qptr, 1, k, 0, 0, b["mine"].data_ptr(), id_base=lo, stream=stream.cuda_stream)
+                if i in ev:
+                    ev[i][1].record(stream)
+                dist.all_gather_into_tensor(b["gathered"], b["mine"])
+                _native.merge_keys_device(local_rank, b["gathered"].data_ptr(), 1, world, k, _native.METRIC_IP,
+                                          b["scores"].data_ptr(), b["ids"].data_ptr(), stream.cuda_stream)
+        ev_all[1].record(stream)
+        barrier()
+        return ev_all[0].elapsed_time(ev_all[1]), sum(a.elapsed_time(z) for a, z in ev.values()) / len(ev), len(ev)
+
     # ---- device-resident timing ------------------------------------------------------------
     for i in range(max(args.warmup, 3)):
         step_device(i)
     barrier()
     clocks = ClockSampler(local_rank).start() if rank == 0 else None
     launches0 = _native.launch_count()
-    # Every EVERY-th scan launch is bracketed by its own pair of events (on the stream it is launched on), so the
-    # kernel's duration is measured live inside the timed region; the launches in between run back to back, as
-    # they do in service (an event record between two kernels also keeps the next scan from starting early).
-    EVERY = 8
-    sampled = [i for i in range(args.steps) if i % EVERY == EVERY - 1] or [args.steps - 1]
-    ev = {i: (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for i in sampled}
-    ev_all = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-    stream = torch.cuda.current_stream()
-    ev_all[0].record(stream)
-    b = sharded._buffers(1, k)
-    for i in range(args.steps):
-        qptr = queries[i % N_QUERIES: i % N_QUERIES + 1].data_ptr()
-        if i in ev:
-            ev[i][0].record(stream)
-        if world == 1:  # the scan's fused merge already emits the final scores / ids
-            index.search_device(qptr, 1, k, b["scores"].data_ptr(), b["ids"].data_ptr(), b["mine"].data_ptr(),
-                                id_base=lo, stream=stream.cuda_stream)
-            if i in ev:
-                ev[i][1].record(stream)
-        elif sharded.exchange == "p2p":  # scan publishes its keys into every peer's buffer; wait + merge kernel
-            sharded._seq += 1
-            index.search_exchange_device(qptr, k, rank, world, sharded._xchg_bases, sharded._seq, 0, 0, id_base=lo,
-                                         stream=stream.cuda_stream, phases=1)
-            if i in ev:
-                ev[i][1].record(stream)
-            index.search_exchange_device(0, k, rank, world, sharded._xchg_bases, sharded._seq, b["scores"].data_ptr(),
-                                         b["ids"].data_ptr(), stream=stream.cuda_stream, phases=2)
-        else:  # keys only, then ONE all-gather and the integer merge on every rank
-            index.search_device(qptr, 1, k, 0, 0, b["mine"].data_ptr(), id_base=lo, stream=stream.cuda_stream)
-            if i in ev:
-                ev[i][1].record(stream)
-            dist.all_gather_into_tensor(b["gathered"], b["mine"])
-            _native.merge_keys_device(local_rank, b["gathered"].data_ptr(), 1, world, k, _native.METRIC_IP,
-                                      b["scores"].data_ptr(), b["ids"].data_ptr(), stream.cuda_stream)
-    ev_all[1].record(stream)
-    barrier()
+    # short runs (the driver passes --steps 20) bracket every other launch so that >= 8 launches are sampled
+    EVERY = 8 if args.steps >= 80 else 2
+    total_ms, scan_ms, n_bracketed = timed_loop(args.steps, EVERY)
     launches = _native.launch_count() - launches0
-    total_ms = ev_all[0].elapsed_time(ev_all[1])
-    scan_ms = sum(a.elapsed_time(z) for a, z in ev.values()) / len(ev)
     t = torch.tensor([total_ms, scan_ms, float(launches)], device=device, dtype=torch.float64)
     if world > 1:
         tmax = t.clone()
@@ -311,14 +342,33 @@ def run_ours(args):
     clock_info = clocks.stop() if clocks else None
     ms_per_step = total_ms / args.steps
     qps = 1e3 / ms_per_step
-
-    # ---- end to end through the host-buffer API ----------------------------------------------
+    # same loop with the overlap tunable (resident queries): context, not the headline
+    index.set_tunable("pdl", 2)
     for i in range(3):
-        sharded.search(queries_host[i], k)
+        step_device(i)
+    barrier()
+    ov_ms, _, _ = timed_loop(args.steps, args.steps + 1)
+    index.set_tunable("pdl", 1)
+    tov = torch.tensor([ov_ms], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tov, op=dist.ReduceOp.MAX)
+    qps_overlap = args.steps / float(tov[0]) * 1e3
+
+    # ---- end to end through the reference-facing host-buffer call ------------------------------------
+    # N=1: psx_search itself (what VectorStore.search calls: pageable host query in, host scores/ids out);
+    # N>1: ShardedIndex.search on every rank (pinned H2D of the query, fused exchange, D2H of the merged result)
+    if world == 1:
+        e2e_call = lambda i: index.search(queries_host[i % N_QUERIES], k)  # noqa: E731
+        e2e_api = "psx_search (C ABI, host query -> host scores/ids) via NativeIndex.search"
+    else:
+        e2e_call = lambda i: sharded.search(queries_host[i % N_QUERIES], k)  # noqa: E731
+        e2e_api = "ShardedIndex.search(host query) -> (scores, ids) on host, every rank"
+    for i in range(3):
+        e2e_call(i)
     barrier()
     t0 = time.perf_counter()
     for i in range(args.steps):
-        S_e2e, I_e2e = sharded.search(queries_host[i % N_QUERIES], k)
+        S_e2e, I_e2e = e2e_call(i)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     te = torch.tensor([e2e_s], device=device, dtype=torch.float64)
@@ -326,37 +376,69 @@ def run_ours(args):
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_qps = args.steps / float(te[0])
 
-    # ---- parity spot check at every N: the sharded GPU result, restricted by a fused row-range
-    # predicate to the first `sample_rows` rows, must equal the CPU oracle on those rows ----------
+    # ---- parity spot check at every N.  A fused predicate selects every P-th GLOBAL row (dt word = 1 + row % P,
+    # filter dt <= 1), i.e. a stripe of EVERY shard; the selected rows are read back from the index' own HBM arena,
+    # gathered to rank 0 and searched by the CPU oracle.  The sharded GPU result must equal it. ----------------------
     cpu = None
     parity = None
-    sample_rows = min(rows, 1 << 20, bounds[1])
     if args.store == "fp32" and not args.no_cpu_baseline:
-        words = torch.arange(lo, hi, device=device, dtype=torch.int64) + 1  # dt = 1 + global row
+        P = max(1, -(-rows // (1 << 20)))
+        words = torch.arange(lo, hi, device=device, dtype=torch.int64) % P + 1
         index.set_attrs_device(0, words.data_ptr(), hi - lo, stream=torch.cuda.current_stream().cuda_stream)
         del words
-        flt = _native.PsxFilter(flags=_native.F_NEED_DT | _native.F_END, end=sample_rows)
-        Dg, Ig = sharded.search(queries_host[:4], k, flt)
+        flt = _native.PsxFilter(flags=_native.F_NEED_DT | _native.F_END, end=1)
+        NQ_CHECK = 4
+        Dg, Ig = sharded.search(queries_host[:NQ_CHECK], k, flt)
+        # the stored bits of the selected rows, straight from the arena (zero-copy view of the index' device memory)
+        ptr, ld, _dt = index.storage_device()
+
+        class _Arena:
+            __cuda_array_interface__ = {"shape": (hi - lo, ld), "typestr": "<f4", "data": (ptr, True), "version": 2}
+
+        arena = torch.as_tensor(_Arena(), device=device)
+        first = -(-lo // P) * P
+        sel = torch.arange(first, hi, P, device=device, dtype=torch.int64)
+        per_rank = -(-(-(-rows // P)) // world) + 1
+        mine = torch.zeros((per_rank, d), device=device)
+        mine_ids = torch.full((per_rank,), -1, device=device, dtype=torch.int64)
+        mine[: sel.numel()] = arena[sel - lo, :d]
+        mine_ids[: sel.numel()] = sel
+        if world > 1:
+            rows_all = [torch.empty_like(mine) for _ in range(world)] if rank == 0 else None
+            ids_all = [torch.empty_like(mine_ids) for _ in range(world)] if rank == 0 else None
+            dist.gather(mine, rows_all, dst=0)
+            dist.gather(mine_ids, ids_all, dst=0)
+        else:
+            rows_all, ids_all = [mine], [mine_ids]
         if rank == 0:
             from oracle import c_oracle
 
-            cores = c_oracle.max_threads()
-            x_host = index.read_rows(0, sample_rows)
-            Dc, Ic = c_oracle.search(x_host, queries_host[:4], k, nthreads=cores)
-            parity = {"rows": sample_rows, "queries": 4, "ids_equal_frac": float((Ig == Ic).mean()),
-                      "max_rel_score_err": float(np.max(np.abs(Dg - Dc) / np.maximum(np.abs(Dc), 1e-6)))}
-            # ---- CPU baseline beside it (rank 0, N=1 only): a bounded sample of the same rows -------
+            cores = c_oracle.host_cores()
+            c_oracle.set_threads(cores)
+            gids = torch.cat(ids_all).cpu().numpy()
+            keep = gids >= 0
+            x_host = torch.cat(rows_all).cpu().numpy()[keep]
+            gids = gids[keep]
+            sample_rows = int(x_host.shape[0])
+            Dc, Ic = c_oracle.search(x_host, queries_host[:NQ_CHECK], k, nthreads=cores)
+            Ic = np.where(Ic >= 0, gids[np.clip(Ic, 0, None)], -1)
+            shards_hit = sorted({int(np.searchsorted(np.asarray(bounds[1:]), g, side="right")) for g in Ig.ravel() if g >= 0})
+            parity = {"rows": sample_rows, "row_stride": P, "queries": NQ_CHECK, "ids_equal_frac": float((Ig == Ic).mean()),
+                      "max_rel_score_err": float(np.max(np.abs(Dg - Dc) / np.maximum(np.abs(Dc), 1e-6))),
+                      "shards_contributing_to_result": shards_hit, "n_shards": world,
+                      "note": "every P-th global row (a stripe of every shard), stored bits read back from HBM, CPU oracle on rank 0"}
+            # ---- CPU baseline beside it (rank 0, every N): a bounded sample of the same rows, threads pinned -------
+            times_all = cpu_time_queries(x_host, queries_host, k, cores, 10.0, 40)
+            times_one = cpu_time_queries(x_host, queries_host, k, 1, 6.0, 6)
+            scale = rows / sample_rows
+            med_all, med_one = statistics.median(times_all), statistics.median(times_one)
+            cpu = {"value": 1.0 / (med_all * scale), "unit": "queries/s", "cores": cores, "kind": "port",
+                   "sample": (f"{sample_rows} of {rows} rows (every {P}-th row, same bits as the GPU corpus), {len(times_all)} queries, "
+                              f"median, time scaled linearly x{scale:.2f}; oracle/flat_scan.c = FAISS IndexFlatIP small-batch "
+                              f"path restated (FAISS is not installable here), rows split over {cores} pinned threads"),
+                   "single_thread_value": 1.0 / (med_one * scale),
+                   "single_thread_note": "what FAISS does for nq=1 (it parallelises over queries only)"}
             if world == 1:
-                times_all = cpu_time_queries(x_host, queries_host, k, cores, 12.0, 40)
-                times_one = cpu_time_queries(x_host, queries_host, k, 1, 8.0, 8)
-                scale = rows / sample_rows
-                med_all, med_one = statistics.median(times_all), statistics.median(times_one)
-                cpu = {"value": 1.0 / (med_all * scale), "unit": "queries/s", "cores": cores, "kind": "port",
-                       "sample": (f"first {sample_rows} of {rows} rows (same bits as the GPU corpus), {len(times_all)} queries, "
-                                  f"median, time scaled linearly x{scale:.2f}; oracle/flat_scan.c = FAISS IndexFlatIP small-batch "
-                                  f"path restated (FAISS is not installable here), rows split over {cores} threads"),
-                       "single_thread_value": 1.0 / (med_one * scale),
-                       "single_thread_note": "what FAISS does for nq=1 (it parallelises over queries only)"}
                 # SURVEY 8d variant (1): numpy / OpenBLAS sgemv + argpartition over the same sample, all BLAS threads
                 t_np = []
                 for i in range(6):
@@ -368,6 +450,7 @@ def run_ours(args):
                 cpu["numpy_openblas_value"] = 1.0 / (statistics.median(t_np[1:]) * scale)
                 cpu["numpy_openblas_note"] = "x @ q (sgemv, all BLAS threads) + argpartition + sort on the same sample, scaled the same way"
             del x_host
+        del mine, mine_ids, rows_all, ids_all, arena
 
     # ---- secondary configurations (not bench lines: context for the judge) -------------------------
     extras = {}
@@ -412,10 +495,12 @@ def run_ours(args):
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32" if args.store == "fp32" else "bf16 storage, f32 accumulate", "data": "synthetic",
             "config": {
-                "workload": f"{rows}x{d} {args.store} flat-IP top-{k}, nq=1 (BASELINE.json configs[3]; the metric's own shape)",
+                "workload": workload_name(rows, d, k, args.store),
                 "rows": rows, "dim": d, "k": k, "rows_per_gpu": local_rows, "parallelism": f"row-shard x{world}",
                 "l2_policy": "inputs larger than L2 (corpus shard >> 126 MB), no flush needed",
-                "launch_overlap": "queries resident on the device: scan i+1 starts streaming while scan i sorts/merges (programmatic dependent launch)",
+                "launch_policy": "library default (tunable pdl=1): consecutive calls in plain stream order",
+                "value_with_pdl2": qps_overlap,
+                "value_with_pdl2_note": "tunable pdl=2 (valid for resident queries only): scan i+1 starts streaming while scan i sorts/merges",
                 "scanned_GBps_aggregate": rows * d * esize / (ms_per_step * 1e-3) / 1e9,
                 "exchange": ("none" if world == 1 else
                              "fused: last CTA of the scan stores its k keys into every peer's buffer over NVLink + flag; one-CTA wait+merge kernel"
@@ -424,11 +509,11 @@ def run_ours(args):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "traffic_source": rec.get("source"),
                          "kernel": "psx::scan_topk_kernel", "algorithmic_bytes_per_launch": algo_bytes,
-                         "kernel_ms": scan_ms, "kernel_ms_note": f"CUDA events around every {EVERY}th scan launch of the timed region ({len(ev)} launches)",
+                         "kernel_ms": scan_ms, "kernel_ms_note": f"CUDA events around every {EVERY}th scan launch of the timed region ({n_bracketed} launches)",
                          "peak_source": peak_src, "frac_of_8TBps_spec": achieved / 8000.0},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_qps, "unit": "queries/s", "h2d_bytes_per_step": world * d * 4, "d2h_bytes_per_step": world * k * 12,
-                    "api": "ShardedIndex.search(host query) -> (scores, ids) on host"},
+                    "api": e2e_api},
             "gpu_launches": launches,
             "clocks": clock_info,
         }
@@ -530,9 +615,57 @@ def run_configs_2_3(torch, _native, queries, k, device):
     return out
 
 
+_MATMUL_PEAKS = {}
+
+
+def measure_matmul_peaks(torch, device):
+    """Yardstick only (cuBLAS through torch.matmul, never on a product path): dense 8192^3 throughput of the
+    tensor pipe with TF32 and bf16 operands, burst (best of 10) and sustained (back to back for ~1.5 s), on THIS
+    box at THIS moment -- the denominators of the batched-query rooflines."""
+    out = {}
+    n = 8192
+    prev = torch.backends.cuda.matmul.allow_tf32
+    try:
+        for name, dt, tf32 in (("tf32", torch.float32, True), ("bf16", torch.bfloat16, False)):
+            torch.backends.cuda.matmul.allow_tf32 = tf32
+            a = torch.randn((n, n), device=device, dtype=dt)
+            b = torch.randn((n, n), device=device, dtype=dt)
+            for _ in range(3):
+                a @ b
+            torch.cuda.synchronize()
+            best = 1e9
+            for _ in range(10):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                a @ b
+                e1.record()
+                torch.cuda.synchronize()
+                best = min(best, e0.elapsed_time(e1))
+            reps = max(10, int(1500.0 / best))
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(reps):
+                a @ b
+            e1.record()
+            torch.cuda.synchronize()
+            flop = 2.0 * n ** 3
+            out[f"{name}_tflops_burst"] = flop / best / 1e9
+            out[f"{name}_tflops_sustained"] = flop / (e0.elapsed_time(e1) / reps) / 1e9
+            del a, b
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+    out["how"] = "torch.matmul 8192^3 (cuBLAS), allow_tf32=True for the fp32 run; best of 10 and ~1.5 s back to back"
+    return out
+
+
 def run_extras(torch, _native, index, queries, rows, d, k, device, esize):
     """BASELINE.json configs 1-2 and the call-site k values, on the already-resident data."""
     out = {}
+    try:
+        _MATMUL_PEAKS.update(measure_matmul_peaks(torch, device))
+        out["matmul_peaks_this_box"] = dict(_MATMUL_PEAKS)
+    except Exception as exc:
+        out["matmul_peaks_this_box/error"] = repr(exc)[:200]
     q_ptrs = [queries[i: i + 1].data_ptr() for i in range(queries.shape[0])]
     for name, v in time_filtered(torch, index, q_ptrs, rows, d, esize, k, device).items():
         out[f"filtered/{name}"] = v
@@ -723,10 +856,17 @@ def run_batched(torch, _native, index, rows, d, k, device, tag="batched", bf16_g
     GEMM -- or bf16 GEMM over the bf16 rows of a bf16+fp32-master index --, selection fused into the
     epilogue, exact fp32 re-score), on the resident corpus."""
     out = {}
-    try:
-        tf32_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops"] / (1.0 if bf16_gemm else 2.0)
-    except Exception:
-        tf32_peak = 1590.0 / (1.0 if bf16_gemm else 2.0)
+    # tensor-pipe denominator: the burst figure measured on this box a moment ago (cuBLAS TF32 / bf16 8192^3); else the
+    # driver's bf16 burst peak (halved for TF32), else the recipe's fallback
+    peak_key = "bf16_tflops_burst" if bf16_gemm else "tf32_tflops_burst"
+    if _MATMUL_PEAKS.get(peak_key):
+        tf32_peak, peak_note = _MATMUL_PEAKS[peak_key], "cuBLAS 8192^3 burst measured in this run"
+    else:
+        try:
+            tf32_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops"] / (1.0 if bf16_gemm else 2.0)
+        except Exception:
+            tf32_peak = 1590.0 / (1.0 if bf16_gemm else 2.0)
+        peak_note = "MEASURED_PEAKS.json bf16 burst" + ("" if bf16_gemm else " / 2")
     gemm_esize = 2 if bf16_gemm else 4
     kind = "bf16" if bf16_gemm else "TF32"
     hbm_peak, _ = measured_peak()
@@ -789,7 +929,7 @@ def run_batched(torch, _native, index, rows, d, k, device, tag="batched", bf16_g
             "unproven_queries_rerun_on_scan_per_batch": unproven / steps,
             "timing_note": "ms_per_batch includes the certificate read-back (one host sync) and the scan re-runs of unproven queries",
             "roofline_frac": max(t_hbm, t_tc) / ms, "roofline_note": f"max(HBM {t_hbm:.3f} ms, {kind} {t_tc:.3f} ms at {tf32_peak:.0f} TFLOP/s"
-                                                                    f"{'' if bf16_gemm else ' = half the measured bf16 peak'}) / measured",
+                                                                    f" = {peak_note}) / measured",
             "bit_identical_to_scan": same,
         }
         if nq == 256:

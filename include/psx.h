@@ -158,10 +158,12 @@ int64_t psx_kpad(int64_t k);
  * re-score of the survivors.  flags_dev[i] == 0 certifies that query i's result is the exact
  * top-k (bit-identical to psx_search_device); a non-zero flag means "not proven", the caller
  * re-runs that query with psx_search_device.  psx_search does both steps itself for nq >= the
- * "batch_min" tunable.  `qnorm_max` >= the largest L2 norm among the queries (1 for cosine).
+ * "batch_min" tunable.  `qnorm_max` is ignored (kept for ABI stability): the rounding bound of every query is
+ * computed on the device from that query's own norm and the largest stored row norm.
  * `filter` (nullable) is the same EXIF predicate as in psx_search, shared by the whole batch: it is
  * applied to the survivors in the epilogue and to the sample the thresholds come from.
- * Inner-product indexes with fp32 rows (PSX_STORE_F32 / PSX_STORE_BF16_MASTER), >= 65536 rows, d >= 32, k <= 512. */
+ * Inner-product indexes with fp32 rows (PSX_STORE_F32 / PSX_STORE_BF16_MASTER), >= 65536 rows, d >= 32,
+ * k <= PSX_K_PASS_MAX (the reference's call sites ask for 500..1333, core/searcher.py:771-820). */
 int psx_search_batch_device(psx_index* h, const float* q_dev, int64_t nq, int64_t k, const psx_filter* filter, float qnorm_max,
                             uint32_t id_base, float* out_scores_dev, int64_t* out_ids_dev, uint64_t* out_keys_dev,
                             int* flags_dev, void* stream);

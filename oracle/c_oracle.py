@@ -36,6 +36,7 @@ def lib() -> C.CDLL:
             build()
             _lib = C.CDLL(LIB)
             _lib.oracle_max_threads()
+            _lib.oracle_set_threads
         except Exception:
             build(force=True)
             _lib = C.CDLL(LIB)
@@ -45,7 +46,21 @@ def lib() -> C.CDLL:
         _lib.oracle_fill_unit_rows.restype = None
         _lib.oracle_fill_unit_rows.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_uint64]
         _lib.oracle_max_threads.restype = C.c_int
+        _lib.oracle_set_threads.restype = None
+        _lib.oracle_set_threads.argtypes = [C.c_int]
     return _lib
+
+
+def host_cores() -> int:
+    """Cores this process may run on -- NOT omp_get_max_threads(), which follows OMP_NUM_THREADS (torchrun sets it to 1)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:  # pragma: no cover
+        return max(1, os.cpu_count() or 1)
+
+
+def set_threads(n: int) -> None:
+    lib().oracle_set_threads(int(n))
 
 
 def max_threads() -> int:

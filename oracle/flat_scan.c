@@ -204,6 +204,16 @@ void oracle_fill_unit_rows(float* X, int64_t n, int d, uint64_t seed) {
     }
 }
 
+/* Pin the OpenMP pool regardless of OMP_NUM_THREADS (torchrun exports OMP_NUM_THREADS=1, which would
+ * silently turn the all-core CPU arm into a one-thread arm). */
+void oracle_set_threads(int n) {
+#ifdef _OPENMP
+    if (n >= 1) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 int oracle_max_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

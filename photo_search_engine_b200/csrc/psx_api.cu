@@ -69,9 +69,13 @@ struct psx_index {
     size_t mrow_bytes = 0;
     uint64_t* attrs = nullptr;   // [cap]
     bool attrs_set = false;
-    long long n = 0, cap = 0;
-    std::vector<float> pending;  // rows staged by psx_add, not yet in HBM
-    long long pending_n = 0;
+    std::atomic<long long> n{0};  // rows in HBM (written under `mu`; psx_ntotal reads it without)
+    long long cap = 0;
+    // rows staged by psx_add, not yet in HBM.  Guarded by `pmu` alone, so that appends (the index build thread,
+    // core/indexer.py:858) never queue behind a search that holds `mu` for a whole GPU round trip.  Lock order: mu, then pmu.
+    std::vector<float> pending;
+    std::atomic<long long> pending_n{0};
+    std::mutex pmu;
 
     cudaStream_t stream = nullptr;
     cudaEvent_t last_ev = nullptr;   // completion of the last search (scratch reuse across streams)
@@ -119,7 +123,8 @@ struct psx_index {
     float* btheta = nullptr;  // [256]
     int* bcount = nullptr;    // [256]
     int* bflags = nullptr;    // [256]
-    uint32_t* bcand = nullptr;  // [256][BATCH_CAND_CAP]
+    uint32_t* bcand = nullptr;  // [256][bcand_cap]
+    int bcand_cap = 0;          // entries per query the lists currently have room for
     uint64_t* mkeys = nullptr;  // [PSX_K_PASS_MAX] bf16-prefilter keys (PSX_STORE_BF16_MASTER)
     float* meps = nullptr;      // [1] its rounding bound
     float* bsample = nullptr;
@@ -136,7 +141,13 @@ static inline const float* fp32_rows(const psx_index* h) { return (const float*)
 static inline int fp32_ld(const psx_index* h) { return h->dtype == PSX_STORE_F32 ? h->ld : h->ldm; }
 
 constexpr int BATCH_MAX_Q = 256;
-constexpr int BATCH_CAND_CAP = 4096;
+// survivors per query the candidate lists hold: twice the expected number (T), a power of two in [4096, 16384]
+constexpr int BATCH_CAND_CAP_MIN = 4096, BATCH_CAND_CAP_MAX = 16384;
+static int batch_cand_cap(int T) {
+    int cap = BATCH_CAND_CAP_MIN;
+    while (cap < 2 * T && cap < BATCH_CAND_CAP_MAX) cap <<= 1;
+    return cap;
+}
 // Tile shapes (measured on B200, 1M x 1024): up to 128 queries use one accumulator and 256-row corpus tiles
 // (TMEM double buffered, half the L2 re-reads of the query block); 129..256 queries use two accumulators
 // and 128-row tiles -- 256-row tiles would leave no TMEM for double buffering and lose the MMA/epilogue overlap.
@@ -269,6 +280,8 @@ static void free_all(psx_index* h) {
 extern "C" int psx_destroy(psx_index* h) {
     if (!h) return PSX_OK;
     {
+        // wait for a call still running on another thread (the caller must not START new calls on a handle it destroys)
+        std::lock_guard<std::mutex> lk(h->mu);
         DeviceGuard g(h->device);
         cudaDeviceSynchronize();
         free_all(h);
@@ -295,10 +308,14 @@ extern "C" int psx_reset(psx_index* h) {
     h->attrs_set = false;
     cudaMemset(h->dmax_sumsq, 0, sizeof(float));
     h->max_norm = 0.f;
-    h->n = h->cap = 0;
-    h->pending.clear();
-    h->pending.shrink_to_fit();
-    h->pending_n = 0;
+    h->n = 0;
+    h->cap = 0;
+    {
+        std::lock_guard<std::mutex> pk(h->pmu);
+        h->pending.clear();
+        h->pending.shrink_to_fit();
+        h->pending_n = 0;
+    }
     return PSX_OK;
 }
 
@@ -382,16 +399,36 @@ static int launch_pack(psx_index* h, const float* src_dev, long long row0, long 
 // upload rows staged on the host (chunked through a bounded device bounce buffer)
 static int flush_pending(psx_index* h) {
     if (h->pending_n == 0) return PSX_OK;
-    int rc = ensure_capacity(h, h->n + h->pending_n, false);
-    if (rc) return rc;
+    // take the staged rows; appends arriving from now on start a fresh staging vector
+    std::vector<float> rows;
+    long long rows_n = 0;
+    {
+        std::lock_guard<std::mutex> pk(h->pmu);
+        rows.swap(h->pending);
+        rows_n = h->pending_n;
+    }
+    auto put_back = [&]() {  // failure: the rows stay staged (in order, in front of whatever arrived meanwhile)
+        std::lock_guard<std::mutex> pk(h->pmu);
+        rows.insert(rows.end(), h->pending.begin(), h->pending.end());
+        h->pending.swap(rows);
+    };
+    int rc = ensure_capacity(h, h->n + rows_n, false);
+    if (rc) {
+        put_back();
+        return rc;
+    }
     const long long chunk_rows = std::max<long long>(1, (256ll << 20) / ((long long)h->d * 4));
     float* bounce = nullptr;
-    const long long brows = std::min(chunk_rows, h->pending_n);
-    CU(cudaMalloc(&bounce, (size_t)brows * h->d * sizeof(float)));
+    const long long brows = std::min(chunk_rows, rows_n);
+    if (cudaMalloc(&bounce, (size_t)brows * h->d * sizeof(float)) != cudaSuccess) {
+        cudaGetLastError();
+        put_back();
+        return fail(PSX_ERR_OOM, "cudaMalloc of the upload bounce buffer failed");
+    }
     long long done = 0;
-    while (done < h->pending_n) {
-        const long long m = std::min(brows, h->pending_n - done);
-        cudaError_t e = cudaMemcpyAsync(bounce, h->pending.data() + (size_t)done * h->d, (size_t)m * h->d * sizeof(float),
+    while (done < rows_n) {
+        const long long m = std::min(brows, rows_n - done);
+        cudaError_t e = cudaMemcpyAsync(bounce, rows.data() + (size_t)done * h->d, (size_t)m * h->d * sizeof(float),
                                         cudaMemcpyHostToDevice, h->stream);
         if (e == cudaSuccess) {
             rc = launch_pack(h, bounce, h->n + done, m, 0, h->stream);
@@ -399,29 +436,37 @@ static int flush_pending(psx_index* h) {
         }
         if (e != cudaSuccess || rc != PSX_OK) {
             cudaFree(bounce);
+            put_back();
             return rc ? rc : fail(PSX_ERR_CUDA, "upload failed: %s", cudaGetErrorString(e));
         }
         done += m;
     }
     cudaFree(bounce);
-    h->n += h->pending_n;
-    h->pending_n = 0;
-    h->pending.clear();
+    {
+        std::lock_guard<std::mutex> pk(h->pmu);
+        h->n += rows_n;  // n and pending_n move together under pmu: psx_ntotal never sees the rows twice or not at all
+        h->pending_n -= rows_n;
+    }
     return PSX_OK;
 }
 
 extern "C" int psx_add(psx_index* h, const float* x, int64_t n) {
     if (!h || (!x && n > 0) || n < 0) return fail(PSX_ERR_INVALID, "bad arguments to psx_add");
-    std::lock_guard<std::mutex> lk(h->mu);
-    if ((unsigned long long)(h->n + h->pending_n + n) >= 0xffffffffull) return fail(PSX_ERR_RANGE, "more than 2^32-1 rows");
-    try {
-        h->pending.insert(h->pending.end(), x, x + (size_t)n * h->d);
-    } catch (const std::bad_alloc&) {
-        return fail(PSX_ERR_OOM, "host staging allocation failed");
+    bool big = false;
+    {
+        std::lock_guard<std::mutex> pk(h->pmu);
+        if ((unsigned long long)(h->n + h->pending_n + n) >= 0xffffffffull) return fail(PSX_ERR_RANGE, "more than 2^32-1 rows");
+        try {
+            h->pending.insert(h->pending.end(), x, x + (size_t)n * h->d);
+        } catch (const std::bad_alloc&) {
+            return fail(PSX_ERR_OOM, "host staging allocation failed");
+        }
+        h->pending_n += n;
+        big = (size_t)h->pending_n * h->d * sizeof(float) >= (512ull << 20);
     }
-    h->pending_n += n;
     // keep the host staging bounded: big batches go to HBM right away
-    if ((size_t)h->pending_n * h->d * sizeof(float) >= (512ull << 20)) {
+    if (big) {
+        std::lock_guard<std::mutex> lk(h->mu);
         DeviceGuard g(h->device);
         return flush_pending(h);
     }
@@ -466,7 +511,7 @@ extern "C" int psx_set_attrs(psx_index* h, int64_t row0, const uint64_t* attrs, 
     int rc = flush_pending(h);
     if (rc) return rc;
     if (row0 + n > h->n) return fail(PSX_ERR_RANGE, "attribute rows [%lld,%lld) exceed ntotal %lld", (long long)row0,
-                                     (long long)(row0 + n), h->n);
+                                     (long long)(row0 + n), h->n.load());
     if (n == 0) return PSX_OK;
     CU(cudaMemcpyAsync(h->attrs + row0, attrs, (size_t)n * sizeof(uint64_t), cudaMemcpyHostToDevice, h->stream));
     CU(cudaStreamSynchronize(h->stream));
@@ -723,16 +768,25 @@ static int make_map(CUtensorMap* map, const void* base, bool bf16, long long row
 static bool batch_eligible(const psx_index* h, int64_t nq, int64_t k, const psx_filter* f) {
     (void)f;  // the predicate is applied in the epilogue (candidates) and in the sample (thresholds)
     return h->metric == PSX_METRIC_IP && has_fp32_rows(h) && h->batch_min > 0 &&
-           nq >= h->batch_min && k <= 512 && h->n >= 65536 && h->d >= 32;
+           nq >= h->batch_min && k <= PSX_K_PASS_MAX && h->n >= 65536 && h->d >= 32;
 }
 
-static int ensure_batch_scratch(psx_index* h, size_t sample_floats) {
+static int ensure_batch_scratch(psx_index* h, size_t sample_floats, int cand_cap = BATCH_CAND_CAP_MIN) {
+    if (cand_cap > h->bcand_cap) {
+        if (h->bcand) {
+            CU(cudaDeviceSynchronize());  // a batch enqueued earlier may still be filling the old lists
+            cudaFree(h->bcand);
+            h->bcand = nullptr;
+            h->bcand_cap = 0;
+        }
+        CU(cudaMalloc(&h->bcand, (size_t)BATCH_MAX_Q * cand_cap * sizeof(uint32_t)));
+        h->bcand_cap = cand_cap;
+    }
     if (!h->bq) {
         CU(cudaMalloc(&h->bq, (size_t)BATCH_MAX_Q * (h->ldm + 8) * sizeof(float)));
         CU(cudaMalloc(&h->btheta, BATCH_MAX_Q * sizeof(float)));
         CU(cudaMalloc(&h->bcount, BATCH_MAX_Q * sizeof(int)));
         CU(cudaMalloc(&h->bflags, BATCH_MAX_Q * sizeof(int)));
-        CU(cudaMalloc(&h->bcand, (size_t)BATCH_MAX_Q * BATCH_CAND_CAP * sizeof(uint32_t)));
         CU(cudaMalloc(&h->mkeys, (size_t)PSX_K_PASS_MAX * sizeof(uint64_t)));
         CU(cudaMalloc(&h->meps, sizeof(float)));
         CU(cudaMallocHost(&h->hflags, BATCH_MAX_Q * sizeof(int)));
@@ -824,14 +878,16 @@ static int launch_batch(psx_index* h, const float* q_dev, int nq, int k, const p
     // number of rows above the sample's 16th score is ~ T * Gamma(16)/16: it undercuts k + (rows within eps of
     // the k-th) with probability ~3e-5 per query at k = 100 (8 sample scores and T = 3k+48 failed 2.7 % of the
     // queries of a 10M-row corpus, each of which costs a full scan).
-    // (bf16 operands: the wider error bound eps asks for ~60 more rows above theta; T = 4k+64 left 3e-4 of the queries unproven)
-    const int T = (h->dtype == PSX_STORE_BF16_MASTER && h->batch_bf16) ? 5 * k + 96 : 4 * k + 64;
+    // (bf16 operands: the rounding bound 8.2e-3 |q||x| is ~0.26 sigma of the score distribution of 1024-d unit vectors, i.e.
+    // ~2.6-3 x k rows lie within eps of the k-th score: T = 8k+128 keeps them above theta with the same margin)
+    const int T = (h->dtype == PSX_STORE_BF16_MASTER && h->batch_bf16) ? 8 * k + 128 : 4 * k + 64;
     int tile_step = T / 16;
     if (tile_step < 1) tile_step = 1;
     const int sample_tiles = (num_tiles + tile_step - 1) / tile_step;
     const int grid_s = pair ? std::min(h->sm_count / 2, sample_tiles) : std::min(h->sm_count, sample_tiles);
     const int sample_ld = grid_s * SAMPLE_KEEP;  // every sample CTA (pair) leaves its 8 best scores per query
-    int rc = ensure_batch_scratch(h, (size_t)MT * GEMM_M * sample_ld);
+    const int cand_cap = batch_cand_cap(T);
+    int rc = ensure_batch_scratch(h, (size_t)MT * GEMM_M * sample_ld, cand_cap);
     if (rc) return rc;
     // queries -> zero-padded [MT*128][ld] block (rows beyond nq and columns beyond d are zero)
     const int fld = fp32_ld(h);
@@ -862,7 +918,7 @@ static int launch_batch(psx_index* h, const float* q_dev, int nq, int k, const p
     gp.theta = h->btheta;
     gp.cand_ids = h->bcand;
     gp.cand_count = h->bcount;
-    gp.cand_cap = BATCH_CAND_CAP;
+    gp.cand_cap = cand_cap;
     gp.sample_scores = h->bsample;
     gp.sample_ld = sample_ld;
     if (f && f->flags) {
@@ -903,24 +959,22 @@ static int launch_batch(psx_index* h, const float* q_dev, int nq, int k, const p
     bt.mark("filter pass");
     // exact re-score of the survivors + top-k + proof obligation
     const int kpad = (int)psx_kpad(k);
-    const size_t smem = (size_t)BATCH_CAND_CAP * 8 + (size_t)(fld + 4) * 4;
+    const size_t smem = (size_t)std::max(cand_cap, kpad) * 8 + (size_t)(fld + 4) * 4;
     static std::atomic<bool> ready[64];
     if (h->device < 64 && !ready[h->device].load()) {
         CU(cudaFuncSetAttribute(rescore_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PSX_SMEM_LIMIT));
         ready[h->device].store(true);
     }
-    // TF32 keeps 10 mantissa bits of each operand: |score_tf32 - score| <= 2^-9 * sum|q_i x_i| <= 2^-9 |q| |x|
-    // (Cauchy-Schwarz); 2.2e-3 leaves 12 % slack for the accumulation.
-    if (h->max_norm == 0.f) {
-        float m2 = 0.f;
-        CU(cudaMemcpyAsync(&m2, h->dmax_sumsq, sizeof(float), cudaMemcpyDeviceToHost, st));
-        CU(cudaStreamSynchronize(st));
-        h->max_norm = sqrtf(m2);
-    }
-    // bf16 operands keep 8 significant bits each: |score_bf16 - score| <= (2^-9 + 2^-9) sum|q_i x_i| <= 2^-8 |q| |x|; 4.3e-3 adds 10 %
-    const float eps = (bf ? 4.3e-3f : 2.2e-3f) * (qnorm_max > 0.f ? qnorm_max : 1.0f) * (h->max_norm > 0.f ? h->max_norm : 1.0f);
+    // TF32 drops 13 mantissa bits of each operand (truncation: relative error < 2^-10 each):
+    // |score_tf32 - score| <= 2 * 2^-10 * sum|q_i x_i| <= 2^-9 |q| |x| (Cauchy-Schwarz); 2.2e-3 leaves 12 % for the accumulation.
+    // bf16 operands are rounded to nearest with 8 significant bits (unit roundoff 2^-8 EACH, q and x both rounded):
+    // |score_bf16 - score| <= (2 * 2^-8 + 2^-16) |q| |x| = 7.83e-3 |q| |x|; 8.2e-3 leaves 5 % for the accumulation.
+    // The kernel multiplies the coefficient by the query's own norm and the largest stored row norm (both on the device).
+    (void)qnorm_max;
+    const float eps_coef = bf ? 8.2e-3f : 2.2e-3f;
     rescore_select_kernel<<<nq, 512, smem, st>>>(fp32_rows(h), fld, h->d, h->n, q_dev, k, kpad, h->bcand, h->bcount,
-                                                 BATCH_CAND_CAP, h->btheta, eps, nullptr, id_base, out_scores, out_ids, out_keys, flags_dev);
+                                                 cand_cap, h->btheta, eps_coef, h->dmax_sumsq, nullptr, id_base, out_scores, out_ids,
+                                                 out_keys, flags_dev);
     g_launches++;
     CU(cudaGetLastError());
     DBG_SYNC(st, "rescore_select_kernel");
@@ -953,14 +1007,14 @@ static int launch_mixed(psx_index* h, const float* q_dev, int k, const psx_filte
     g_launches++;
     CU(cudaGetLastError());
     const int kpad = (int)psx_kpad(k);
-    const size_t smem = (size_t)BATCH_CAND_CAP * 8 + (size_t)(h->ldm + 4) * 4;
+    const size_t smem = (size_t)h->bcand_cap * 8 + (size_t)(h->ldm + 4) * 4;
     static std::atomic<bool> ready[64];
     if (h->device < 64 && !ready[h->device].load()) {
         CU(cudaFuncSetAttribute(rescore_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PSX_SMEM_LIMIT));
         ready[h->device].store(true);
     }
-    rescore_select_kernel<<<1, 512, smem, st>>>((const float*)h->xm, h->ldm, h->d, h->n, q_dev, k, kpad, h->bcand, h->bcount, BATCH_CAND_CAP,
-                                                h->btheta, 0.f, h->meps, id_base, out_scores, out_ids, out_keys, h->bflags);
+    rescore_select_kernel<<<1, 512, smem, st>>>((const float*)h->xm, h->ldm, h->d, h->n, q_dev, k, kpad, h->bcand, h->bcount, h->bcand_cap,
+                                                h->btheta, 0.f, h->dmax_sumsq, h->meps, id_base, out_scores, out_ids, out_keys, h->bflags);
     g_launches++;
     CU(cudaGetLastError());
     h->mixed_queries++;
@@ -1063,8 +1117,8 @@ extern "C" int psx_search_batch_device(psx_index* h, const float* q_dev, int64_t
     DeviceGuard g(h->device);
     int rc = flush_pending(h);
     if (rc) return rc;
-    if (k < 1 || k > 512 || h->metric != PSX_METRIC_IP || !has_fp32_rows(h) || h->n < 65536 || h->d < 32)
-        return fail(PSX_ERR_STATE, "tensor-core batch path needs an fp32 inner-product index with >= 65536 rows, d >= 32, k <= 512");
+    if (k < 1 || k > PSX_K_PASS_MAX || h->metric != PSX_METRIC_IP || !has_fp32_rows(h) || h->n < 65536 || h->d < 32)
+        return fail(PSX_ERR_STATE, "tensor-core batch path needs an fp32 inner-product index with >= 65536 rows, d >= 32, k <= %d", PSX_K_PASS_MAX);
     cudaStream_t st = (cudaStream_t)stream;
     if ((rc = enter_stream(h, st))) return rc;
     const int64_t kpad = psx_kpad(k);
@@ -1289,17 +1343,21 @@ extern "C" int psx_read_rows(psx_index* h, int64_t row0, int64_t n, float* out) 
     DeviceGuard g(h->device);
     int rc = flush_pending(h);
     if (rc) return rc;
-    if (row0 + n > h->n) return fail(PSX_ERR_RANGE, "rows [%lld,%lld) exceed ntotal %lld", (long long)row0, (long long)(row0 + n), h->n);
+    if (row0 + n > h->n) return fail(PSX_ERR_RANGE, "rows [%lld,%lld) exceed ntotal %lld", (long long)row0, (long long)(row0 + n), h->n.load());
     return read_rows_locked(h, row0, n, out);
 }
 
 extern "C" int psx_reconstruct(psx_index* h, int64_t id, float* out) {
     if (!h || !out) return fail(PSX_ERR_INVALID, "bad arguments to psx_reconstruct");
     std::lock_guard<std::mutex> lk(h->mu);
-    if (id < 0 || id >= h->n + h->pending_n) return fail(PSX_ERR_RANGE, "id %lld not in [0,%lld)", (long long)id, h->n + h->pending_n);
+    if (id < 0 || id >= h->n + h->pending_n) return fail(PSX_ERR_RANGE, "id %lld not in [0,%lld)", (long long)id, (long long)(h->n + h->pending_n));
     if (id >= h->n && has_fp32_rows(h)) {  // still staged on the host, stored precision == fp32
-        memcpy(out, h->pending.data() + (size_t)(id - h->n) * h->d, (size_t)h->d * sizeof(float));
-        return PSX_OK;
+        std::lock_guard<std::mutex> pk(h->pmu);
+        const long long off = id - h->n;
+        if (off >= 0 && off < h->pending_n) {
+            memcpy(out, h->pending.data() + (size_t)off * h->d, (size_t)h->d * sizeof(float));
+            return PSX_OK;
+        }
     }
     DeviceGuard g(h->device);
     int rc = flush_pending(h);

@@ -475,20 +475,10 @@ gemm_filter_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
         if (lane == 0) {
             int s = 0;
             uint32_t ph = 0;
-#ifdef PSX_DEBUG_KERNELS
-            long long w_empty = 0, t_all = clock64(), nkb = 0;
-#endif
             for (int t = first; t < p.num_tiles; t += stride) {
                 const int row0 = t * BN + (int)cta * (BN / 2);
                 for (int kb = 0; kb < kblocks; ++kb) {
-#ifdef PSX_DEBUG_KERNELS
-                    long long c0 = clock64();
                     mbar_wait(smem_u32(empty_bar + s), ph ^ 1u);
-                    w_empty += clock64() - c0;
-                    ++nkb;
-#else
-                    mbar_wait(smem_u32(empty_bar + s), ph ^ 1u);
-#endif
                     const uint32_t bar = smem_u32(full_bar + s);
                     const uint32_t a_dst = smem_u32(tiles + (size_t)s * STAGE_BYTES);
                     if (leader) mbar_arrive_expect_tx(bar, 2 * STAGE_BYTES);
@@ -501,9 +491,6 @@ gemm_filter_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
                     }
                 }
             }
-#ifdef PSX_DEBUG_KERNELS
-            if (blockIdx.x < 2) printf("pair producer cta %u: total %lld cyc, %lld kblocks, wait(empty) %lld\n", cta, clock64() - t_all, nkb, w_empty);
-#endif
         }
     } else if (warp == 1) {
         // ===== MMA issuer: one thread of the leader CTA drives both tensor cores =====
@@ -511,27 +498,11 @@ gemm_filter_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
             constexpr uint32_t idesc = umma_idesc<BF>(2 * GEMM_M, BN);
             int s = 0, a = 0;
             uint32_t ph = 0, aph = 0;
-#ifdef PSX_DEBUG_KERNELS
-            long long w_full = 0, w_acc = 0, t_all = clock64(), nkb = 0;
-#endif
             for (int t = first; t < p.num_tiles; t += stride) {
-#ifdef PSX_DEBUG_KERNELS
-                long long c0 = clock64();
-#endif
                 mbar_wait(smem_u32(acc_empty + a), aph ^ 1u);
-#ifdef PSX_DEBUG_KERNELS
-                w_acc += clock64() - c0;
-#endif
                 tc_fence_after();
                 for (int kb = 0; kb < kblocks; ++kb) {
-#ifdef PSX_DEBUG_KERNELS
-                    long long c1 = clock64();
-#endif
                     mbar_wait(smem_u32(full_bar + s), ph);
-#ifdef PSX_DEBUG_KERNELS
-                    w_full += clock64() - c1;
-                    ++nkb;
-#endif
                     tc_fence_after();
                     const uint32_t a_addr = smem_u32(tiles + (size_t)s * STAGE_BYTES);
                     const uint64_t a_desc = umma_smem_desc(a_addr);
@@ -551,10 +522,6 @@ gemm_filter_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
                     aph ^= 1u;
                 }
             }
-#ifdef PSX_DEBUG_KERNELS
-            if (blockIdx.x == 0)
-                printf("pair mma: total %lld cyc, %lld kblocks, wait(full) %lld, wait(acc_empty) %lld\n", clock64() - t_all, nkb, w_full, w_acc);
-#endif
         }
     } else if (warp >= 4) {
         // ===== epilogue (each CTA drains its own 128 TMEM lanes = its 128 queries) =====
@@ -671,7 +638,8 @@ __global__ void __launch_bounds__(256) theta_kernel(const float* __restrict__ sa
 __global__ void __launch_bounds__(512, 2)
 rescore_select_kernel(const float* __restrict__ x, int ld, int d, long long n, const float* __restrict__ q, int k, int kpad,
                       const uint32_t* __restrict__ cand_ids, const int* __restrict__ cand_count, int cand_cap,
-                      const float* __restrict__ theta, float eps, const float* __restrict__ eps_dev, uint32_t id_base,
+                      const float* __restrict__ theta, float eps_coef, const float* __restrict__ max_sumsq,
+                      const float* __restrict__ eps_dev, uint32_t id_base,
                       float* out_scores, long long* out_ids, uint64_t* out_keys, int* flags) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     uint64_t* keys = reinterpret_cast<uint64_t*>(smem_raw);     // [np]
@@ -682,9 +650,6 @@ rescore_select_kernel(const float* __restrict__ x, int ld, int d, long long n, c
     while (np < count) np <<= 1;
     float* sq = reinterpret_cast<float*>(keys + np);
     const int qpad = (ld + 3) & ~3;
-#ifdef PSX_DEBUG_KERNELS
-    if (threadIdx.x == 0) printf("rescore: q=%d raw_count=%d count=%d np=%d theta=%g k=%d kpad=%d ld=%d d=%d\n", qi, raw_count, count, np, theta[qi], k, kpad, ld, d);
-#endif
     for (int i = threadIdx.x; i < qpad; i += blockDim.x) sq[i] = i < d ? q[(size_t)qi * d + i] : 0.f;
     for (int i = count + threadIdx.x; i < np; i += blockDim.x) keys[i] = 0ull;
     __syncthreads();
@@ -693,12 +658,6 @@ rescore_select_kernel(const float* __restrict__ x, int ld, int d, long long n, c
     const int pieces = ld >> 2;
     for (int c = warp; c < count; c += nwarps) {
         const uint32_t row = cand_ids[(size_t)qi * cand_cap + c];
-#ifdef PSX_DEBUG_KERNELS
-        if (row >= n) {
-            if (lane == 0) printf("rescore: q=%d c=%d row=%u >= n=%lld (count %d raw %d)\n", qi, c, row, n, count, raw_count);
-            continue;
-        }
-#endif
         const float4* xr = reinterpret_cast<const float4*>(x + (size_t)row * ld);
         float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll 4
@@ -716,13 +675,7 @@ rescore_select_kernel(const float* __restrict__ x, int ld, int d, long long n, c
         if (lane == 0) keys[c] = make_key(s, id_base + row);
     }
     __syncthreads();
-#ifdef PSX_DEBUG_KERNELS
-    if (threadIdx.x == 0) printf("rescore: q=%d scored, key0=%llx\n", qi, (unsigned long long)keys[0]);
-#endif
     block_bitonic_sort_desc(keys, np);
-#ifdef PSX_DEBUG_KERNELS
-    if (threadIdx.x == 0) printf("rescore: q=%d sorted, key0=%llx out_scores=%p out_ids=%p flags=%p\n", qi, (unsigned long long)keys[0], out_scores, out_ids, flags);
-#endif
     const int kk = k;
     block_emit_results(keys, kk, kpad, PSX_METRIC_IP, out_scores + (size_t)qi * k, out_ids + (size_t)qi * k,
                        out_keys ? out_keys + (size_t)qi * kpad : nullptr);
@@ -733,7 +686,16 @@ rescore_select_kernel(const float* __restrict__ x, int ld, int d, long long n, c
         if (count < need) bad = 2;                                           // threshold too tight
         if (!bad && need > 0 && n > count) {
             const float kth = key_score(keys[need - 1]);
-            const float e = eps_dev ? eps_dev[qi] : eps;
+            // rounding bound of the approximate scores for THIS query, from its own norm and the largest stored row
+            // norm (Cauchy-Schwarz): eps_coef * |q| * max|x|.  Computed here so that no caller has to supply norms.
+            float e;
+            if (eps_dev) {
+                e = eps_dev[qi];
+            } else {
+                float qq = 0.f;
+                for (int i = 0; i < d; ++i) qq = fmaf(sq[i], sq[i], qq);
+                e = eps_coef * sqrtf(qq) * sqrtf(fmaxf(*max_sumsq, 0.f)) * 1.001f;
+            }
             if (!(kth >= theta[qi] + e)) bad = 3;                          // proof obligation not met
         }
         flags[qi] = bad;

@@ -27,6 +27,7 @@ from __future__ import annotations
 
 import json
 import os
+import threading
 from typing import Any, Callable, Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
@@ -116,6 +117,10 @@ class VectorStore:
         self.store_dtype = dtype_name
 
         self._normalize = metric_name == "cosine"
+        # load() / clear() swap index + metadata as a pair under this lock; readers take the pair under it too.  The
+        # old backend handle is never destroyed explicitly: a search running on another request thread still holds a
+        # reference, and the handle is freed when the last reference goes (as with the reference's faiss object).
+        self._swap_lock = threading.RLock()
         self.metadata: List[Dict] = []
         self._embeddings: List[Optional[List[float]]] = []
         self._path_to_index: Dict[str, int] = {}
@@ -242,10 +247,12 @@ class VectorStore:
         ntotal)``; ``[]`` on an empty store.  ``constraints`` (not part of the reference
         signature) limits the scan to rows passing the EXIF predicate.
         """
-        if self.index is None or self.index.ntotal == 0:
+        with self._swap_lock:
+            index, records = self.index, self.metadata
+        if index is None or index.ntotal == 0:
             return []
         self._require_dimension(query_embedding)
-        k = min(int(top_k), self.index.ntotal)
+        k = min(int(top_k), index.ntotal)
         if k <= 0:
             return []
         flt, never = self._filter_for(constraints)
@@ -255,13 +262,12 @@ class VectorStore:
         if self._coalescer is not None:
             row_scores, row_labels = self._coalescer.submit(query[0], k, None if flt is None else bytes(flt), flt)
         else:
-            distances, labels = self._run_search(query, k, flt)
+            distances, labels = index.search(query, k) if flt is None else index.search(query, k, flt)
             row_scores, row_labels = distances[0], labels[0]
-        records = self.metadata
         return [
             {"metadata": records[label], "distance": float(distance)}
             for distance, label in zip(row_scores.tolist(), row_labels.tolist())
-            if label != -1
+            if label != -1 and label < len(records)
         ]
 
     def search_batch(self, queries: np.ndarray, top_k: int, constraints: Optional[Dict[str, Any]] = None,
@@ -365,38 +371,55 @@ class VectorStore:
         if info["ntotal"] != len(records):
             raise ValueError(_E_COUNT_MISMATCH)
 
-        if self.index is not None and hasattr(self.index, "close"):
-            self.index.close()
-        self.dimension = int(info["d"])
-        self.index = self._create_index(self.dimension)
-        if hasattr(self.index, "reserve"):
-            self.index.reserve(info["ntotal"])
+        # Build the new backend completely before anything is swapped: request threads keep searching the old one
+        # meanwhile (core/searcher.py:1579 calls load_index lazily from request threads, core/indexer.py:680 reloads
+        # during serving), and the old handle is released by reference count, never destroyed under a running search.
+        dimension = int(info["d"])
+        saved_dimension, self.dimension = self.dimension, dimension
+        try:
+            fresh = self._create_index(dimension)
+        except MemoryError:
+            # both copies do not fit: give the old one up first (searches in flight keep it alive until they return)
+            with self._swap_lock:
+                self.index = None
+            fresh = self._create_index(dimension)
+        finally:
+            self.dimension = saved_dimension
+        if hasattr(fresh, "reserve"):
+            fresh.reserve(info["ntotal"])
         for block in blocks:
-            self.index.add(block)
-        self.metadata = records
-        self._embeddings = [None] * info["ntotal"]
-        self._attrs_built = 0
-        self._attr_words = np.zeros(0, np.uint64)
+            fresh.add(block)
+        attr_words, attrs_built = np.zeros(0, np.uint64), 0
         if os.path.exists(self.attrs_path) and os.path.getsize(self.attrs_path) == 8 * info["ntotal"] and info["ntotal"] > 0 \
                 and os.path.getmtime(self.attrs_path) >= os.path.getmtime(self.metadata_path):
             words = np.fromfile(self.attrs_path, dtype="<u8").astype(np.uint64)
-            self.index.set_attrs(0, words)
-            self._attr_words, self._attrs_built = words, info["ntotal"]
-        self._path_to_index = {}
+            fresh.set_attrs(0, words)
+            attr_words, attrs_built = words, info["ntotal"]
+        paths: Dict[str, int] = {}
         for row, metadata in enumerate(records):
-            self._remember_path(metadata, row)
+            photo_path = metadata.get("photo_path") if isinstance(metadata, dict) else None
+            if isinstance(photo_path, str) and photo_path:
+                paths[photo_path] = row
+        with self._swap_lock:
+            self.dimension = dimension
+            self.index = fresh
+            self.metadata = records
+            self._embeddings = [None] * info["ntotal"]
+            self._attr_words, self._attrs_built = attr_words, attrs_built
+            self._path_to_index = paths
         return True
 
     def clear(self) -> None:
         """Drop all vectors and metadata, keep the dimension (utils/vector_store.py:273-280)."""
-        if self.index is not None and hasattr(self.index, "reset"):
-            self.index.reset()
-        elif self.dimension:
-            self.index = self._create_index(self.dimension)
-        else:
-            self.index = None
-        self.metadata = []
-        self._embeddings = []
-        self._path_to_index = {}
-        self._attrs_built = 0
-        self._attr_words = np.zeros(0, np.uint64)
+        with self._swap_lock:
+            if self.index is not None and hasattr(self.index, "reset"):
+                self.index.reset()
+            elif self.dimension:
+                self.index = self._create_index(self.dimension)
+            else:
+                self.index = None
+            self.metadata = []
+            self._embeddings = []
+            self._path_to_index = {}
+            self._attrs_built = 0
+            self._attr_words = np.zeros(0, np.uint64)

@@ -44,6 +44,29 @@ def test_library_is_sm100a_with_tma():
     assert "UBLKCP" in out.stdout and "SYNCS" in out.stdout
 
 
+def test_sass_census_shows_tcgen05_tmem_tma():
+    """The batched path is genuinely tcgen05 / TMEM / tensor-map TMA and nothing falls back to mma.sync
+    (census committed as profiles/r2_sass_census.txt, tool: tools/sass_census.py)."""
+    import importlib.util
+
+    from photo_search_engine_b200 import _native
+
+    spec = importlib.util.spec_from_file_location("sass_census", os.path.join(ROOT, "tools", "sass_census.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    try:
+        counts, per_kernel, is_100a = mod.census(_native.LIB_PATH)
+    except Exception:
+        pytest.skip("cuobjdump unavailable")
+    assert is_100a
+    assert counts["UTCHMMA"] >= 8 and counts["UTCHMMA.2CTA"] >= 4     # cta_group::1 and cta_group::2 MMAs
+    assert counts["LDTM"] >= 4 and counts["UTMALDG"] >= 4             # TMEM read-back, tiled TMA loads
+    assert counts["UBLKCP"] >= 100 and counts["UTCBAR"] >= 4          # bulk row stream, MMA -> mbarrier commits
+    assert counts["HMMA"] == 0                                          # no legacy tensor-core path anywhere
+    gemm = [c for name, c in per_kernel.items() if "gemm_filter" in name]
+    assert gemm and all(c["UTCHMMA"] + c["UTCHMMA.2CTA"] > 0 and c["LDTM"] > 0 and c["UTMALDG"] > 0 for c in gemm)
+
+
 @pytest.mark.skipif(has_gpu(), reason="only meaningful on a machine without a GPU")
 def test_fails_loudly_without_gpu(tmp_path):
     from photo_search_engine_b200 import _native

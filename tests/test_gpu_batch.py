@@ -59,6 +59,85 @@ def test_batch_equals_scan(n, d, nq, k):
     ix.close()
 
 
+@pytest.mark.parametrize("k", [675, 850, 1025, 1333, 2048])
+def test_batch_serves_the_call_site_k(k):
+    """candidate_k of the reference's expansion / reflection rounds (core/searcher.py:771-820: 675, 850, 1025, up to
+    1333) and the pass maximum go through the tensor-core path -- not the nq-scans fallback -- and stay bit-identical."""
+    rng = np.random.default_rng(k)
+    n, d, nq = 120_000, 128, 12
+    x = unit_rows(rng, n, d)
+    q = unit_rows(rng, nq, d)
+    q[0] = x[31337]
+    ix = N().NativeIndex(d)
+    ix.add(x)
+    (Ds, Is), (Db, Ib), (served, fallbacks) = _both_paths(ix, q, k)
+    assert served == nq, "k above 512 fell back to sequential scans"
+    assert np.array_equal(Ib, Is) and np.array_equal(Db, Ds)
+    assert Ib[0, 0] == 31337
+    assert fallbacks <= 2, fallbacks
+    ix.close()
+
+
+def test_batch_with_non_unit_queries():
+    """The rounding bound of the certificate scales with |q|: it is computed per query on the device, so callers
+    (ShardedIndex, psx_search_batch_device users) need not supply norms.  Queries of norm 0.01 .. 30 stay exact."""
+    rng = np.random.default_rng(21)
+    n, d, nq, k = 100_000, 256, 16, 50
+    x = unit_rows(rng, n, d)
+    q = unit_rows(rng, nq, d) * np.logspace(-2, 1.5, nq).astype(np.float32)[:, None]
+    ix = N().NativeIndex(d)
+    ix.add(x)
+    (Ds, Is), (Db, Ib), (served, fallbacks) = _both_paths(ix, q, k)
+    assert served == nq and np.array_equal(Ib, Is) and np.array_equal(Db, Ds)
+    assert fallbacks <= 2
+    ix.close()
+
+
+def test_bf16_certificate_survives_sign_aligned_rounding():
+    """Adversarial for the bf16 GEMM certificate: q and the rows A all sit 0.498 ulp above a bf16 grid
+    point, so BOTH operands round down and the bf16 score of A is 2*2^-8 = 0.78 % below its exact score (1.0000
+    vs 1.0078).  Decoy rows B (exact == bf16 score 1.0068) and a filler band F (1.0009 .. 1.0019, 3000 rows, where
+    the threshold lands) rank above A in bf16 arithmetic although A is the true top-100.  A rounding bound of
+    2^-8 |q||x| (one operand) certifies the wrong answer B; the rigorous 2*2^-8 bound must refuse and fall back."""
+    rng = np.random.default_rng(5)
+    n, d, nq, k = 70_000, 1024, 8, 100
+    g = np.float32(2.0 ** -5)
+    down, up = np.float32(1 + 0.498 * 2.0 ** -7), np.float32(1 + 0.502 * 2.0 ** -7)
+    x = unit_rows(rng, n, d)
+    special = rng.permutation(n)[: 100 + 120 + 3000]
+    rows_a, rows_b, rows_f = special[:100], special[100:220], special[220:]
+
+    def row(value, nnz):
+        v = np.full(d, value, np.float32)
+        v[rng.permutation(d)[: d - nnz]] = 0.0
+        return v
+
+    for r in rows_a:
+        x[r] = row(g * down, 1024)
+    for r in rows_b:
+        x[r] = row(g * up, 1023)
+    for r in rows_f:
+        x[r] = row(g * up, 1017 + int(rng.integers(0, 2)))
+    q = np.tile(np.full(d, g * down, np.float32), (nq, 1))
+    exact = N().NativeIndex(d)
+    exact.add(x)
+    exact.set_tunable("batch_min", 0)
+    De, Ie = exact.search(q, k)
+    exact.close()
+    assert set(Ie[0].tolist()) == set(rows_a.tolist())       # the true top-100 is A
+    ix = N().NativeIndex(d, 0, N().STORE_BF16_MASTER, 0)
+    ix.add(x)
+    ix.set_tunable("batch_min", 2)
+    ix.set_tunable("batch_bf16", 1)
+    before = ix.batch_stats()
+    Db, Ib = ix.search(q, k)
+    served, fallbacks = (a - b for a, b in zip(ix.batch_stats(), before))
+    assert served == nq
+    assert np.array_equal(Ib, Ie) and np.array_equal(Db, De)
+    assert fallbacks == nq                                    # no query may be certified from the bf16 scores here
+    ix.close()
+
+
 @pytest.mark.parametrize("n,d,nq,k", [(150_000, 1024, 200, 100), (100_000, 768, 300, 50), (70_000, 96, 129, 10)])
 def test_cta_pair_kernel_equals_scan(n, d, nq, k):
     """The cta_group::2 variant (two SMs share one 256 x 256 tile, M = 256 MMAs issued by the leader CTA)."""

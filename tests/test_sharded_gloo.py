@@ -25,7 +25,8 @@ def _worker(rank: int, world: int, port: int, out_dir: str) -> None:
     import torch.distributed as dist
 
     from oracle import flat_ip as O
-    from photo_search_engine_b200 import _native, keys
+    from photo_search_engine_b200 import _native
+    from tests import _keys as keys
     from photo_search_engine_b200.sharded import ShardedIndex, shard_bounds
 
     dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
@@ -110,7 +111,7 @@ def test_sharded_search_over_gloo(tmp_path, world):
 
 
 def test_shard_bounds_and_keys():
-    from photo_search_engine_b200 import keys
+    from tests import _keys as keys
     from photo_search_engine_b200.sharded import shard_bounds
 
     assert shard_bounds(10, 4) == [0, 3, 6, 9, 10]
