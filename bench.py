@@ -393,7 +393,7 @@ def run_ours(args):
         ptr, ld, _dt = index.storage_device()
 
         class _Arena:
-            __cuda_array_interface__ = {"shape": (hi - lo, ld), "typestr": "<f4", "data": (ptr, True), "version": 2}
+            __cuda_array_interface__ = {"shape": (hi - lo, ld), "typestr": "<f4", "data": (ptr, False), "version": 2}
 
         arena = torch.as_tensor(_Arena(), device=device)
         first = -(-lo // P) * P

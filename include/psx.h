@@ -98,6 +98,23 @@ typedef struct psx_filter {
 /* Replaces faiss.IndexFlatIP(d) / faiss.IndexFlatL2(d) (utils/vector_store.py:72-81).
  * `device` is a CUDA ordinal.  Fails with PSX_ERR_CUDA if the device is absent or not sm_100. */
 int psx_create(int d, int metric, int store_dtype, int device, psx_index** out);
+/* ONE handle over several GPUs of one box, for the reference's process model: main.py:59-68 constructs a single
+ * VectorStore that core/searcher.py:78 and core/indexer.py:57 share, so the corpus is row-sharded BEHIND the handle
+ * instead of across processes.  `devices` lists n_devices CUDA ordinals (an ordinal may repeat: several shards on one
+ * GPU, used by the tests); devices[0] is the "home" that merges.  Rows are split in contiguous id ranges (re-split with
+ * device-to-device copies when appends unbalance them), every host-buffer entry point below works on the handle
+ * (add / sync / reserve / set_attrs / search / reconstruct / read_rows / reset / tunables), results are bit-identical
+ * to a single-device index.  The device-pointer entry points (psx_search_device, psx_search_batch_device,
+ * psx_search_exchange_device, psx_storage_device) are per-device calls and fail with PSX_ERR_STATE on such a handle;
+ * psx_add_device / psx_set_attrs_device accept a pointer on any device.  Needs peer access devices[i] -> devices[0].
+ * n_devices == 1 is psx_create. */
+int psx_create_sharded(int d, int metric, int store_dtype, int n_devices, const int* devices, psx_index** out);
+/* number of shards behind the handle (1 for psx_create), rows and device of each (arrays of `capacity` >= that number) */
+int psx_device_count(const psx_index* h);
+int psx_shard_rows(psx_index* h, int64_t* rows, int* devices, int capacity);
+/* multi-device handles: queries answered through the fused NVLink exchange / through event-ordered key lists, and
+ * fused exchanges that timed out (a device that never published; the query was re-run over the key-list path) */
+int psx_group_stats(psx_index* h, int64_t* fused, int64_t* keyed, int64_t* timeouts);
 /* Replaces dropping the faiss index object. */
 int psx_destroy(psx_index* h);
 /* Replaces re-creating the index in VectorStore.clear() (utils/vector_store.py:273-280). */
@@ -188,6 +205,12 @@ int64_t psx_exchange_bytes(void);
 int psx_search_exchange_device(psx_index* h, const float* q_dev, int64_t k, const psx_filter* filter, uint32_t id_base,
                                int rank, int world, const uint64_t* peer_bases, uint32_t seq, int phases,
                                float* out_scores_dev, int64_t* out_ids_dev, void* stream);
+/* The wait of the fused exchange is bounded (tunable "xchg_timeout_ms", default 20 s): a rank that never publishes
+ * does not hang or fault this GPU.  After the stream has been synchronised, *status is 0 when every exchange since
+ * the last call completed, else 1 + the first silent rank -- the outputs of that query are then undefined and the
+ * caller re-runs it over the collective path (psx_search_device keys + all-gather + psx_merge_keys_device).  Reading
+ * clears the word. */
+int psx_exchange_status(psx_index* h, int* status);
 
 /* On-device form of the numeric core of Searcher._hybrid_search (core/searcher.py:893-986) and
  * Searcher._distance_to_score (core/searcher.py:605-625) over the merged vector candidates

@@ -44,6 +44,10 @@ class PsxFilter(C.Structure):
 _P = C.c_void_p
 _SIGNATURES = [
     ("psx_create", C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(_P)]),
+    ("psx_create_sharded", C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(_P)]),
+    ("psx_device_count", C.c_int, [_P]),
+    ("psx_shard_rows", C.c_int, [_P, C.POINTER(C.c_int64), C.POINTER(C.c_int), C.c_int]),
+    ("psx_group_stats", C.c_int, [_P, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     ("psx_destroy", C.c_int, [_P]),
     ("psx_reset", C.c_int, [_P]),
     ("psx_ntotal", C.c_int64, [_P]),
@@ -66,6 +70,7 @@ _SIGNATURES = [
     ("psx_exchange_bytes", C.c_int64, []),
     ("psx_search_exchange_device", C.c_int, [_P, _P, C.c_int64, C.POINTER(PsxFilter), C.c_uint32, C.c_int, C.c_int, _P, C.c_uint32,
                                               C.c_int, _P, _P, _P]),
+    ("psx_exchange_status", C.c_int, [_P, C.POINTER(C.c_int)]),
     ("psx_hybrid_fuse_device", C.c_int, [C.c_int, C.c_int64, C.c_int64, _P, _P, _P, C.c_int64, _P, _P, _P, C.c_double, C.c_double,
                                           C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P, _P]),
     ("psx_reconstruct", C.c_int, [_P, C.c_int64, _P]),
@@ -122,16 +127,25 @@ def _ptr(a: np.ndarray) -> int:
 
 
 class NativeIndex:
-    """Thin RAII wrapper of one ``psx_index`` handle (one GPU)."""
+    """Thin RAII wrapper of one ``psx_index`` handle: one GPU (``device`` an int), or several GPUs of the box behind
+    the one handle (``device`` a sequence of ordinals, ``psx_create_sharded``; ``device[0]`` merges)."""
 
-    def __init__(self, d: int, metric: int = METRIC_IP, store_dtype: int = STORE_F32, device: int = 0) -> None:
+    def __init__(self, d: int, metric: int = METRIC_IP, store_dtype: int = STORE_F32, device=0) -> None:
         self._lib = load_library()
         self._h = _P()
-        check(self._lib.psx_create(int(d), int(metric), int(store_dtype), int(device), C.byref(self._h)))
+        devices = [int(device)] if isinstance(device, (int, np.integer)) else [int(x) for x in device]
+        if not devices:
+            raise ValueError("at least one device is needed")
+        if len(devices) == 1:
+            check(self._lib.psx_create(int(d), int(metric), int(store_dtype), devices[0], C.byref(self._h)))
+        else:
+            arr = (C.c_int * len(devices))(*devices)
+            check(self._lib.psx_create_sharded(int(d), int(metric), int(store_dtype), len(devices), arr, C.byref(self._h)))
         self.d = int(d)
         self.metric = int(metric)
         self.store_dtype = int(store_dtype)
-        self.device = int(device)
+        self.device = devices[0]
+        self.devices = tuple(devices)
 
     # -- lifecycle ---------------------------------------------------------------------
     def close(self) -> None:
@@ -205,12 +219,31 @@ class NativeIndex:
                                                    peer_bases.ctypes.data, int(seq), int(phases), out_scores_ptr or None,
                                                    out_ids_ptr or None, stream or None))
 
+    def exchange_status(self) -> int:
+        """0, or 1 + the rank whose keys never arrived in a fused exchange since the last call (clears the word)."""
+        v = C.c_int()
+        check(self._lib.psx_exchange_status(self._h, C.byref(v)))
+        return v.value
+
     def search_batch_device(self, q_ptr: int, nq: int, k: int, out_scores_ptr: int, out_ids_ptr: int, flags_ptr: int,
                             out_keys_ptr: int = 0, qnorm_max: float = 1.0, id_base: int = 0, stream: int = 0,
                             flt: Optional[PsxFilter] = None) -> None:
         fp = C.byref(flt) if flt is not None else None
         check(self._lib.psx_search_batch_device(self._h, q_ptr, int(nq), int(k), fp, float(qnorm_max), int(id_base), out_scores_ptr,
                                                 out_ids_ptr, out_keys_ptr or None, flags_ptr, stream or None))
+
+    def shard_rows(self):
+        """``[(device, rows), ...]`` of the shards behind the handle."""
+        n = int(self._lib.psx_device_count(self._h))
+        rows, devs = (C.c_int64 * n)(), (C.c_int * n)()
+        check(self._lib.psx_shard_rows(self._h, rows, devs, n))
+        return [(int(devs[i]), int(rows[i])) for i in range(n)]
+
+    def group_stats(self):
+        """multi-device handles: (queries through the fused exchange, through key lists, fused time-outs)."""
+        a, b, c = C.c_int64(), C.c_int64(), C.c_int64()
+        check(self._lib.psx_group_stats(self._h, C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
 
     def batch_stats(self):
         a, b = C.c_int64(), C.c_int64()

@@ -132,8 +132,53 @@ struct psx_index {
     int* hflags = nullptr;    // pinned [256]
     long long batch_fallbacks = 0, batch_queries = 0, mixed_queries = 0;
     unsigned long long* trace = nullptr;  // diagnostics: phase timestamps of the next scans (caller-owned)
+    // fused exchange: status word of merge_wait_kernel in host-mapped memory (0 = fine, 1 + r = rank r never published)
+    int* xstatus_host = nullptr;
+    int* xstatus_dev = nullptr;
+    // ---- multi-device group (psx_create_sharded): this handle owns one child index per device entry and no rows itself.
+    // Rows are split in contiguous id ranges: child s holds [s*quota, (s+1)*quota) of the rows in HBM, the last child also
+    // everything beyond (appends land there until the layout is rebalanced).  Child 0 is the "home": it merges.
+    std::vector<psx_index*> shards;
+    long long quota = 0;
+    long long shard_min_rows = 8192;     // never split a corpus into shards smaller than this (tunable "shard_min_rows")
+    unsigned char* gx = nullptr;         // home device: receive buffer of the fused exchange (psx_exchange_bytes())
+    uint32_t gseq = 0;
+    uint64_t* gkeys = nullptr;           // home device: [nq][active shards][kpad] key lists (batches, paging, mixed tier)
+    size_t gkeys_cap = 0;
+    cudaEvent_t g_merged[2] = {nullptr, nullptr};  // home stream: the merge of query i (slot i & 1) has completed
+    std::vector<cudaEvent_t> g_done;     // per child: its part of the current step is complete
+    std::vector<cudaEvent_t> g_h2d;      // per child: its copy out of the query staging is complete
+    std::vector<char> g_h2d_busy;
+    float* g_hq = nullptr;               // pinned (portable) staging of the queries
+    size_t g_hq_cap = 0;
+    int fault_skip_publish = -1;         // test hook (tunable): this shard never publishes to the fused exchange
+    long long xchg_timeout_ms = 0;       // tunable: bounded spin of the fused wait (0 = default, PSX_XCHG_TIMEOUT_MS or 20 s)
+    long long g_fused = 0, g_keyed = 0, g_timeouts = 0;  // queries served by the fused exchange / the key-list path / fused timeouts
     std::mutex mu;
 };
+static inline bool is_group(const psx_index* h) { return !h->shards.empty(); }
+#define NOT_ON_GROUP(h, what)                                                                                          \
+    do {                                                                                                               \
+        if (is_group(h)) return fail(PSX_ERR_STATE, what " is a single-device call; a multi-device handle is driven through the host-buffer API"); \
+    } while (0)
+
+static void group_destroy_parts(psx_index* g);
+static int group_reset(psx_index* g);
+static int group_reserve(psx_index* g, long long n);
+static int group_add_device(psx_index* g, const float* x_dev, long long n, int normalize, cudaStream_t st);
+static int group_set_attrs(psx_index* g, long long row0, const uint64_t* attrs, long long n, bool from_device, cudaStream_t st);
+static int group_read_rows(psx_index* g, long long row0, long long n, float* out);
+static int group_set_tunable(psx_index* g, const char* key, int value);
+
+// bounded spin of merge_wait_kernel: ~64 ns sleep + one system-scope load per poll.  PSX_XCHG_TIMEOUT_MS overrides (tests).
+static unsigned long long xchg_spin_limit(long long override_ms = 0) {
+    static const double env_ms = [] {
+        const char* e = getenv("PSX_XCHG_TIMEOUT_MS");
+        return e && *e ? atof(e) : 20000.0;
+    }();
+    const double ms = override_ms > 0 ? (double)override_ms : env_ms;
+    return (unsigned long long)std::max(1000.0, ms * 1e6 / 600.0);  // ~0.6 us per poll
+}
 
 static inline int scan_dtype(const psx_index* h) { return h->dtype == PSX_STORE_F32 ? PSX_STORE_F32 : PSX_STORE_BF16; }
 static inline bool has_fp32_rows(const psx_index* h) { return h->dtype != PSX_STORE_BF16; }
@@ -178,6 +223,16 @@ static int pow2ceil(long long v) {
     long long p = 1;
     while (p < v) p <<= 1;
     return (int)p;
+}
+
+static int ensure_xstatus(psx_index* h, int** dev) {
+    if (!h->xstatus_host) {
+        CU(cudaHostAlloc(&h->xstatus_host, sizeof(int), cudaHostAllocMapped | cudaHostAllocPortable));
+        *h->xstatus_host = 0;
+        CU(cudaHostGetDevicePointer(&h->xstatus_dev, h->xstatus_host, 0));
+    }
+    *dev = h->xstatus_dev;
+    return PSX_OK;
 }
 
 extern "C" int64_t psx_kpad(int64_t k) {
@@ -273,12 +328,21 @@ static void free_all(psx_index* h) {
     cudaFree(h->meps);
     cudaFree(h->bsample);
     cudaFreeHost(h->hflags);
+    cudaFreeHost(h->xstatus_host);
     if (h->last_ev) cudaEventDestroy(h->last_ev);
     if (h->stream) cudaStreamDestroy(h->stream);
 }
 
 extern "C" int psx_destroy(psx_index* h) {
     if (!h) return PSX_OK;
+    if (is_group(h)) {
+        {
+            std::lock_guard<std::mutex> lk(h->mu);
+            group_destroy_parts(h);
+        }
+        delete h;
+        return PSX_OK;
+    }
     {
         // wait for a call still running on another thread (the caller must not START new calls on a handle it destroys)
         std::lock_guard<std::mutex> lk(h->mu);
@@ -297,6 +361,7 @@ extern "C" int psx_metric(const psx_index* h) { return h ? h->metric : 0; }
 extern "C" int psx_reset(psx_index* h) {
     if (!h) return fail(PSX_ERR_INVALID, "null handle");
     std::lock_guard<std::mutex> lk(h->mu);
+    if (is_group(h)) return group_reset(h);
     DeviceGuard g(h->device);
     cudaDeviceSynchronize();
     cudaFree(h->x);
@@ -396,7 +461,41 @@ static int launch_pack(psx_index* h, const float* src_dev, long long row0, long 
     return PSX_OK;
 }
 
-// upload rows staged on the host (chunked through a bounded device bounce buffer)
+// upload host rows into the arena behind row h->n (chunked through a bounded device bounce buffer); the caller
+// holds h->mu (or owns h as the child of a group) and the device is current
+static int upload_host_rows(psx_index* h, const float* rows, long long rows_n) {
+    if (rows_n <= 0) return PSX_OK;
+    int rc = ensure_capacity(h, h->n + rows_n, false);
+    if (rc) return rc;
+    const long long chunk_rows = std::max<long long>(1, (256ll << 20) / ((long long)h->d * 4));
+    float* bounce = nullptr;
+    const long long brows = std::min(chunk_rows, rows_n);
+    if (cudaMalloc(&bounce, (size_t)brows * h->d * sizeof(float)) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(PSX_ERR_OOM, "cudaMalloc of the upload bounce buffer failed");
+    }
+    long long done = 0;
+    while (done < rows_n) {
+        const long long m = std::min(brows, rows_n - done);
+        cudaError_t e = cudaMemcpyAsync(bounce, rows + (size_t)done * h->d, (size_t)m * h->d * sizeof(float),
+                                        cudaMemcpyHostToDevice, h->stream);
+        if (e == cudaSuccess) {
+            rc = launch_pack(h, bounce, h->n + done, m, 0, h->stream);
+            if (rc == PSX_OK) e = cudaStreamSynchronize(h->stream);
+        }
+        if (e != cudaSuccess || rc != PSX_OK) {
+            cudaFree(bounce);
+            return rc ? rc : fail(PSX_ERR_CUDA, "upload failed: %s", cudaGetErrorString(e));
+        }
+        done += m;
+    }
+    cudaFree(bounce);
+    return PSX_OK;
+}
+
+static int group_place_host_rows(psx_index* g, const float* rows, long long rows_n);
+
+// move everything psx_add staged into HBM (single device: behind the arena's last row; group: to the tail shard(s))
 static int flush_pending(psx_index* h) {
     if (h->pending_n == 0) return PSX_OK;
     // take the staged rows; appends arriving from now on start a fresh staging vector
@@ -407,46 +506,16 @@ static int flush_pending(psx_index* h) {
         rows.swap(h->pending);
         rows_n = h->pending_n;
     }
-    auto put_back = [&]() {  // failure: the rows stay staged (in order, in front of whatever arrived meanwhile)
-        std::lock_guard<std::mutex> pk(h->pmu);
+    const int rc = is_group(h) ? group_place_host_rows(h, rows.data(), rows_n) : upload_host_rows(h, rows.data(), rows_n);
+    std::lock_guard<std::mutex> pk(h->pmu);
+    if (rc) {  // failure: the rows stay staged (in order, in front of whatever arrived meanwhile)
         rows.insert(rows.end(), h->pending.begin(), h->pending.end());
         h->pending.swap(rows);
-    };
-    int rc = ensure_capacity(h, h->n + rows_n, false);
-    if (rc) {
-        put_back();
         return rc;
     }
-    const long long chunk_rows = std::max<long long>(1, (256ll << 20) / ((long long)h->d * 4));
-    float* bounce = nullptr;
-    const long long brows = std::min(chunk_rows, rows_n);
-    if (cudaMalloc(&bounce, (size_t)brows * h->d * sizeof(float)) != cudaSuccess) {
-        cudaGetLastError();
-        put_back();
-        return fail(PSX_ERR_OOM, "cudaMalloc of the upload bounce buffer failed");
-    }
-    long long done = 0;
-    while (done < rows_n) {
-        const long long m = std::min(brows, rows_n - done);
-        cudaError_t e = cudaMemcpyAsync(bounce, rows.data() + (size_t)done * h->d, (size_t)m * h->d * sizeof(float),
-                                        cudaMemcpyHostToDevice, h->stream);
-        if (e == cudaSuccess) {
-            rc = launch_pack(h, bounce, h->n + done, m, 0, h->stream);
-            if (rc == PSX_OK) e = cudaStreamSynchronize(h->stream);
-        }
-        if (e != cudaSuccess || rc != PSX_OK) {
-            cudaFree(bounce);
-            put_back();
-            return rc ? rc : fail(PSX_ERR_CUDA, "upload failed: %s", cudaGetErrorString(e));
-        }
-        done += m;
-    }
-    cudaFree(bounce);
-    {
-        std::lock_guard<std::mutex> pk(h->pmu);
-        h->n += rows_n;  // n and pending_n move together under pmu: psx_ntotal never sees the rows twice or not at all
-        h->pending_n -= rows_n;
-    }
+    // n and pending_n move together under pmu: psx_ntotal never sees the rows twice or not at all
+    h->n += rows_n;  // (a group's n is the total over its children)
+    h->pending_n -= rows_n;
     return PSX_OK;
 }
 
@@ -484,6 +553,10 @@ extern "C" int psx_reserve(psx_index* h, int64_t n) {
     if (!h || n < 0) return fail(PSX_ERR_INVALID, "bad arguments to psx_reserve");
     std::lock_guard<std::mutex> lk(h->mu);
     DeviceGuard g(h->device);
+    if (is_group(h)) {
+        int rc = flush_pending(h);
+        return rc ? rc : group_reserve(h, n);
+    }
     return ensure_capacity(h, n, true);
 }
 
@@ -493,6 +566,7 @@ extern "C" int psx_add_device(psx_index* h, const float* x_dev, int64_t n, int n
     DeviceGuard g(h->device);
     int rc = flush_pending(h);
     if (rc) return rc;
+    if (is_group(h)) return group_add_device(h, x_dev, n, normalize, (cudaStream_t)stream);
     if ((unsigned long long)(h->n + n) >= 0xffffffffull) return fail(PSX_ERR_RANGE, "more than 2^32-1 rows");
     rc = ensure_capacity(h, h->n + n, false);
     if (rc) return rc;
@@ -510,6 +584,7 @@ extern "C" int psx_set_attrs(psx_index* h, int64_t row0, const uint64_t* attrs, 
     DeviceGuard g(h->device);
     int rc = flush_pending(h);
     if (rc) return rc;
+    if (is_group(h)) return group_set_attrs(h, row0, attrs, n, false, nullptr);
     if (row0 + n > h->n) return fail(PSX_ERR_RANGE, "attribute rows [%lld,%lld) exceed ntotal %lld", (long long)row0,
                                      (long long)(row0 + n), h->n.load());
     if (n == 0) return PSX_OK;
@@ -525,6 +600,7 @@ extern "C" int psx_set_attrs_device(psx_index* h, int64_t row0, const uint64_t* 
     DeviceGuard g(h->device);
     int rc = flush_pending(h);
     if (rc) return rc;
+    if (is_group(h)) return group_set_attrs(h, row0, attrs_dev, n, true, (cudaStream_t)stream);
     if (row0 + n > h->n) return fail(PSX_ERR_RANGE, "attribute rows exceed ntotal");
     cudaStream_t st = (cudaStream_t)stream;
     CU(cudaMemcpyAsync(h->attrs + row0, attrs_dev, (size_t)n * sizeof(uint64_t), cudaMemcpyDeviceToDevice, st));
@@ -642,7 +718,8 @@ static int launch_scan_variant(int device, int dtype, int metric, int ppl, bool 
 struct XchgArgs {
     int world, rank;
     uint32_t seq;
-    const uint64_t* bases;  // host array [world]: base address of every rank's exchange buffer
+    const uint64_t* bases;  // host array [targets]: base address of every receive buffer this shard publishes to
+    int targets;            // 0 = world (one process per GPU: every rank merges); 1 = only bases[0] merges (one process, G devices)
 };
 static size_t xchg_flag_offset() { return (size_t)2 * PSX_XCHG_MAX_WORLD * PSX_K_PASS_MAX * sizeof(uint64_t); }
 
@@ -712,7 +789,8 @@ static int launch_scan(psx_index* h, const float* q_dev, int k, const psx_filter
         p.xchg_world = xa->world;
         p.xchg_rank = xa->rank;
         p.xchg_seq = xa->seq;
-        for (int r = 0; r < xa->world; ++r) {
+        p.xchg_targets = xa->targets > 0 ? xa->targets : xa->targets < 0 ? 0 : xa->world;
+        for (int r = 0; r < p.xchg_targets; ++r) {
             p.xchg_recv[r] = (uint64_t*)(uintptr_t)xa->bases[r];
             p.xchg_flag[r] = (uint32_t*)(uintptr_t)(xa->bases[r] + xchg_flag_offset());
         }
@@ -765,10 +843,22 @@ static int make_map(CUtensorMap* map, const void* base, bool bf16, long long row
     return PSX_OK;
 }
 
+// survivors per query the threshold aims at.  (bf16 operands: the rounding bound 8.2e-3 |q||x| is ~0.26 sigma of the
+// score distribution of 1024-d unit vectors, i.e. ~2.6-3 x k rows lie within eps of the k-th score: 8k+128 keeps them
+// above theta with the margin 4k+64 gives the TF32 form.)
+static int batch_T(const psx_index* h, int k) {
+    return (h->dtype == PSX_STORE_BF16_MASTER && h->batch_bf16) ? 8 * k + 128 : 4 * k + 64;
+}
+// shape test of the tensor-core path: an fp32 inner-product index, and a corpus large enough that the threshold's
+// survivors are a small fraction of it (T <= n / 24: otherwise a sampled threshold is meaningless and the lists approach
+// the corpus itself -- such small corpora are latency-bound on the scan anyway)
+static bool batch_shape_ok(const psx_index* h, int64_t k) {
+    return h->metric == PSX_METRIC_IP && has_fp32_rows(h) && k >= 1 && k <= PSX_K_PASS_MAX && h->n >= 65536 && h->d >= 32 &&
+           (long long)batch_T(h, (int)k) * 24 <= h->n;
+}
 static bool batch_eligible(const psx_index* h, int64_t nq, int64_t k, const psx_filter* f) {
     (void)f;  // the predicate is applied in the epilogue (candidates) and in the sample (thresholds)
-    return h->metric == PSX_METRIC_IP && has_fp32_rows(h) && h->batch_min > 0 &&
-           nq >= h->batch_min && k <= PSX_K_PASS_MAX && h->n >= 65536 && h->d >= 32;
+    return h->batch_min > 0 && nq >= h->batch_min && batch_shape_ok(h, k);
 }
 
 static int ensure_batch_scratch(psx_index* h, size_t sample_floats, int cand_cap = BATCH_CAND_CAP_MIN) {
@@ -868,7 +958,8 @@ static int launch_gemm(psx_index* h, const CUtensorMap& mq, const CUtensorMap& m
 // One batch of nq <= 256 queries (device pointers).  flags_dev[qi] != 0 marks results that are not
 // proven exact; the caller re-runs those queries on the streaming scan.
 static int launch_batch(psx_index* h, const float* q_dev, int nq, int k, const psx_filter* f, uint32_t id_base, float qnorm_max,
-                        float* out_scores, long long* out_ids, uint64_t* out_keys, int* flags_dev, cudaStream_t st) {
+                        float* out_scores, long long* out_ids, uint64_t* out_keys, int* flags_dev, cudaStream_t st,
+                        long long keys_stride = 0) {
     const int MT = nq > GEMM_M ? 2 : 1;
     const bool pair = MT == 2 && h->batch_pair;
     const int BATCH_BN = batch_bn(MT, pair);
@@ -878,12 +969,21 @@ static int launch_batch(psx_index* h, const float* q_dev, int nq, int k, const p
     // number of rows above the sample's 16th score is ~ T * Gamma(16)/16: it undercuts k + (rows within eps of
     // the k-th) with probability ~3e-5 per query at k = 100 (8 sample scores and T = 3k+48 failed 2.7 % of the
     // queries of a 10M-row corpus, each of which costs a full scan).
-    // (bf16 operands: the rounding bound 8.2e-3 |q||x| is ~0.26 sigma of the score distribution of 1024-d unit vectors, i.e.
-    // ~2.6-3 x k rows lie within eps of the k-th score: T = 8k+128 keeps them above theta with the same margin)
-    const int T = (h->dtype == PSX_STORE_BF16_MASTER && h->batch_bf16) ? 8 * k + 128 : 4 * k + 64;
-    int tile_step = T / 16;
+    const int T = batch_T(h, k);
+    // The sample: every tile_step-th tile, and of a visited tile only the first sample_cols rows, sized so that about
+    // SAMPLE_RANK sample rows score above the threshold that T rows of the corpus pass.  A sample CTA keeps its 8 best
+    // scores per query, so a CTA must not see more than a few rows above theta: narrow the columns when T/n is large
+    // (small corpora with a large k) and never give one CTA more than its share.
+    constexpr double SAMPLE_RANK = 16.0;
+    const double frac = (double)T / (double)h->n;  // fraction of the rows above theta
+    int sample_cols = 256;
+    while (sample_cols > 32 && frac * sample_cols > 1.5) sample_cols >>= 1;
+    if (sample_cols > BATCH_BN) sample_cols = BATCH_BN;
+    const double want_rows = SAMPLE_RANK / frac;
+    int sample_tiles = (int)std::min<double>(num_tiles, std::max(1.0, want_rows / sample_cols + 0.5));
+    int tile_step = num_tiles / sample_tiles;
     if (tile_step < 1) tile_step = 1;
-    const int sample_tiles = (num_tiles + tile_step - 1) / tile_step;
+    sample_tiles = (num_tiles + tile_step - 1) / tile_step;
     const int grid_s = pair ? std::min(h->sm_count / 2, sample_tiles) : std::min(h->sm_count, sample_tiles);
     const int sample_ld = grid_s * SAMPLE_KEEP;  // every sample CTA (pair) leaves its 8 best scores per query
     const int cand_cap = batch_cand_cap(T);
@@ -921,6 +1021,7 @@ static int launch_batch(psx_index* h, const float* q_dev, int nq, int k, const p
     gp.cand_cap = cand_cap;
     gp.sample_scores = h->bsample;
     gp.sample_ld = sample_ld;
+    gp.sample_cols = sample_cols;
     if (f && f->flags) {
         gp.attrs = h->attrs;
         gp.f = *f;
@@ -941,7 +1042,10 @@ static int launch_batch(psx_index* h, const float* q_dev, int nq, int k, const p
     if (rc) return rc;
     DBG_SYNC(st, "gemm_filter_kernel(sample)");
     bt.mark("sample pass");
-    const long long sample_rows = std::min<long long>(h->n, (long long)sample_tiles * BATCH_BN);
+    // rows actually sampled: sample_cols of every visited tile (the last tile may be short)
+    long long sample_rows = 0;
+    for (int t = 0; t < num_tiles; t += tile_step)
+        sample_rows += std::max<long long>(0, std::min<long long>(sample_cols, h->n - (long long)t * BATCH_BN));
     int rank = (int)((double)T * (double)sample_rows / (double)h->n + 0.5);
     if (rank < 2) rank = 2;
     theta_kernel<<<nq, 256, 0, st>>>(h->bsample, sample_ld, sample_ld, rank, h->btheta, h->bcount);
@@ -974,7 +1078,7 @@ static int launch_batch(psx_index* h, const float* q_dev, int nq, int k, const p
     const float eps_coef = bf ? 8.2e-3f : 2.2e-3f;
     rescore_select_kernel<<<nq, 512, smem, st>>>(fp32_rows(h), fld, h->d, h->n, q_dev, k, kpad, h->bcand, h->bcount,
                                                  cand_cap, h->btheta, eps_coef, h->dmax_sumsq, nullptr, id_base, out_scores, out_ids,
-                                                 out_keys, flags_dev);
+                                                 out_keys, keys_stride > 0 ? keys_stride : kpad, flags_dev);
     g_launches++;
     CU(cudaGetLastError());
     DBG_SYNC(st, "rescore_select_kernel");
@@ -1014,7 +1118,7 @@ static int launch_mixed(psx_index* h, const float* q_dev, int k, const psx_filte
         ready[h->device].store(true);
     }
     rescore_select_kernel<<<1, 512, smem, st>>>((const float*)h->xm, h->ldm, h->d, h->n, q_dev, k, kpad, h->bcand, h->bcount, h->bcand_cap,
-                                                h->btheta, 0.f, h->dmax_sumsq, h->meps, id_base, out_scores, out_ids, out_keys, h->bflags);
+                                                h->btheta, 0.f, h->dmax_sumsq, h->meps, id_base, out_scores, out_ids, out_keys, kpad, h->bflags);
     g_launches++;
     CU(cudaGetLastError());
     h->mixed_queries++;
@@ -1050,6 +1154,7 @@ extern "C" int psx_search_device(psx_index* h, const float* q_dev, int64_t nq, i
                                  void* stream) {
     if (!h || !q_dev || nq < 0) return fail(PSX_ERR_INVALID, "bad arguments to psx_search_device");
     if (k < 1 || k > PSX_K_PASS_MAX) return fail(PSX_ERR_INVALID, "k=%lld not in [1,%d]", (long long)k, PSX_K_PASS_MAX);
+    NOT_ON_GROUP(h, "psx_search_device");
     std::lock_guard<std::mutex> lk(h->mu);
     DeviceGuard g(h->device);
     int rc = flush_pending(h);
@@ -1080,6 +1185,7 @@ extern "C" int psx_search_exchange_device(psx_index* h, const float* q_dev, int6
     if (world < 1 || world > PSX_XCHG_MAX_WORLD || rank < 0 || rank >= world || seq == 0)
         return fail(PSX_ERR_INVALID, "exchange needs 1 <= world <= %d, 0 <= rank < world, seq >= 1", PSX_XCHG_MAX_WORLD);
     if (k < 1 || k > PSX_K_PASS_MAX) return fail(PSX_ERR_INVALID, "k=%lld not in [1,%d]", (long long)k, PSX_K_PASS_MAX);
+    NOT_ON_GROUP(h, "psx_search_exchange_device");
     if (h->dtype == PSX_STORE_BF16_MASTER)
         return fail(PSX_ERR_STATE, "the fused exchange publishes the scan's own keys; a bf16+master index exchanges through psx_search_device keys");
     std::lock_guard<std::mutex> lk(h->mu);
@@ -1088,7 +1194,7 @@ extern "C" int psx_search_exchange_device(psx_index* h, const float* q_dev, int6
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     if ((rc = enter_stream(h, st))) return rc;
-    XchgArgs xa{world, rank, seq, peer_bases};
+    XchgArgs xa{world, rank, seq, peer_bases, 0};
     if ((phases & 1) && (rc = launch_scan(h, q_dev, (int)k, filter, id_base, nullptr, nullptr, nullptr, nullptr, st, &xa))) return rc;
     if (!(phases & 2)) return leave_stream(h, st);
     const int kpad = (int)psx_kpad(k);
@@ -1101,8 +1207,11 @@ extern "C" int psx_search_exchange_device(psx_index* h, const float* q_dev, int6
         ready[h->device].store(true);
     }
     const uint64_t mine = peer_bases[rank];
+    int* status_dev = nullptr;
+    if ((rc = ensure_xstatus(h, &status_dev))) return rc;
     merge_wait_kernel<<<1, 256, smem, st>>>((const uint64_t*)(uintptr_t)mine, (const uint32_t*)(uintptr_t)(mine + xchg_flag_offset()), world,
-                                           seq, (int)k, kpad, np, h->metric, out_scores_dev, (long long*)out_ids_dev);
+                                           seq, (int)k, kpad, np, h->metric, out_scores_dev, (long long*)out_ids_dev, nullptr, status_dev,
+                                           xchg_spin_limit(h->xchg_timeout_ms));
     g_launches++;
     CU(cudaGetLastError());
     return leave_stream(h, st);
@@ -1113,12 +1222,14 @@ extern "C" int psx_search_batch_device(psx_index* h, const float* q_dev, int64_t
                                        uint64_t* out_keys_dev, int* flags_dev, void* stream) {
     if (!h || !q_dev || !out_scores_dev || !out_ids_dev || !flags_dev || nq < 1)
         return fail(PSX_ERR_INVALID, "bad arguments to psx_search_batch_device");
+    NOT_ON_GROUP(h, "psx_search_batch_device");
     std::lock_guard<std::mutex> lk(h->mu);
     DeviceGuard g(h->device);
     int rc = flush_pending(h);
     if (rc) return rc;
-    if (k < 1 || k > PSX_K_PASS_MAX || h->metric != PSX_METRIC_IP || !has_fp32_rows(h) || h->n < 65536 || h->d < 32)
-        return fail(PSX_ERR_STATE, "tensor-core batch path needs an fp32 inner-product index with >= 65536 rows, d >= 32, k <= %d", PSX_K_PASS_MAX);
+    if (!batch_shape_ok(h, k))
+        return fail(PSX_ERR_STATE, "tensor-core batch path needs an fp32 inner-product index with >= max(65536, 24 * (4k+64)) rows, d >= 32, k <= %d",
+                    PSX_K_PASS_MAX);
     cudaStream_t st = (cudaStream_t)stream;
     if ((rc = enter_stream(h, st))) return rc;
     const int64_t kpad = psx_kpad(k);
@@ -1149,7 +1260,7 @@ extern "C" int psx_merge_keys_device(int device, const uint64_t* keys_dev, int64
     if (cap_lists < 2) cap_lists = 2;
     const size_t smem = (size_t)cap_lists * kpad * 8;
     merge_keys_kernel<<<(unsigned)nq, 256, smem, (cudaStream_t)stream>>>(keys_dev, (int)nlists, (int)k, kpad, cap_lists, metric,
-                                                                       out_scores_dev, (long long*)out_ids_dev);
+                                                                       out_scores_dev, (long long*)out_ids_dev, nullptr);
     g_launches++;
     CU(cudaGetLastError());
     return PSX_OK;
@@ -1198,7 +1309,7 @@ static int ensure_io(psx_index* h, size_t qfloats, size_t outs) {
 
 // Host-buffer batch search through the tensor-core path; unproven queries are re-run on the scan.
 static int search_batched_host(psx_index* h, const float* q, int64_t nq, int64_t kk, int64_t k, const psx_filter* filter,
-                               float* out_scores, int64_t* out_ids) {
+                               uint32_t id_base, float* out_scores, int64_t* out_ids) {
     int rc;
     cudaStream_t st = h->stream;
     if ((rc = ensure_batch_scratch(h, 0))) return rc;  // h->bflags / h->hflags must exist before they are passed on
@@ -1215,7 +1326,7 @@ static int search_batched_host(psx_index* h, const float* q, int64_t nq, int64_t
             qn2 = std::max(qn2, (float)acc);
         }
         CU(cudaMemcpyAsync(h->dq, h->hq, (size_t)gq * h->d * sizeof(float), cudaMemcpyHostToDevice, st));
-        if ((rc = launch_batch(h, h->dq, gq, (int)kk, filter, 0, sqrtf(qn2) * 1.0001f, h->dscores, h->dids, nullptr, h->bflags, st)))
+        if ((rc = launch_batch(h, h->dq, gq, (int)kk, filter, id_base, sqrtf(qn2) * 1.0001f, h->dscores, h->dids, nullptr, h->bflags, st)))
             return rc;
         CU(cudaMemcpyAsync(h->hflags, h->bflags, gq * sizeof(int), cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
@@ -1223,7 +1334,7 @@ static int search_batched_host(psx_index* h, const float* q, int64_t nq, int64_t
         for (int qi = 0; qi < gq; ++qi) {
             if (!h->hflags[qi]) continue;
             h->batch_fallbacks++;
-            rc = launch_exact_scan(h, h->dq + (size_t)qi * h->d, (int)kk, filter, 0, nullptr, h->dscores + (size_t)qi * kk,
+            rc = launch_exact_scan(h, h->dq + (size_t)qi * h->d, (int)kk, filter, id_base, nullptr, h->dscores + (size_t)qi * kk,
                                    h->dids + (size_t)qi * kk, nullptr, st);
             if (rc) return rc;
         }
@@ -1244,15 +1355,14 @@ static int search_batched_host(psx_index* h, const float* q, int64_t nq, int64_t
     return leave_stream(h, st);
 }
 
-extern "C" int psx_search(psx_index* h, const float* q, int64_t nq, int64_t k, const psx_filter* filter, float* out_scores,
-                          int64_t* out_ids) {
-    if (!h || !q || !out_scores || !out_ids || nq < 0) return fail(PSX_ERR_INVALID, "bad arguments to psx_search");
-    if (k < 1) return fail(PSX_ERR_INVALID, "k=%lld must be >= 1", (long long)k);
-    if (nq == 0) return PSX_OK;
-    std::lock_guard<std::mutex> lk(h->mu);
-    DeviceGuard g(h->device);
-    int rc = flush_pending(h);
-    if (rc) return rc;
+static int group_search(psx_index* g, const float* q, int64_t nq, int64_t k, const psx_filter* filter, float* out_scores,
+                        int64_t* out_ids);
+
+// Host-buffer search of ONE device's rows (ids reported as id_base + row).  The caller holds h->mu (or owns h as
+// the child of a group), the device is current and nothing is staged.
+static int search_single(psx_index* h, const float* q, int64_t nq, int64_t k, const psx_filter* filter, uint32_t id_base,
+                         float* out_scores, int64_t* out_ids) {
+    int rc;
     const float empty = h->metric == PSX_METRIC_L2 ? INFINITY : -INFINITY;
     if (h->n == 0) {
         for (int64_t i = 0; i < nq * k; ++i) {
@@ -1263,7 +1373,7 @@ extern "C" int psx_search(psx_index* h, const float* q, int64_t nq, int64_t k, c
     }
     // results beyond ntotal can never be filled: scan for min(k, n) and pad on the host
     const int64_t kk = std::min<int64_t>(k, h->n);
-    if (batch_eligible(h, nq, kk, filter)) return search_batched_host(h, q, nq, kk, k, filter, out_scores, out_ids);
+    if (batch_eligible(h, nq, kk, filter)) return search_batched_host(h, q, nq, kk, k, filter, id_base, out_scores, out_ids);
     const int64_t pages = (kk + PSX_K_PASS_MAX - 1) / PSX_K_PASS_MAX;
     // per-query stride of the device outputs
     const int64_t kslot = pages == 1 ? psx_kpad(kk) : pages * PSX_K_PASS_MAX;
@@ -1282,7 +1392,7 @@ extern "C" int psx_search(psx_index* h, const float* q, int64_t nq, int64_t k, c
                 const size_t off = (size_t)qi * kslot + (size_t)pg * PSX_K_PASS_MAX;
                 // page pg continues strictly below the last key of page pg-1 (a full page)
                 const uint64_t* ceil_ptr = pg ? h->dkeys + off - 1 : nullptr;
-                rc = launch_query(h, h->dq + qi * h->d, kp, filter, 0, ceil_ptr, h->dscores + off, h->dids + off,
+                rc = launch_query(h, h->dq + qi * h->d, kp, filter, id_base, ceil_ptr, h->dscores + off, h->dids + off,
                                   h->dkeys + off, st);
                 if (rc) return rc;
             }
@@ -1302,6 +1412,19 @@ extern "C" int psx_search(psx_index* h, const float* q, int64_t nq, int64_t k, c
         }
     }
     return leave_stream(h, st);
+}
+
+extern "C" int psx_search(psx_index* h, const float* q, int64_t nq, int64_t k, const psx_filter* filter, float* out_scores,
+                          int64_t* out_ids) {
+    if (!h || !q || !out_scores || !out_ids || nq < 0) return fail(PSX_ERR_INVALID, "bad arguments to psx_search");
+    if (k < 1) return fail(PSX_ERR_INVALID, "k=%lld must be >= 1", (long long)k);
+    if (nq == 0) return PSX_OK;
+    std::lock_guard<std::mutex> lk(h->mu);
+    DeviceGuard g(h->device);
+    int rc = flush_pending(h);
+    if (rc) return rc;
+    if (is_group(h)) return group_search(h, q, nq, k, filter, out_scores, out_ids);
+    return search_single(h, q, nq, k, filter, 0, out_scores, out_ids);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1344,6 +1467,7 @@ extern "C" int psx_read_rows(psx_index* h, int64_t row0, int64_t n, float* out) 
     int rc = flush_pending(h);
     if (rc) return rc;
     if (row0 + n > h->n) return fail(PSX_ERR_RANGE, "rows [%lld,%lld) exceed ntotal %lld", (long long)row0, (long long)(row0 + n), h->n.load());
+    if (is_group(h)) return group_read_rows(h, row0, n, out);
     return read_rows_locked(h, row0, n, out);
 }
 
@@ -1362,11 +1486,13 @@ extern "C" int psx_reconstruct(psx_index* h, int64_t id, float* out) {
     DeviceGuard g(h->device);
     int rc = flush_pending(h);
     if (rc) return rc;
+    if (is_group(h)) return group_read_rows(h, id, 1, out);
     return read_rows_locked(h, id, 1, out);
 }
 
 extern "C" int psx_storage_device(psx_index* h, const void** rows_dev, int64_t* ld_elems, int* store_dtype) {
     if (!h) return fail(PSX_ERR_INVALID, "null handle");
+    NOT_ON_GROUP(h, "psx_storage_device");
     std::lock_guard<std::mutex> lk(h->mu);
     DeviceGuard g(h->device);
     int rc = flush_pending(h);
@@ -1425,15 +1551,32 @@ extern "C" int psx_hybrid_fuse_device(int device, int64_t nq, int64_t kv, const 
     return PSX_OK;
 }
 
+extern "C" int psx_exchange_status(psx_index* h, int* status) {
+    if (!h || !status) return fail(PSX_ERR_INVALID, "bad arguments to psx_exchange_status");
+    std::lock_guard<std::mutex> lk(h->mu);
+    *status = h->xstatus_host ? *h->xstatus_host : 0;
+    if (h->xstatus_host) *h->xstatus_host = 0;
+    return PSX_OK;
+}
+
 extern "C" int psx_batch_stats(psx_index* h, int64_t* queries, int64_t* fallbacks) {
     if (!h) return fail(PSX_ERR_INVALID, "null handle");
-    if (queries) *queries = h->batch_queries;
-    if (fallbacks) *fallbacks = h->batch_fallbacks;
+    long long bq = h->batch_queries, bf = h->batch_fallbacks;
+    // a group counts a query once (every child serves every query of a batch) and a fallback per child re-run
+    if (is_group(h)) {
+        for (psx_index* c : h->shards) {
+            bq = std::max(bq, (long long)c->batch_queries);
+            bf += c->batch_fallbacks;
+        }
+    }
+    if (queries) *queries = bq;
+    if (fallbacks) *fallbacks = bf;
     return PSX_OK;
 }
 
 extern "C" int psx_set_trace_device(psx_index* h, uint64_t* trace_dev) {
     if (!h) return fail(PSX_ERR_INVALID, "null handle");
+    NOT_ON_GROUP(h, "psx_set_trace_device");
     std::lock_guard<std::mutex> lk(h->mu);
     h->trace = (unsigned long long*)trace_dev;
     return PSX_OK;
@@ -1465,8 +1608,23 @@ extern "C" int psx_set_tunable(psx_index* h, const char* key, int value) {
         h->batch_bf16 = value > 0;
     } else if (!strcmp(key, "batch_min")) {  // smallest nq sent to the tensor-core path; 0 disables it
         h->batch_min = value < 0 ? 4 : value;
+    } else if (!strcmp(key, "xchg_timeout_ms")) {  // bounded wait of the fused exchange's merge kernel
+        h->xchg_timeout_ms = value > 0 ? value : 0;
+    } else if (!strcmp(key, "fault_skip_publish")) {  // test hook: shard `value` of a multi-device handle stays silent
+        h->fault_skip_publish = value;
+        return PSX_OK;
+    } else if (!strcmp(key, "shard_min_rows") && is_group(h)) {
+        // multi-device handles: a corpus is never split into shards smaller than this (default 8192)
+    } else if (!strcmp(key, "shard_min_rows")) {
+        return PSX_OK;  // meaningless on one device; accepted so that callers need not care
     } else {
         return fail(PSX_ERR_INVALID, "unknown tunable '%s'", key);
     }
+    if (is_group(h)) return group_set_tunable(h, key, value);
     return PSX_OK;
 }
+
+// ------------------------------------------------------------------------------------------
+// one handle over several devices (psx_create_sharded)
+// ------------------------------------------------------------------------------------------
+#include "psx_group.cuh"

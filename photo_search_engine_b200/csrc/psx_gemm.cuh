@@ -53,6 +53,7 @@ struct GemmParams {
     int cand_cap;
     float* sample_scores;    // [nq][sample_ld] (MODE_SAMPLE): SAMPLE_KEEP scores per sample CTA (pair)
     int sample_ld;
+    int sample_cols;         // MODE_SAMPLE: only the first sample_cols rows of a visited tile are sampled (multiple of 32)
     const uint64_t* attrs;   // EXIF words [n], or nullptr: rows failing `f` are neither sampled nor kept
     psx_filter f;
 };
@@ -297,8 +298,9 @@ gemm_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
             for (int m = 0; m < MT; ++m) {
                 const int qi = m * GEMM_M + qlane;
                 const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(a * ACC_COLS + m * BN);
+                const int nblocks = p.mode == GEMM_MODE_FILTER ? BN / 32 : p.sample_cols / 32;
 #pragma unroll 1
-                for (int c = 0; c < BN / 32; ++c) {
+                for (int c = 0; c < nblocks; ++c) {
                     uint32_t r[32];
                     tmem_ld_32x32(taddr + c * 32, r);
                     if (p.mode == GEMM_MODE_FILTER) {
@@ -538,8 +540,9 @@ gemm_filter_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
             tc_fence_after();
             const long long row0 = (long long)t * BN;
             const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(a * BN);
+            const int nblocks = p.mode == GEMM_MODE_FILTER ? BN / 32 : p.sample_cols / 32;
 #pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
+            for (int c = 0; c < nblocks; ++c) {
                 uint32_t r[32];
                 tmem_ld_32x32(taddr + c * 32, r);
                 if (p.mode == GEMM_MODE_FILTER) {
@@ -594,34 +597,23 @@ gemm_filter_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
 }
 
 // ---- theta: per query, the rank-th largest of its sample ------------------------------------------------------
-// One CTA per query over the ns = (sample CTAs) x 8 kept scores.  Every thread keeps the three largest of
-// its strided share (ns <= 1184: at most 5 values each); the 768 survivors are sorted and the element at
-// the requested rank is taken.  Approximate by design: the threshold only has to land between the k-th and
-// roughly the (cand_cap)-th score -- exactness comes from the proof obligation checked after the exact re-score.
+// One CTA per query over the ns = (sample CTAs) x 8 kept scores (ns <= 1184 <= THETA_SORT): all of them are
+// sorted and the element at the requested rank is taken.  Approximate by design: the threshold only has to land
+// between the k-th and roughly the (cand_cap)-th score -- exactness comes from the proof obligation checked after
+// the exact re-score.
+constexpr int THETA_SORT = 2048;
 __global__ void __launch_bounds__(256) theta_kernel(const float* __restrict__ sample, int sample_ld, int ns, int rank,
                                                     float* __restrict__ theta, int* __restrict__ cand_count) {
-    __shared__ uint64_t keys[1024];
+    __shared__ uint64_t keys[THETA_SORT];
     const int qi = blockIdx.x;
     const float* s = sample + (size_t)qi * sample_ld;
-    float b0 = -INFINITY, b1 = -INFINITY, b2 = -INFINITY;
-    for (int i = threadIdx.x; i < ns; i += blockDim.x) {
-        const float v = s[i];
-        if (v > b2) {
-            b2 = v;
-            if (b2 > b1) { const float t = b1; b1 = b2; b2 = t; }
-            if (b1 > b0) { const float t = b0; b0 = b1; b1 = t; }
-        }
-    }
-    keys[3 * threadIdx.x] = make_key(b0, 3 * threadIdx.x);
-    keys[3 * threadIdx.x + 1] = make_key(b1, 3 * threadIdx.x + 1);
-    keys[3 * threadIdx.x + 2] = make_key(b2, 3 * threadIdx.x + 2);
-    for (int i = 3 * blockDim.x + threadIdx.x; i < 1024; i += blockDim.x) keys[i] = 0ull;
+    for (int i = threadIdx.x; i < THETA_SORT; i += blockDim.x) keys[i] = i < ns ? make_key(s[i], (uint32_t)i) : 0ull;
     __syncthreads();
-    block_bitonic_sort_desc(keys, 1024);
+    block_bitonic_sort_desc(keys, THETA_SORT);
     if (threadIdx.x == 0) {
         int r = rank < 1 ? 1 : rank;
-        if (r > 768) r = 768;
-        float v = keys[r - 1] ? key_score(keys[r - 1]) : -INFINITY;
+        if (r > ns) r = ns;
+        float v = (r >= 1 && keys[r - 1]) ? key_score(keys[r - 1]) : -INFINITY;
         if (!(v > -INFINITY)) v = -INFINITY;  // fewer samples than the rank: take everything
         theta[qi] = v;
         cand_count[qi] = 0;
@@ -640,7 +632,7 @@ rescore_select_kernel(const float* __restrict__ x, int ld, int d, long long n, c
                       const uint32_t* __restrict__ cand_ids, const int* __restrict__ cand_count, int cand_cap,
                       const float* __restrict__ theta, float eps_coef, const float* __restrict__ max_sumsq,
                       const float* __restrict__ eps_dev, uint32_t id_base,
-                      float* out_scores, long long* out_ids, uint64_t* out_keys, int* flags) {
+                      float* out_scores, long long* out_ids, uint64_t* out_keys, long long keys_stride, int* flags) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     uint64_t* keys = reinterpret_cast<uint64_t*>(smem_raw);     // [np]
     const int qi = blockIdx.x;
@@ -677,8 +669,10 @@ rescore_select_kernel(const float* __restrict__ x, int ld, int d, long long n, c
     __syncthreads();
     block_bitonic_sort_desc(keys, np);
     const int kk = k;
-    block_emit_results(keys, kk, kpad, PSX_METRIC_IP, out_scores + (size_t)qi * k, out_ids + (size_t)qi * k,
-                       out_keys ? out_keys + (size_t)qi * kpad : nullptr);
+    // keys_stride: distance between two queries' key lists (kpad, or world * kpad when the lists of several shards
+    // interleave in one buffer -- possibly peer memory on the merging GPU)
+    block_emit_results(keys, kk, kpad, PSX_METRIC_IP, out_scores ? out_scores + (size_t)qi * k : nullptr,
+                       out_ids ? out_ids + (size_t)qi * k : nullptr, out_keys ? out_keys + (size_t)qi * keys_stride : nullptr);
     if (threadIdx.x == 0) {
         int bad = 0;
         if (raw_count > cand_cap) bad = 1;                                   // list overflow: survivors were dropped

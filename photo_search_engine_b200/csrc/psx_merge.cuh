@@ -71,26 +71,42 @@ __global__ void __launch_bounds__(256) filter_list_kernel(const uint64_t* __rest
 }
 
 // K4 fused, receiving side: wait until every rank's list for query `seq` has landed in this GPU's
-// receive buffer, then select the global top-k.  One CTA.  The spin is bounded (a dead peer becomes
-// a trap, not a hung GPU).
+// receive buffer, then select the global top-k.  One CTA.  The spin is bounded: a peer that never
+// publishes (dead process, faulted GPU) does not hang this GPU.  With a `status` word (host-mapped
+// memory) the kernel then reports the timeout there and returns without a result -- the context stays
+// healthy and the host re-runs the query over the collective path; without one it traps.
 __global__ void __launch_bounds__(256, 1)
 merge_wait_kernel(const uint64_t* __restrict__ recv, const uint32_t* flags, int world, uint32_t seq, int k, int kpad, int cap_keys,
-                  int metric, float* out_scores, long long* out_ids) {
+                  int metric, float* out_scores, long long* out_ids, uint64_t* out_keys, int* status, unsigned long long spin_limit) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     uint64_t* buf = reinterpret_cast<uint64_t*>(smem_raw);
+    __shared__ int s_timeout;
     // the next query's scan may start streaming now: it touches nothing this merge reads, and it publishes only
     // after its own pdl_wait(), i.e. after this kernel has completed
     pdl_launch_dependents();
+    if (threadIdx.x == 0) s_timeout = 0;
+    __syncthreads();
     const int slot = (int)(seq & 1u);
     if ((int)threadIdx.x < world) {
         const uint32_t* f = flags + slot * PSX_XCHG_MAX_WORLD + threadIdx.x;
         unsigned long long spins = 0;
         while (ld_acquire_sys_u32(f) != seq) {
             __nanosleep(64);
-            if (++spins > (1ull << 26)) __trap();
+            if (++spins > spin_limit) {
+                if (!status) __trap();
+                s_timeout = 1 + (int)threadIdx.x;
+                break;
+            }
         }
     }
     __syncthreads();
+    if (s_timeout) {
+        if (threadIdx.x == 0) {
+            *status = s_timeout;  // 1 + a rank that did not publish
+            __threadfence_system();
+        }
+        return;
+    }
     const uint64_t* lists = recv + (size_t)slot * world * PSX_K_PASS_MAX;
     // lists are PSX_K_PASS_MAX apart; compact them to a kpad stride view by reading through an index map
     // (block_select_from_lists expects stride kpad): gather the heads into shared memory first
@@ -105,19 +121,19 @@ merge_wait_kernel(const uint64_t* __restrict__ recv, const uint32_t* flags, int 
     __syncthreads();
     (void)cap_keys;
     block_bitonic_sort_desc(buf, np);
-    block_emit_results(buf, k, kpad, metric, out_scores, out_ids, nullptr);
+    block_emit_results(buf, k, kpad, metric, out_scores, out_ids, out_keys);
 }
 
 // Standalone merge (K4 final merge of all-gathered shard lists): one CTA per query.
 __global__ void __launch_bounds__(256, 1)
 merge_keys_kernel(const uint64_t* __restrict__ keys, int nlists, int k, int kpad, int cap_lists, int metric,
-                  float* out_scores, long long* out_ids) {
+                  float* out_scores, long long* out_ids, uint64_t* out_keys) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     uint64_t* buf = reinterpret_cast<uint64_t*>(smem_raw);
     pdl_launch_dependents();  // see merge_wait_kernel
     const size_t qi = blockIdx.x;
     block_select_from_lists(keys + qi * (size_t)nlists * kpad, nlists, k, kpad, buf, cap_lists * kpad);
-    block_emit_results(buf, k, kpad, metric, out_scores + qi * k, out_ids + qi * k, nullptr);
+    block_emit_results(buf, k, kpad, metric, out_scores + qi * k, out_ids + qi * k, out_keys ? out_keys + qi * kpad : nullptr);
 }
 
 }  // namespace psx

@@ -63,6 +63,8 @@ struct ScanParams {
     int static_batch;           // units per statically dealt batch (and cap of a dynamic one)
     int dyn_tail;               // 0 = deal everything statically
     int xchg_world, xchg_rank;
+    int xchg_targets;      // receive buffers this shard publishes to: xchg_recv[0 .. xchg_targets) (all ranks when one
+                           // process per GPU; only the merging device when one process drives every GPU)
     uint32_t xchg_seq;
     uint64_t* xchg_recv[PSX_XCHG_MAX_WORLD];   // peer p: [2 parities][world][PSX_K_PASS_MAX] keys
     uint32_t* xchg_flag[PSX_XCHG_MAX_WORLD];   // peer p: [2 parities][PSX_XCHG_MAX_WORLD] sequence numbers
@@ -681,13 +683,13 @@ __global__ void __launch_bounds__(PSX_MAX_THREADS, 1) scan_topk_kernel(const Sca
     if (p.xchg_world > 0) {
         // K4 fused: publish this shard's list to every rank (NVLink P2P stores), then the flags
         const int slot = (int)(p.xchg_seq & 1u);
-        for (int peer = 0; peer < p.xchg_world; ++peer) {
+        for (int peer = 0; peer < p.xchg_targets; ++peer) {
             uint64_t* dst = p.xchg_recv[peer] + ((size_t)slot * p.xchg_world + p.xchg_rank) * PSX_K_PASS_MAX;
             for (int i = threadIdx.x; i < p.kpad; i += blockDim.x) st_relaxed_sys_u64(dst + i, i < p.k ? buf[i] : 0ull);
         }
         __threadfence_system();
         __syncthreads();
-        if ((int)threadIdx.x < p.xchg_world)
+        if ((int)threadIdx.x < p.xchg_targets)
             st_release_sys_u32(p.xchg_flag[threadIdx.x] + slot * PSX_XCHG_MAX_WORLD + p.xchg_rank, p.xchg_seq);
     }
     __syncthreads();

@@ -217,4 +217,18 @@ class ShardedIndex:
         b["ids_host"].copy_(i, non_blocking=True)
         if self.device.type == "cuda":
             t.cuda.current_stream(self.device).synchronize()
+            if self.exchange == "p2p" and self._local_search is None and hasattr(self.local, "exchange_status"):
+                # the fused wait is bounded: a rank that never published leaves a status word instead of a trap.  Every
+                # rank waits for every rank, so all of them see it; answer this query over the collective path.
+                silent = self.local.exchange_status()
+                if silent:
+                    self.exchange_timeouts = getattr(self, "exchange_timeouts", 0) + 1
+                    self.exchange = "nccl"
+                    try:
+                        s, i = self.search_device(b["q"], k, flt)
+                        b["scores_host"].copy_(s, non_blocking=True)
+                        b["ids_host"].copy_(i, non_blocking=True)
+                        t.cuda.current_stream(self.device).synchronize()
+                    finally:
+                        self.exchange = "p2p"
         return b["scores_host"].numpy().copy(), b["ids_host"].numpy().copy()

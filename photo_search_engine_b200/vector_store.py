@@ -17,6 +17,9 @@ Additive, optional surface (defaults reproduce the reference):
   ``PSX_STORE_DTYPE``): ``fp32`` (default), ``bf16`` (half the HBM, approximate), ``bf16+fp32`` (bf16
   rows for the scan plus an fp32 master: results bit-identical to ``fp32`` at about half the bytes
   streamed per query);
+* ``devices=[0, 1, ...]`` (env ``PSX_DEVICES=0,1,...``): the corpus is row-sharded over several GPUs of the
+  box BEHIND this one instance -- the reference constructs a single store in a single process
+  (main.py:59-68) -- with results bit-identical to one device (``psx_create_sharded``, include/psx.h);
 * ``search(..., constraints=None)``: fused pre-filter with the semantics of
   ``Searcher._check_time_match_v2`` (core/searcher.py:1884-1950);
 * ``search_batch`` / ``add_batch``: arrays in, arrays out, no per-hit Python objects;
@@ -90,6 +93,7 @@ class VectorStore:
         hnsw_ef_search: int = 96,
         *,
         device: Optional[int] = None,
+        devices: Optional[Sequence[int]] = None,
         store_dtype: Optional[str] = None,
         coalesce: Optional[bool] = None,
     ) -> None:
@@ -113,7 +117,15 @@ class VectorStore:
         self.hnsw_m = max(4, int(hnsw_m))
         self.hnsw_ef_construction = max(8, int(hnsw_ef_construction))
         self.hnsw_ef_search = max(8, int(hnsw_ef_search))
-        self.device = int(os.environ.get("PSX_DEVICE", "0")) if device is None else int(device)
+        if devices is None and device is None and os.environ.get("PSX_DEVICES", "").strip():
+            devices = [int(tok) for tok in os.environ["PSX_DEVICES"].replace(";", ",").split(",") if tok.strip()]
+        if devices is not None and len(devices) == 0:
+            raise ValueError("devices不能为空")
+        self.devices = tuple(int(x) for x in devices) if devices is not None else None
+        if self.devices is not None:
+            self.device = self.devices[0]
+        else:
+            self.device = int(os.environ.get("PSX_DEVICE", "0")) if device is None else int(device)
         self.store_dtype = dtype_name
 
         self._normalize = metric_name == "cosine"
@@ -142,7 +154,12 @@ class VectorStore:
     def _create_index(self, dimension: int):
         """Backend for ``dimension`` (utils/vector_store.py:72-81); ``hnsw`` is served exactly."""
         dtype = _DTYPE_CODES[self.store_dtype]
-        return type(self)._index_factory(int(dimension), self._metric_code, dtype, self.device)
+        where = self.devices if self.devices is not None and len(self.devices) > 1 else self.device
+        index = type(self)._index_factory(int(dimension), self._metric_code, dtype, where)
+        min_rows = os.environ.get("PSX_SHARD_MIN_ROWS", "").strip()
+        if min_rows and hasattr(index, "set_tunable") and self.devices is not None and len(self.devices) > 1:
+            index.set_tunable("shard_min_rows", int(min_rows))
+        return index
 
     def _require_dimension(self, vector: Sequence[float]) -> None:
         if len(vector) != self.dimension:

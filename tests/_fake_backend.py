@@ -40,8 +40,9 @@ def attr_pass_np(words: np.ndarray, f: N.PsxFilter) -> np.ndarray:
 
 
 class FakeIndex:
-    def __init__(self, d: int, metric: int = 0, store_dtype: int = 0, device: int = 0) -> None:
-        self.d, self.metric, self.store_dtype, self.device = int(d), int(metric), int(store_dtype), int(device)
+    def __init__(self, d: int, metric: int = 0, store_dtype: int = 0, device=0) -> None:
+        self.devices = (int(device),) if isinstance(device, (int, np.integer)) else tuple(int(x) for x in device)
+        self.d, self.metric, self.store_dtype, self.device = int(d), int(metric), int(store_dtype), self.devices[0]
         self._ix = OracleIndexFlat(self.d, self.metric)
         self._attrs = np.zeros(0, np.uint64)
 
@@ -60,6 +61,9 @@ class FakeIndex:
         pass
 
     def sync(self) -> None:
+        pass
+
+    def set_tunable(self, key: str, value: int) -> None:
         pass
 
     def add(self, x: np.ndarray) -> None:

@@ -37,7 +37,7 @@ def _both_paths(ix, q, k):
 
 
 @pytest.mark.parametrize("n,d,nq,k", [(70_000, 64, 5, 10), (200_000, 256, 128, 100), (150_000, 1024, 200, 100),
-                                      (100_000, 768, 300, 50), (66_000, 100, 17, 512), (131_072, 4096, 9, 20)])
+                                      (100_000, 768, 300, 50), (66_000, 100, 17, 100), (131_072, 4096, 9, 20), (70_000, 64, 40, 512)])
 def test_batch_equals_scan(n, d, nq, k):
     rng = np.random.default_rng(n + d + nq)
     x = unit_rows(rng, n, d)
@@ -64,7 +64,7 @@ def test_batch_serves_the_call_site_k(k):
     """candidate_k of the reference's expansion / reflection rounds (core/searcher.py:771-820: 675, 850, 1025, up to
     1333) and the pass maximum go through the tensor-core path -- not the nq-scans fallback -- and stay bit-identical."""
     rng = np.random.default_rng(k)
-    n, d, nq = 120_000, 128, 12
+    n, d, nq = 240_000, 128, 12          # the path asks for n >= 24 * (4k + 64) rows
     x = unit_rows(rng, n, d)
     q = unit_rows(rng, nq, d)
     q[0] = x[31337]
