@@ -58,6 +58,7 @@ struct DeviceGuard {
 // ------------------------------------------------------------------------------------------
 // index object
 // ------------------------------------------------------------------------------------------
+constexpr int BATCH_MAX_Q_ROWS = 256;
 struct psx_index {
     int d = 0, ld = 0, metric = 0, dtype = 0, device = 0;
     size_t esize = 4, row_bytes = 0;
@@ -120,10 +121,23 @@ struct psx_index {
     bool batch_pair = true;   // 129..256 queries: CTA-pair (cta_group::2) kernel instead of two accumulators per CTA
     bool batch_bf16 = true;   // PSX_STORE_BF16_MASTER: the batched GEMM reads the bf16 rows (kind::f16) instead of the fp32 master (kind::tf32)
     float* bq = nullptr;      // [256][ld] zero-padded query block
+    int bq_dirty_rows = BATCH_MAX_Q_ROWS;  // leading rows of bq that may hold non-zero data (rows beyond nq must read as zero)
+    size_t bq_row_bytes = 0;               // row pitch those rows were written with
+    // tensor maps of the batched GEMM, re-encoded only when what they describe changes
+    struct MapKey {
+        const void* base = nullptr;
+        long long rows = 0;
+        int cols = 0, ld = 0, box_rows = 0, bf16 = -1;
+        bool operator==(const MapKey& o) const {
+            return base == o.base && rows == o.rows && cols == o.cols && ld == o.ld && box_rows == o.box_rows && bf16 == o.bf16;
+        }
+    };
+    MapKey mq_key, mx_key;
+    CUtensorMap mq_map, mx_map;
     float* btheta = nullptr;  // [256]
     int* bcount = nullptr;    // [256]
     int* bflags = nullptr;    // [256]
-    uint32_t* bcand = nullptr;  // [256][bcand_cap]
+    uint64_t* bcand = nullptr;  // [256][bcand_cap]  (orderable approximate score << 32 | row)
     int bcand_cap = 0;          // entries per query the lists currently have room for
     uint64_t* mkeys = nullptr;  // [PSX_K_PASS_MAX] bf16-prefilter keys (PSX_STORE_BF16_MASTER)
     float* meps = nullptr;      // [1] its rounding bound
@@ -844,10 +858,10 @@ static int make_map(CUtensorMap* map, const void* base, bool bf16, long long row
 }
 
 // survivors per query the threshold aims at.  (bf16 operands: the rounding bound 8.2e-3 |q||x| is ~0.26 sigma of the
-// score distribution of 1024-d unit vectors, i.e. ~2.6-3 x k rows lie within eps of the k-th score: 8k+128 keeps them
-// above theta with the margin 4k+64 gives the TF32 form.)
+// score distribution of 1024-d unit vectors, i.e. ~2.6-3 x k rows lie within eps of the k-th score and ~7 x k within the
+// 2 eps band the re-score visits: 12k+192 keeps them above theta.  Listing a row costs 8 bytes; only band rows are re-read.)
 static int batch_T(const psx_index* h, int k) {
-    return (h->dtype == PSX_STORE_BF16_MASTER && h->batch_bf16) ? 8 * k + 128 : 4 * k + 64;
+    return (h->dtype == PSX_STORE_BF16_MASTER && h->batch_bf16) ? 12 * k + 192 : 4 * k + 64;
 }
 // shape test of the tensor-core path: an fp32 inner-product index, and a corpus large enough that the threshold's
 // survivors are a small fraction of it (T <= n / 24: otherwise a sampled threshold is meaningless and the lists approach
@@ -856,6 +870,22 @@ static bool batch_shape_ok(const psx_index* h, int64_t k) {
     return h->metric == PSX_METRIC_IP && has_fp32_rows(h) && k >= 1 && k <= PSX_K_PASS_MAX && h->n >= 65536 && h->d >= 32 &&
            (long long)batch_T(h, (int)k) * 24 <= h->n;
 }
+// cached cuTensorMapEncodeTiled
+static int cached_map(psx_index::MapKey& key, CUtensorMap& map, const void* base, bool bf16, long long rows, int cols, int ld, int box_rows) {
+    psx_index::MapKey want;
+    want.base = base;
+    want.rows = rows;
+    want.cols = cols;
+    want.ld = ld;
+    want.box_rows = box_rows;
+    want.bf16 = bf16 ? 1 : 0;
+    if (key == want) return PSX_OK;
+    int rc = make_map(&map, base, bf16, rows, cols, ld, box_rows);
+    if (rc) return rc;
+    key = want;
+    return PSX_OK;
+}
+
 static bool batch_eligible(const psx_index* h, int64_t nq, int64_t k, const psx_filter* f) {
     (void)f;  // the predicate is applied in the epilogue (candidates) and in the sample (thresholds)
     return h->batch_min > 0 && nq >= h->batch_min && batch_shape_ok(h, k);
@@ -869,7 +899,7 @@ static int ensure_batch_scratch(psx_index* h, size_t sample_floats, int cand_cap
             h->bcand = nullptr;
             h->bcand_cap = 0;
         }
-        CU(cudaMalloc(&h->bcand, (size_t)BATCH_MAX_Q * cand_cap * sizeof(uint32_t)));
+        CU(cudaMalloc(&h->bcand, (size_t)BATCH_MAX_Q * cand_cap * sizeof(uint64_t)));
         h->bcand_cap = cand_cap;
     }
     if (!h->bq) {
@@ -994,21 +1024,36 @@ static int launch_batch(psx_index* h, const float* q_dev, int nq, int k, const p
     // bf16 + fp32 master: the GEMM streams the bf16 rows (half the HBM bytes, kind::f16 at twice the TF32 rate);
     // the survivors are re-scored on the master exactly as in the TF32 form
     const bool bf = h->dtype == PSX_STORE_BF16_MASTER && h->batch_bf16;
-    CUtensorMap mq, mx;
+    // Query staging: the block the TMA reads is [MT*128][ld] with rows beyond nq and columns beyond d zero.  Only the rows
+    // an earlier, larger batch left behind are cleared (none in steady state); the padding columns of a row are written
+    // by the copy / pack itself.
+    const size_t q_row_bytes = bf ? (size_t)h->ld * sizeof(__nv_bfloat16) : (size_t)fld * sizeof(float);
+    if (h->bq_row_bytes != q_row_bytes) {  // first use, or the operand type changed: everything is stale
+        h->bq_dirty_rows = BATCH_MAX_Q_ROWS;
+        h->bq_row_bytes = q_row_bytes;
+    }
+    if (h->bq_dirty_rows > nq)
+        CU(cudaMemsetAsync((unsigned char*)h->bq + (size_t)nq * q_row_bytes, 0, (size_t)(h->bq_dirty_rows - nq) * q_row_bytes, st));
+    h->bq_dirty_rows = nq;
     if (bf) {
-        CU(cudaMemsetAsync(h->bq, 0, (size_t)MT * GEMM_M * h->ld * sizeof(__nv_bfloat16), st));
         pack_rows_kernel<__nv_bfloat16><<<(nq + 7) / 8, 256, 0, st>>>(q_dev, (__nv_bfloat16*)h->bq, nq, h->d, h->ld, 0, nullptr);
         g_launches++;
         CU(cudaGetLastError());
-        if ((rc = make_map(&mq, h->bq, true, (long long)MT * GEMM_M, h->d, h->ld, GEMM_M))) return rc;
-        if ((rc = make_map(&mx, h->x, true, h->n, h->d, h->ld, pair ? 128 : BATCH_BN))) return rc;
+        if ((rc = cached_map(h->mq_key, h->mq_map, h->bq, true, (long long)MT * GEMM_M, h->d, h->ld, GEMM_M))) return rc;
+        if ((rc = cached_map(h->mx_key, h->mx_map, h->x, true, h->n, h->d, h->ld, pair ? 128 : BATCH_BN))) return rc;
     } else {
-        CU(cudaMemsetAsync(h->bq, 0, (size_t)MT * GEMM_M * fld * sizeof(float), st));
-        CU(cudaMemcpy2DAsync(h->bq, (size_t)fld * sizeof(float), q_dev, (size_t)h->d * sizeof(float), (size_t)h->d * sizeof(float), nq,
-                             cudaMemcpyDeviceToDevice, st));
-        if ((rc = make_map(&mq, h->bq, false, (long long)MT * GEMM_M, h->d, fld, GEMM_M))) return rc;
-        if ((rc = make_map(&mx, fp32_rows(h), false, h->n, h->d, fld, pair ? 128 : BATCH_BN))) return rc;
+        if (fld == h->d) {
+            CU(cudaMemcpyAsync(h->bq, q_dev, (size_t)nq * h->d * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        } else {  // d not a multiple of 4: rows are padded to ld floats (pack = copy + zero padding)
+            pack_rows_kernel<float><<<(nq + 7) / 8, 256, 0, st>>>(q_dev, h->bq, nq, h->d, fld, 0, nullptr);
+            g_launches++;
+            CU(cudaGetLastError());
+        }
+        if ((rc = cached_map(h->mq_key, h->mq_map, h->bq, false, (long long)MT * GEMM_M, h->d, fld, GEMM_M))) return rc;
+        if ((rc = cached_map(h->mx_key, h->mx_map, fp32_rows(h), false, h->n, h->d, fld, pair ? 128 : BATCH_BN))) return rc;
     }
+    const CUtensorMap& mq = h->mq_map;
+    const CUtensorMap& mx = h->mx_map;
     GemmParams gp;
     memset(&gp, 0, sizeof gp);
     gp.n = h->n;
@@ -1016,7 +1061,7 @@ static int launch_batch(psx_index* h, const float* q_dev, int nq, int k, const p
     gp.nq = nq;
     gp.num_tiles = num_tiles;
     gp.theta = h->btheta;
-    gp.cand_ids = h->bcand;
+    gp.cand = h->bcand;
     gp.cand_count = h->bcount;
     gp.cand_cap = cand_cap;
     gp.sample_scores = h->bsample;
@@ -1063,10 +1108,10 @@ static int launch_batch(psx_index* h, const float* q_dev, int nq, int k, const p
     bt.mark("filter pass");
     // exact re-score of the survivors + top-k + proof obligation
     const int kpad = (int)psx_kpad(k);
-    const size_t smem = (size_t)std::max(cand_cap, kpad) * 8 + (size_t)(fld + 4) * 4;
+    const size_t smem = (size_t)std::max(cand_cap, kpad) * 8 + (size_t)(fld + 8) * 4;
     static std::atomic<bool> ready[64];
     if (h->device < 64 && !ready[h->device].load()) {
-        CU(cudaFuncSetAttribute(rescore_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PSX_SMEM_LIMIT));
+        CU(cudaFuncSetAttribute(rescore_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PSX_SMEM_LIMIT - 1024));
         ready[h->device].store(true);
     }
     // TF32 drops 13 mantissa bits of each operand (truncation: relative error < 2^-10 each):
@@ -1076,7 +1121,7 @@ static int launch_batch(psx_index* h, const float* q_dev, int nq, int k, const p
     // The kernel multiplies the coefficient by the query's own norm and the largest stored row norm (both on the device).
     (void)qnorm_max;
     const float eps_coef = bf ? 8.2e-3f : 2.2e-3f;
-    rescore_select_kernel<<<nq, 512, smem, st>>>(fp32_rows(h), fld, h->d, h->n, q_dev, k, kpad, h->bcand, h->bcount,
+    rescore_select_kernel<<<nq, 256, smem, st>>>(fp32_rows(h), fld, h->d, h->n, q_dev, k, kpad, h->bcand, h->bcount,
                                                  cand_cap, h->btheta, eps_coef, h->dmax_sumsq, nullptr, id_base, out_scores, out_ids,
                                                  out_keys, keys_stride > 0 ? keys_stride : kpad, flags_dev);
     g_launches++;
@@ -1111,13 +1156,13 @@ static int launch_mixed(psx_index* h, const float* q_dev, int k, const psx_filte
     g_launches++;
     CU(cudaGetLastError());
     const int kpad = (int)psx_kpad(k);
-    const size_t smem = (size_t)h->bcand_cap * 8 + (size_t)(h->ldm + 4) * 4;
+    const size_t smem = (size_t)h->bcand_cap * 8 + (size_t)(h->ldm + 8) * 4;
     static std::atomic<bool> ready[64];
     if (h->device < 64 && !ready[h->device].load()) {
-        CU(cudaFuncSetAttribute(rescore_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PSX_SMEM_LIMIT));
+        CU(cudaFuncSetAttribute(rescore_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PSX_SMEM_LIMIT - 1024));
         ready[h->device].store(true);
     }
-    rescore_select_kernel<<<1, 512, smem, st>>>((const float*)h->xm, h->ldm, h->d, h->n, q_dev, k, kpad, h->bcand, h->bcount, h->bcand_cap,
+    rescore_select_kernel<<<1, 256, smem, st>>>((const float*)h->xm, h->ldm, h->d, h->n, q_dev, k, kpad, h->bcand, h->bcount, h->bcand_cap,
                                                 h->btheta, 0.f, h->dmax_sumsq, h->meps, id_base, out_scores, out_ids, out_keys, kpad, h->bflags);
     g_launches++;
     CU(cudaGetLastError());
@@ -1203,7 +1248,7 @@ extern "C" int psx_search_exchange_device(psx_index* h, const float* q_dev, int6
     const size_t smem = (size_t)np * 8;
     static std::atomic<bool> ready[64];
     if (h->device < 64 && !ready[h->device].load()) {
-        CU(cudaFuncSetAttribute(merge_wait_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PSX_SMEM_LIMIT));
+        CU(cudaFuncSetAttribute(merge_wait_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PSX_SMEM_LIMIT - 1024));
         ready[h->device].store(true);
     }
     const uint64_t mine = peer_bases[rank];
@@ -1328,19 +1373,26 @@ static int search_batched_host(psx_index* h, const float* q, int64_t nq, int64_t
         CU(cudaMemcpyAsync(h->dq, h->hq, (size_t)gq * h->d * sizeof(float), cudaMemcpyHostToDevice, st));
         if ((rc = launch_batch(h, h->dq, gq, (int)kk, filter, id_base, sqrtf(qn2) * 1.0001f, h->dscores, h->dids, nullptr, h->bflags, st)))
             return rc;
+        // the certificates travel with the results: ONE synchronisation per batch unless a query has to be re-run
         CU(cudaMemcpyAsync(h->hflags, h->bflags, gq * sizeof(int), cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(h->hscores, h->dscores, (size_t)gq * kk * sizeof(float), cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(h->hids, h->dids, (size_t)gq * kk * sizeof(long long), cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
         h->batch_queries += gq;
+        bool rerun = false;
         for (int qi = 0; qi < gq; ++qi) {
             if (!h->hflags[qi]) continue;
             h->batch_fallbacks++;
+            rerun = true;
             rc = launch_exact_scan(h, h->dq + (size_t)qi * h->d, (int)kk, filter, id_base, nullptr, h->dscores + (size_t)qi * kk,
                                    h->dids + (size_t)qi * kk, nullptr, st);
             if (rc) return rc;
         }
-        CU(cudaMemcpyAsync(h->hscores, h->dscores, (size_t)gq * kk * sizeof(float), cudaMemcpyDeviceToHost, st));
-        CU(cudaMemcpyAsync(h->hids, h->dids, (size_t)gq * kk * sizeof(long long), cudaMemcpyDeviceToHost, st));
-        CU(cudaStreamSynchronize(st));
+        if (rerun) {
+            CU(cudaMemcpyAsync(h->hscores, h->dscores, (size_t)gq * kk * sizeof(float), cudaMemcpyDeviceToHost, st));
+            CU(cudaMemcpyAsync(h->hids, h->dids, (size_t)gq * kk * sizeof(long long), cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+        }
         for (int qi = 0; qi < gq; ++qi) {
             float* os = out_scores + (q0 + qi) * k;
             int64_t* oi = out_ids + (q0 + qi) * k;

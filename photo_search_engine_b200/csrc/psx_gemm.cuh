@@ -48,7 +48,7 @@ struct GemmParams {
     int tile_step;           // MODE_SAMPLE: visit tiles 0, tile_step, 2*tile_step, ...
     int mode;
     const float* theta;      // [nq] thresholds (MODE_FILTER)
-    uint32_t* cand_ids;      // [nq][cand_cap]
+    uint64_t* cand;          // [nq][cand_cap] survivors: orderable(approximate score) << 32 | row
     int* cand_count;         // [nq]
     int cand_cap;
     float* sample_scores;    // [nq][sample_ld] (MODE_SAMPLE): SAMPLE_KEEP scores per sample CTA (pair)
@@ -139,6 +139,27 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32])
         : "memory");
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+
+// r[j] for a run-time j.  Indexing a register array with a run-time value would move the whole array to local memory;
+// a switch compiles to a branch table with one move per case.  Called once per survivor (~2 % of the lanes per block).
+__device__ __forceinline__ uint32_t pick32(const uint32_t (&r)[32], int j) {
+    switch (j) {
+#define PSX_PICK(i) case i: return r[i];
+        PSX_PICK(0) PSX_PICK(1) PSX_PICK(2) PSX_PICK(3) PSX_PICK(4) PSX_PICK(5) PSX_PICK(6) PSX_PICK(7)
+        PSX_PICK(8) PSX_PICK(9) PSX_PICK(10) PSX_PICK(11) PSX_PICK(12) PSX_PICK(13) PSX_PICK(14) PSX_PICK(15)
+        PSX_PICK(16) PSX_PICK(17) PSX_PICK(18) PSX_PICK(19) PSX_PICK(20) PSX_PICK(21) PSX_PICK(22) PSX_PICK(23)
+        PSX_PICK(24) PSX_PICK(25) PSX_PICK(26) PSX_PICK(27) PSX_PICK(28) PSX_PICK(29) PSX_PICK(30)
+#undef PSX_PICK
+        default: return r[31];
+    }
+}
+// a survivor of the threshold test: its approximate score travels with the row id (the exact re-score only visits
+// the rows whose approximate score can still reach the top-k)
+__device__ __forceinline__ uint64_t cand_entry(uint32_t score_bits, uint32_t row) {
+    return ((uint64_t)f32_to_ord(__uint_as_float(score_bits)) << 32) | row;
+}
+__device__ __forceinline__ float cand_score(uint64_t e) { return ord_to_f32((uint32_t)(e >> 32)); }
+__device__ __forceinline__ uint32_t cand_row(uint64_t e) { return (uint32_t)e; }
 
 // Sample pass: the 8 largest scores one (CTA, query) has seen, kept sorted in registers.  Only these
 // reach memory -- the thresholds need the ~16th largest score of the whole sample, and no CTA holds more
@@ -320,7 +341,7 @@ gemm_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
                                 const long long row = row0 + c * 32 + j;
                                 if (row < p.n && (!p.attrs || gemm_attr_pass(__ldg(p.attrs + row), p.f))) {
                                     const int pos = atomicAdd(p.cand_count + qi, 1);
-                                    if (pos < p.cand_cap) p.cand_ids[(size_t)qi * p.cand_cap + pos] = (uint32_t)row;
+                                    if (pos < p.cand_cap) p.cand[(size_t)qi * p.cand_cap + pos] = cand_entry(pick32(r, j), (uint32_t)row);
                                 }
                             }
                         }
@@ -559,7 +580,7 @@ gemm_filter_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
                             const long long row = row0 + c * 32 + j;
                             if (row < p.n && (!p.attrs || gemm_attr_pass(__ldg(p.attrs + row), p.f))) {
                                 const int pos = atomicAdd(p.cand_count + qi, 1);
-                                if (pos < p.cand_cap) p.cand_ids[(size_t)qi * p.cand_cap + pos] = (uint32_t)row;
+                                if (pos < p.cand_cap) p.cand[(size_t)qi * p.cand_cap + pos] = cand_entry(pick32(r, j), (uint32_t)row);
                             }
                         }
                     }
@@ -621,76 +642,125 @@ __global__ void __launch_bounds__(256) theta_kernel(const float* __restrict__ sa
 }
 
 // ---- exact re-score + selection ------------------------------------------------------------------------------
-// One CTA per query: every warp takes candidates round-robin, recomputes <q, x_row> in fp32 with
-// exactly the reduction tree of scan_topk_kernel (per-lane pieces lane, lane+32, ... into four
-// accumulators, (a0+a1)+(a2+a3), xor butterfly), so the scores are bit-identical to the
-// single-query path; keys are sorted in shared memory and the first k emitted.
-// flags[qi] != 0  <=>  the result is NOT proven exact (list overflow, fewer than k candidates while
-// more rows exist, or k-th exact score < theta + eps): the caller re-runs that query on the scan.
-__global__ void __launch_bounds__(512, 2)
+// One CTA per query.  The list holds every row whose APPROXIMATE score s~ (TF32 / bf16 GEMM, or the bf16 scan) is
+// >= theta, together with that score; |s~ - s| <= eps for every row (eps = eps_coef |q| max|x|, computed here).
+//   1. sort the list by s~;  tau = the k-th largest s~;
+//   2. only the BAND { s~ >= tau - 2 eps } is re-scored exactly: a row below the band has s <= s~ + eps < tau - eps,
+//      while the k rows with s~ >= tau have s >= tau - eps -- it cannot be among the k best.  (At k = 100 over 1M
+//      1024-d rows the band holds ~170 of the ~460 listed rows: the random 4 KB row reads, which dominated this
+//      kernel, shrink by that factor.)
+//   3. exact fp32 dot of the band rows with exactly the reduction tree of scan_topk_kernel (per-lane pieces lane,
+//      lane+32, ... into four accumulators, (a0+a1)+(a2+a3), xor butterfly), so the scores are bit-identical to the
+//      single-query path; integer sort of the exact keys; the first k are emitted.
+// flags[qi] != 0  <=>  the result is NOT proven exact and the caller re-runs the query on the scan:
+//   1  the list overflowed (survivors were dropped);
+//   2  fewer than k rows above a finite threshold;
+//   3  rows OUTSIDE the list could matter: neither  tau - 2 eps >= theta  (the band is complete inside the list)
+//      nor  k-th exact score >= theta + eps  (every unlisted row has s < theta + eps) holds.
+__global__ void __launch_bounds__(256, 3)
 rescore_select_kernel(const float* __restrict__ x, int ld, int d, long long n, const float* __restrict__ q, int k, int kpad,
-                      const uint32_t* __restrict__ cand_ids, const int* __restrict__ cand_count, int cand_cap,
+                      const uint64_t* __restrict__ cand, const int* __restrict__ cand_count, int cand_cap,
                       const float* __restrict__ theta, float eps_coef, const float* __restrict__ max_sumsq,
                       const float* __restrict__ eps_dev, uint32_t id_base,
                       float* out_scores, long long* out_ids, uint64_t* out_keys, long long keys_stride, int* flags) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    uint64_t* keys = reinterpret_cast<uint64_t*>(smem_raw);     // [np]
+    __shared__ float s_part[8];
+    __shared__ float s_eps;
+    __shared__ int s_band;
     const int qi = blockIdx.x;
+    const int qpad = (ld + 3) & ~3;
+    float* sq = reinterpret_cast<float*>(smem_raw);                       // [qpad]
+    uint64_t* keys = reinterpret_cast<uint64_t*>(smem_raw + (((size_t)qpad * 4 + 15) & ~(size_t)15));  // [np]
     const int raw_count = cand_count[qi];
     const int count = raw_count < cand_cap ? raw_count : cand_cap;
     int np = kpad;
     while (np < count) np <<= 1;
-    float* sq = reinterpret_cast<float*>(keys + np);
-    const int qpad = (ld + 3) & ~3;
-    for (int i = threadIdx.x; i < qpad; i += blockDim.x) sq[i] = i < d ? q[(size_t)qi * d + i] : 0.f;
-    for (int i = count + threadIdx.x; i < np; i += blockDim.x) keys[i] = 0ull;
-    __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    // the query, and its squared norm for the rounding bound
+    float qq = 0.f;
+    for (int i = threadIdx.x; i < qpad; i += blockDim.x) {
+        const float v = i < d ? q[(size_t)qi * d + i] : 0.f;
+        sq[i] = v;
+        qq = fmaf(v, v, qq);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) qq += __shfl_xor_sync(0xffffffffu, qq, o);
+    if (lane == 0) s_part[warp] = qq;
+    const uint64_t* mine = cand + (size_t)qi * cand_cap;
+    for (int i = threadIdx.x; i < np; i += blockDim.x) keys[i] = i < count ? mine[i] : 0ull;
+    if (threadIdx.x == 0) s_band = 0;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float tot = 0.f;
+        for (int w = 0; w < nwarps; ++w) tot += s_part[w];
+        s_eps = eps_dev ? eps_dev[qi] : eps_coef * sqrtf(tot) * sqrtf(fmaxf(*max_sumsq, 0.f)) * 1.001f;
+    }
+    // 1. by approximate score
+    block_bitonic_sort_desc(keys, np);
+    const long long need = n < k ? n : (long long)k;
+    const float eps = s_eps;
+    const float th = theta[qi];
+    float beta = -INFINITY;  // lower edge of the band
+    if (need > 0 && count >= need) beta = cand_score(keys[need - 1]) - 2.f * eps;
+    // 2. the band is a prefix of the sorted list
+    for (int i = threadIdx.x; i < count; i += blockDim.x)
+        if (cand_score(keys[i]) >= beta && (i + 1 == count || !(cand_score(keys[i + 1]) >= beta))) s_band = i + 1;
+    __syncthreads();
+    const int m = s_band;
+    // 3. exact scores of the band, two rows per warp and trip (8 independent 16-byte loads in flight per lane)
     const float4* q4 = reinterpret_cast<const float4*>(sq);
     const int pieces = ld >> 2;
-    for (int c = warp; c < count; c += nwarps) {
-        const uint32_t row = cand_ids[(size_t)qi * cand_cap + c];
-        const float4* xr = reinterpret_cast<const float4*>(x + (size_t)row * ld);
-        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    for (int c = 2 * warp; c < m; c += 2 * nwarps) {
+        const bool two = c + 1 < m;
+        const uint32_t r0 = cand_row(keys[c]), r1 = two ? cand_row(keys[c + 1]) : r0;
+        const float4* x0 = reinterpret_cast<const float4*>(x + (size_t)r0 * ld);
+        const float4* x1 = reinterpret_cast<const float4*>(x + (size_t)r1 * ld);
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f, b3 = 0.f;
 #pragma unroll 4
         for (int pc = lane; pc < pieces; pc += 32) {
-            const float4 v = __ldg(xr + pc);
+            const float4 v = __ldg(x0 + pc);
+            const float4 u = __ldg(x1 + pc);
             const float4 w = q4[pc];
             a0 = fmaf(v.x, w.x, a0);
             a1 = fmaf(v.y, w.y, a1);
             a2 = fmaf(v.z, w.z, a2);
             a3 = fmaf(v.w, w.w, a3);
+            b0 = fmaf(u.x, w.x, b0);
+            b1 = fmaf(u.y, w.y, b1);
+            b2 = fmaf(u.z, w.z, b2);
+            b3 = fmaf(u.w, w.w, b3);
         }
-        float s = (a0 + a1) + (a2 + a3);
+        float s0 = (a0 + a1) + (a2 + a3), s1 = (b0 + b1) + (b2 + b3);
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        if (lane == 0) keys[c] = make_key(s, id_base + row);
+        for (int o = 16; o > 0; o >>= 1) {
+            s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+            s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+        }
+        __syncwarp();
+        if (lane == 0) {
+            keys[c] = make_key(s0, id_base + r0);
+            if (two) keys[c + 1] = make_key(s1, id_base + r1);
+        }
     }
+    int np2 = kpad;
+    while (np2 < m) np2 <<= 1;
+    for (int i = m + threadIdx.x; i < np2; i += blockDim.x) keys[i] = 0ull;
     __syncthreads();
-    block_bitonic_sort_desc(keys, np);
-    const int kk = k;
+    block_bitonic_sort_desc(keys, np2);
     // keys_stride: distance between two queries' key lists (kpad, or world * kpad when the lists of several shards
     // interleave in one buffer -- possibly peer memory on the merging GPU)
-    block_emit_results(keys, kk, kpad, PSX_METRIC_IP, out_scores ? out_scores + (size_t)qi * k : nullptr,
+    block_emit_results(keys, k, kpad, PSX_METRIC_IP, out_scores ? out_scores + (size_t)qi * k : nullptr,
                        out_ids ? out_ids + (size_t)qi * k : nullptr, out_keys ? out_keys + (size_t)qi * keys_stride : nullptr);
     if (threadIdx.x == 0) {
         int bad = 0;
-        if (raw_count > cand_cap) bad = 1;                                   // list overflow: survivors were dropped
-        const long long need = n < k ? n : k;
-        if (count < need) bad = 2;                                           // threshold too tight
-        if (!bad && need > 0 && n > count) {
+        const bool everything_listed = !(th > -INFINITY);  // no finite threshold: every eligible row is in the list
+        if (raw_count > cand_cap) {
+            bad = 1;
+        } else if (count < need) {
+            bad = everything_listed ? 0 : 2;
+        } else if (need > 0 && n > count && !everything_listed) {
             const float kth = key_score(keys[need - 1]);
-            // rounding bound of the approximate scores for THIS query, from its own norm and the largest stored row
-            // norm (Cauchy-Schwarz): eps_coef * |q| * max|x|.  Computed here so that no caller has to supply norms.
-            float e;
-            if (eps_dev) {
-                e = eps_dev[qi];
-            } else {
-                float qq = 0.f;
-                for (int i = 0; i < d; ++i) qq = fmaf(sq[i], sq[i], qq);
-                e = eps_coef * sqrtf(qq) * sqrtf(fmaxf(*max_sumsq, 0.f)) * 1.001f;
-            }
-            if (!(kth >= theta[qi] + e)) bad = 3;                          // proof obligation not met
+            if (!(beta >= th) && !(kth >= th + eps)) bad = 3;
         }
         flags[qi] = bad;
     }
@@ -701,7 +771,7 @@ rescore_select_kernel(const float* __restrict__ x, int ld, int d, long long n, c
 // pass the predicate, in which case every eligible row is already a candidate).
 // Also computes the rounding bound for this query: storing x as bf16 (8 significant bits, round to
 // nearest) perturbs <q,x> by at most 2^-8 * sum|q_i x_i| <= 2^-8 |q| |x|; 4.1e-3 adds 5 % slack.
-__global__ void keys_to_cands_kernel(const uint64_t* __restrict__ keys, int kprime, uint32_t id_base, uint32_t* cand_ids,
+__global__ void keys_to_cands_kernel(const uint64_t* __restrict__ keys, int kprime, uint32_t id_base, uint64_t* cand,
                                      int* cand_count, float* theta, const float* __restrict__ q, int d,
                                      const float* __restrict__ max_sumsq, float* eps_out) {
     __shared__ int cnt;
@@ -717,7 +787,8 @@ __global__ void keys_to_cands_kernel(const uint64_t* __restrict__ keys, int kpri
     for (int i = threadIdx.x; i < kprime; i += blockDim.x) {
         const uint64_t key = keys[i];
         if (key) {
-            cand_ids[i] = key_id(key) - id_base;  // keys are sorted: the non-empty ones form a prefix
+            // keys are sorted: the non-empty ones form a prefix.  Entry = (orderable bf16-scan score, local row)
+            cand[i] = (key & 0xffffffff00000000ull) | (uint64_t)(key_id(key) - id_base);
             ++mine;
         }
     }
