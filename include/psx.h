@@ -184,6 +184,8 @@ int64_t psx_kpad(int64_t k);
 int psx_search_batch_device(psx_index* h, const float* q_dev, int64_t nq, int64_t k, const psx_filter* filter, float qnorm_max,
                             uint32_t id_base, float* out_scores_dev, int64_t* out_ids_dev, uint64_t* out_keys_dev,
                             int* flags_dev, void* stream);
+/* 1 when psx_search_batch_device accepts this index for this k (metric, rows, dimension, k -- see above), else 0 */
+int psx_batch_supported(psx_index* h, int64_t k);
 /* queries served by the batched path so far, and how many of them had to be re-run on the scan */
 int psx_batch_stats(psx_index* h, int64_t* queries, int64_t* fallbacks);
 /* Final merge of `nlists` sorted key lists per query (layout [nq][nlists][kpad], e.g. the

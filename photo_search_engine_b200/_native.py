@@ -65,6 +65,7 @@ _SIGNATURES = [
     ("psx_search_device", C.c_int, [_P, _P, C.c_int64, C.c_int64, C.POINTER(PsxFilter), C.c_uint32, _P, _P, _P, _P]),
     ("psx_kpad", C.c_int64, [C.c_int64]),
     ("psx_search_batch_device", C.c_int, [_P, _P, C.c_int64, C.c_int64, C.POINTER(PsxFilter), C.c_float, C.c_uint32, _P, _P, _P, _P, _P]),
+    ("psx_batch_supported", C.c_int, [_P, C.c_int64]),
     ("psx_batch_stats", C.c_int, [_P, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     ("psx_merge_keys_device", C.c_int, [C.c_int, _P, C.c_int64, C.c_int64, C.c_int64, C.c_int, _P, _P, _P]),
     ("psx_exchange_bytes", C.c_int64, []),
@@ -244,6 +245,9 @@ class NativeIndex:
         a, b, c = C.c_int64(), C.c_int64(), C.c_int64()
         check(self._lib.psx_group_stats(self._h, C.byref(a), C.byref(b), C.byref(c)))
         return a.value, b.value, c.value
+
+    def batch_supported(self, k: int) -> bool:
+        return bool(self._lib.psx_batch_supported(self._h, int(k)))
 
     def batch_stats(self):
         a, b = C.c_int64(), C.c_int64()

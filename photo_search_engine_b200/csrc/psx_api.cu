@@ -218,18 +218,35 @@ struct BatchCfg {
 constexpr int PAIR_STAGES = 6;
 static int batch_bn(int mt, bool pair) { return mt == 2 ? (pair ? 256 : BatchCfg<2>::BN) : BatchCfg<1>::BN; }
 
+// launch with (optionally) programmatic stream serialization: the kernel may become resident while its predecessor in
+// the stream still runs; it synchronises with it through griddepcontrol.wait where it consumes its results
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_ex(void (*kernel)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t st, bool pdl, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(block);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+
 // cta_group::2 variant for 129..256 queries: grid = 2 * pairs, cluster (2,1,1) is a kernel attribute
 template <bool BF>
-static int launch_gemm_pair(psx_index* h, const CUtensorMap& mq, const CUtensorMap& mx, const GemmParams& gp, int pairs, cudaStream_t st) {
+static int launch_gemm_pair(psx_index* h, const CUtensorMap& mq, const CUtensorMap& mx, const GemmParams& gp, int pairs, cudaStream_t st,
+                            bool pdl) {
     constexpr size_t smem = (size_t)PAIR_STAGES * (GEMM_M + 128) * GEMM_KB_BYTES + 256;
     static std::atomic<bool> ready[64];
     if (h->device < 64 && !ready[h->device].load()) {
         CU(cudaFuncSetAttribute(gemm_filter_pair_kernel<PAIR_STAGES, BF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         ready[h->device].store(true);
     }
-    gemm_filter_pair_kernel<PAIR_STAGES, BF><<<2 * pairs, GEMM_THREADS, smem, st>>>(mq, mx, gp);
+    CU(launch_ex(gemm_filter_pair_kernel<PAIR_STAGES, BF>, 2u * pairs, GEMM_THREADS, smem, st, pdl, mq, mx, gp));
     g_launches++;
-    CU(cudaGetLastError());
     return PSX_OK;
 }
 
@@ -860,8 +877,15 @@ static int make_map(CUtensorMap* map, const void* base, bool bf16, long long row
 // survivors per query the threshold aims at.  (bf16 operands: the rounding bound 8.2e-3 |q||x| is ~0.26 sigma of the
 // score distribution of 1024-d unit vectors, i.e. ~2.6-3 x k rows lie within eps of the k-th score and ~7 x k within the
 // 2 eps band the re-score visits: 12k+192 keeps them above theta.  Listing a row costs 8 bytes; only band rows are re-read.)
+// bf16 operands are used for k <= 512 only: beyond, the 2-eps band alone outgrows the lists (the TF32 form over the
+// master rows serves those k)
+static bool batch_uses_bf16(const psx_index* h, int k) { return h->dtype == PSX_STORE_BF16_MASTER && h->batch_bf16 && k <= 512; }
 static int batch_T(const psx_index* h, int k) {
-    return (h->dtype == PSX_STORE_BF16_MASTER && h->batch_bf16) ? 12 * k + 192 : 4 * k + 64;
+    if (batch_uses_bf16(h, k)) return 12 * k + 192;
+    // TF32: 4k+64 rows keep the eps band above theta; listing a row is cheap (8 bytes, only the band is re-read), so the
+    // same number again (at most 2048, and never more than the lists can absorb at k = 2048) buys a threshold sample of
+    // half the size for the same noise
+    return std::min(std::min(8 * k + 128, 4 * k + 64 + 2048), 9000);
 }
 // shape test of the tensor-core path: an fp32 inner-product index, and a corpus large enough that the threshold's
 // survivors are a small fraction of it (T <= n / 24: otherwise a sampled threshold is meaningless and the lists approach
@@ -969,7 +993,7 @@ struct BatchTimer {
 };
 
 template <int MT, bool BF>
-static int launch_gemm(psx_index* h, const CUtensorMap& mq, const CUtensorMap& mx, const GemmParams& gp, int grid, cudaStream_t st) {
+static int launch_gemm(psx_index* h, const CUtensorMap& mq, const CUtensorMap& mx, const GemmParams& gp, int grid, cudaStream_t st, bool pdl) {
     constexpr int STAGES = BatchCfg<MT>::STAGES;
     constexpr int BATCH_BN = BatchCfg<MT>::BN;
     constexpr int STAGE_BYTES = (MT * GEMM_M + BATCH_BN) * GEMM_KB_BYTES;
@@ -979,9 +1003,8 @@ static int launch_gemm(psx_index* h, const CUtensorMap& mq, const CUtensorMap& m
         CU(cudaFuncSetAttribute(gemm_filter_kernel<MT, BATCH_BN, STAGES, BF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         ready[h->device].store(true);
     }
-    gemm_filter_kernel<MT, BATCH_BN, STAGES, BF><<<grid, GEMM_THREADS, smem, st>>>(mq, mx, gp);
+    CU(launch_ex(gemm_filter_kernel<MT, BATCH_BN, STAGES, BF>, (unsigned)grid, GEMM_THREADS, smem, st, pdl, mq, mx, gp));
     g_launches++;
-    CU(cudaGetLastError());
     return PSX_OK;
 }
 
@@ -994,17 +1017,17 @@ static int launch_batch(psx_index* h, const float* q_dev, int nq, int k, const p
     const bool pair = MT == 2 && h->batch_pair;
     const int BATCH_BN = batch_bn(MT, pair);
     const int num_tiles = (int)((h->n + BATCH_BN - 1) / BATCH_BN);
-    // theta from a strided sample: aim at ~16 sample scores above the threshold that ~T rows pass.  The
+    // theta from a strided sample: aim at ~SAMPLE_RANK sample scores above the threshold that ~T rows pass.  The
     // threshold has to land between the k-th score and roughly the (cand_cap)-th; the certificate decides.  The
-    // number of rows above the sample's 16th score is ~ T * Gamma(16)/16: it undercuts k + (rows within eps of
-    // the k-th) with probability ~3e-5 per query at k = 100 (8 sample scores and T = 3k+48 failed 2.7 % of the
-    // queries of a 10M-row corpus, each of which costs a full scan).
+    // number of rows above the sample's r-th score is ~ T * Gamma(r)/r; it must not undercut the ~1.3-1.7 k rows of
+    // the eps band (history: 8 sample scores with T = 3k+48 failed 2.7 % of the queries of a 10M-row corpus, each of
+    // which costs a full scan; 16 with T = 4k+64 none in 10 240; now 12 with T = 8k+128, i.e. twice the head room).
     const int T = batch_T(h, k);
     // The sample: every tile_step-th tile, and of a visited tile only the first sample_cols rows, sized so that about
     // SAMPLE_RANK sample rows score above the threshold that T rows of the corpus pass.  A sample CTA keeps its 8 best
     // scores per query, so a CTA must not see more than a few rows above theta: narrow the columns when T/n is large
     // (small corpora with a large k) and never give one CTA more than its share.
-    constexpr double SAMPLE_RANK = 16.0;
+    constexpr double SAMPLE_RANK = 12.0;
     const double frac = (double)T / (double)h->n;  // fraction of the rows above theta
     int sample_cols = 256;
     while (sample_cols > 32 && frac * sample_cols > 1.5) sample_cols >>= 1;
@@ -1023,7 +1046,7 @@ static int launch_batch(psx_index* h, const float* q_dev, int nq, int k, const p
     const int fld = fp32_ld(h);
     // bf16 + fp32 master: the GEMM streams the bf16 rows (half the HBM bytes, kind::f16 at twice the TF32 rate);
     // the survivors are re-scored on the master exactly as in the TF32 form
-    const bool bf = h->dtype == PSX_STORE_BF16_MASTER && h->batch_bf16;
+    const bool bf = batch_uses_bf16(h, k);
     // Query staging: the block the TMA reads is [MT*128][ld] with rows beyond nq and columns beyond d zero.  Only the rows
     // an earlier, larger batch left behind are cleared (none in steady state); the padding columns of a row are written
     // by the copy / pack itself.
@@ -1071,19 +1094,21 @@ static int launch_batch(psx_index* h, const float* q_dev, int nq, int k, const p
         gp.attrs = h->attrs;
         gp.f = *f;
     }
-    auto run_gemm = [&](int grid) -> int {
+    // the kernels of one batch chain by programmatic dependent launch (see psx_gemm.cuh) unless a phase is being timed
+    const bool chain = !BatchTimer::enabled() && !debug_sync();
+    auto run_gemm = [&](int grid, bool pdl) -> int {
         if (bf)
-            return pair ? launch_gemm_pair<true>(h, mq, mx, gp, grid, st)
-                        : MT == 2 ? launch_gemm<2, true>(h, mq, mx, gp, grid, st) : launch_gemm<1, true>(h, mq, mx, gp, grid, st);
-        return pair ? launch_gemm_pair<false>(h, mq, mx, gp, grid, st)
-                    : MT == 2 ? launch_gemm<2, false>(h, mq, mx, gp, grid, st) : launch_gemm<1, false>(h, mq, mx, gp, grid, st);
+            return pair ? launch_gemm_pair<true>(h, mq, mx, gp, grid, st, pdl)
+                        : MT == 2 ? launch_gemm<2, true>(h, mq, mx, gp, grid, st, pdl) : launch_gemm<1, true>(h, mq, mx, gp, grid, st, pdl);
+        return pair ? launch_gemm_pair<false>(h, mq, mx, gp, grid, st, pdl)
+                    : MT == 2 ? launch_gemm<2, false>(h, mq, mx, gp, grid, st, pdl) : launch_gemm<1, false>(h, mq, mx, gp, grid, st, pdl);
     };
     BatchTimer bt(st);
     // pass 1: sample
     gp.mode = GEMM_MODE_SAMPLE;
     gp.tile_step = tile_step;
     DBG_SYNC(st, "query staging");
-    rc = run_gemm(grid_s);
+    rc = run_gemm(grid_s, false);  // behind the staging copies in plain stream order
     if (rc) return rc;
     DBG_SYNC(st, "gemm_filter_kernel(sample)");
     bt.mark("sample pass");
@@ -1093,16 +1118,15 @@ static int launch_batch(psx_index* h, const float* q_dev, int nq, int k, const p
         sample_rows += std::max<long long>(0, std::min<long long>(sample_cols, h->n - (long long)t * BATCH_BN));
     int rank = (int)((double)T * (double)sample_rows / (double)h->n + 0.5);
     if (rank < 2) rank = 2;
-    theta_kernel<<<nq, 256, 0, st>>>(h->bsample, sample_ld, sample_ld, rank, h->btheta, h->bcount);
+    CU(launch_ex(theta_kernel, (unsigned)nq, 512u, 0, st, chain, (const float*)h->bsample, sample_ld, sample_ld, rank, h->btheta, h->bcount));
     g_launches++;
-    CU(cudaGetLastError());
     DBG_SYNC(st, "theta_kernel");
     bt.mark("theta");
     // pass 2: every tile, threshold test fused into the epilogue
     gp.mode = GEMM_MODE_FILTER;
     gp.tile_step = 1;
     const int grid_f = pair ? std::min(h->sm_count / 2, num_tiles) : std::min(h->sm_count, num_tiles);
-    rc = run_gemm(grid_f);
+    rc = run_gemm(grid_f, chain);
     if (rc) return rc;
     DBG_SYNC(st, "gemm_filter_kernel(filter)");
     bt.mark("filter pass");
@@ -1121,11 +1145,10 @@ static int launch_batch(psx_index* h, const float* q_dev, int nq, int k, const p
     // The kernel multiplies the coefficient by the query's own norm and the largest stored row norm (both on the device).
     (void)qnorm_max;
     const float eps_coef = bf ? 8.2e-3f : 2.2e-3f;
-    rescore_select_kernel<<<nq, 256, smem, st>>>(fp32_rows(h), fld, h->d, h->n, q_dev, k, kpad, h->bcand, h->bcount,
-                                                 cand_cap, h->btheta, eps_coef, h->dmax_sumsq, nullptr, id_base, out_scores, out_ids,
-                                                 out_keys, keys_stride > 0 ? keys_stride : kpad, flags_dev);
+    CU(launch_ex(rescore_select_kernel, (unsigned)nq, 256u, smem, st, chain, fp32_rows(h), fld, h->d, (long long)h->n, q_dev, k, kpad,
+                 (const uint64_t*)h->bcand, (const int*)h->bcount, cand_cap, (const float*)h->btheta, eps_coef, (const float*)h->dmax_sumsq,
+                 (const float*)nullptr, id_base, out_scores, out_ids, out_keys, (long long)(keys_stride > 0 ? keys_stride : kpad), flags_dev));
     g_launches++;
-    CU(cudaGetLastError());
     DBG_SYNC(st, "rescore_select_kernel");
     bt.mark("rescore");
     bt.report();
@@ -1601,6 +1624,14 @@ extern "C" int psx_hybrid_fuse_device(int device, int64_t nq, int64_t kv, const 
     g_launches++;
     CU(cudaGetLastError());
     return PSX_OK;
+}
+
+extern "C" int psx_batch_supported(psx_index* h, int64_t k) {
+    if (!h || is_group(h)) return 0;
+    std::lock_guard<std::mutex> lk(h->mu);
+    DeviceGuard g(h->device);
+    if (flush_pending(h) != PSX_OK) return 0;
+    return batch_shape_ok(h, k) ? 1 : 0;
 }
 
 extern "C" int psx_exchange_status(psx_index* h, int* status) {

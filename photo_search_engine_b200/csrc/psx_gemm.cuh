@@ -77,6 +77,14 @@ __device__ __forceinline__ bool gemm_attr_pass(uint64_t a, const psx_filter& f) 
     return true;
 }
 
+// Programmatic dependent launch inside one batch: sample pass -> theta_kernel -> filter pass -> rescore_select_kernel are
+// launched back to back; each kernel lets its successor become resident at once (launch_dependents at its start) and
+// waits for its predecessor ("has completed, writes visible") only where it consumes what that one produced.  The
+// filter pass's TMA and MMA warps therefore stream and multiply while theta_kernel still runs -- only its epilogue
+// warps wait for the thresholds -- and every launch latency / prologue hides behind the kernel before.
+__device__ __forceinline__ void gemm_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void gemm_pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---- PTX wrappers -----------------------------------------------------------------------------
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
     asm volatile(
@@ -213,6 +221,7 @@ gemm_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int kblocks = (p.d + BK - 1) / BK;
+    gemm_pdl_launch_dependents();
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&map_q);
@@ -301,6 +310,7 @@ gemm_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
         // ===== epilogue: TMEM -> registers -> threshold test -> candidate lists =====
         const int ew = warp - 4;            // TMEM lanes [32*ew, 32*ew + 32)
         const int qlane = ew * 32 + lane;   // query row inside an accumulator tile
+        gemm_pdl_wait();                    // thresholds / zeroed list counters come from the kernel before
         float theta[MT];
         SampleTop top[MT];
 #pragma unroll
@@ -470,6 +480,7 @@ gemm_filter_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
     const bool leader = cta == 0;
     const int kblocks = (p.d + BK - 1) / BK;
     const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+    gemm_pdl_launch_dependents();
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&map_q);
@@ -550,6 +561,7 @@ gemm_filter_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
         // ===== epilogue (each CTA drains its own 128 TMEM lanes = its 128 queries) =====
         const int ew = warp - 4;
         const int qi = (int)cta * GEMM_M + ew * 32 + lane;
+        gemm_pdl_wait();  // thresholds / zeroed list counters come from the kernel before
         const float theta = (p.mode == GEMM_MODE_FILTER && qi < p.nq) ? p.theta[qi] : INFINITY;
         SampleTop top;
         top.init();
@@ -623,14 +635,18 @@ gemm_filter_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
 // between the k-th and roughly the (cand_cap)-th score -- exactness comes from the proof obligation checked after
 // the exact re-score.
 constexpr int THETA_SORT = 2048;
-__global__ void __launch_bounds__(256) theta_kernel(const float* __restrict__ sample, int sample_ld, int ns, int rank,
+__global__ void __launch_bounds__(512) theta_kernel(const float* __restrict__ sample, int sample_ld, int ns, int rank,
                                                     float* __restrict__ theta, int* __restrict__ cand_count) {
     __shared__ uint64_t keys[THETA_SORT];
+    gemm_pdl_launch_dependents();
+    gemm_pdl_wait();  // the sample pass has completed
     const int qi = blockIdx.x;
     const float* s = sample + (size_t)qi * sample_ld;
-    for (int i = threadIdx.x; i < THETA_SORT; i += blockDim.x) keys[i] = i < ns ? make_key(s[i], (uint32_t)i) : 0ull;
+    int np = 64;
+    while (np < ns) np <<= 1;
+    for (int i = threadIdx.x; i < np; i += blockDim.x) keys[i] = i < ns ? make_key(s[i], (uint32_t)i) : 0ull;
     __syncthreads();
-    block_bitonic_sort_desc(keys, THETA_SORT);
+    block_bitonic_sort_desc(keys, np);
     if (threadIdx.x == 0) {
         int r = rank < 1 ? 1 : rank;
         if (r > ns) r = ns;
@@ -669,14 +685,11 @@ rescore_select_kernel(const float* __restrict__ x, int ld, int d, long long n, c
     __shared__ int s_band;
     const int qi = blockIdx.x;
     const int qpad = (ld + 3) & ~3;
+    gemm_pdl_launch_dependents();
     float* sq = reinterpret_cast<float*>(smem_raw);                       // [qpad]
     uint64_t* keys = reinterpret_cast<uint64_t*>(smem_raw + (((size_t)qpad * 4 + 15) & ~(size_t)15));  // [np]
-    const int raw_count = cand_count[qi];
-    const int count = raw_count < cand_cap ? raw_count : cand_cap;
-    int np = kpad;
-    while (np < count) np <<= 1;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-    // the query, and its squared norm for the rounding bound
+    // the query, and its squared norm for the rounding bound (inputs of the whole batch: nothing to wait for)
     float qq = 0.f;
     for (int i = threadIdx.x; i < qpad; i += blockDim.x) {
         const float v = i < d ? q[(size_t)qi * d + i] : 0.f;
@@ -686,6 +699,11 @@ rescore_select_kernel(const float* __restrict__ x, int ld, int d, long long n, c
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) qq += __shfl_xor_sync(0xffffffffu, qq, o);
     if (lane == 0) s_part[warp] = qq;
+    gemm_pdl_wait();  // the lists (filter pass / bf16 scan) are complete
+    const int raw_count = cand_count[qi];
+    const int count = raw_count < cand_cap ? raw_count : cand_cap;
+    int np = kpad;
+    while (np < count) np <<= 1;
     const uint64_t* mine = cand + (size_t)qi * cand_cap;
     for (int i = threadIdx.x; i < np; i += blockDim.x) keys[i] = i < count ? mine[i] : 0ull;
     if (threadIdx.x == 0) s_band = 0;

@@ -584,7 +584,7 @@ static int group_fused_query(psx_index* g, const std::vector<GroupActive>& act, 
     while (np < A * kpad) np <<= 1;
     static std::atomic<bool> ready[64];
     if (home->device < 64 && !ready[home->device].load()) {
-        CU(cudaFuncSetAttribute(merge_wait_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PSX_SMEM_LIMIT));
+        CU(cudaFuncSetAttribute(merge_wait_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PSX_SMEM_LIMIT - 1024));
         ready[home->device].store(true);
     }
     merge_wait_kernel<<<1, 256, (size_t)np * 8, home->stream>>>((const uint64_t*)g->gx, (const uint32_t*)(g->gx + xchg_flag_offset()), A, seq, kp, kpad,

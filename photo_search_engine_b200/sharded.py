@@ -162,8 +162,7 @@ class ShardedIndex:
         (one host synchronisation to read the certificate flags), else one scan per query."""
         local = self.local
         mine, d = b["mine"], local.d
-        eligible = (local.metric == _native.METRIC_IP and getattr(local, "store_dtype", 0) != _native.STORE_BF16
-                    and local.ntotal >= 65536 and d >= 32 and k <= _native.K_PASS_MAX)
+        eligible = local.batch_supported(k) if hasattr(local, "batch_supported") else False
         if not eligible:
             local.search_device(q_dev.data_ptr(), nq, k, 0, 0, mine.data_ptr(), flt=flt, id_base=self.row0, stream=stream)
             return

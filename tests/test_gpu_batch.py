@@ -37,7 +37,7 @@ def _both_paths(ix, q, k):
 
 
 @pytest.mark.parametrize("n,d,nq,k", [(70_000, 64, 5, 10), (200_000, 256, 128, 100), (150_000, 1024, 200, 100),
-                                      (100_000, 768, 300, 50), (66_000, 100, 17, 100), (131_072, 4096, 9, 20), (70_000, 64, 40, 512)])
+                                      (100_000, 768, 300, 50), (66_000, 100, 17, 100), (131_072, 4096, 9, 20), (110_000, 64, 40, 512)])
 def test_batch_equals_scan(n, d, nq, k):
     rng = np.random.default_rng(n + d + nq)
     x = unit_rows(rng, n, d)
