@@ -88,7 +88,8 @@ struct psx_index {
 
     uint64_t* lists = nullptr;  // [grid][kpad]
     size_t lists_cap = 0;
-    unsigned int* counter = nullptr;  // [0] merge tickets, [1] / [3] dynamic-tail tickets of even / odd launches, [2] entries of rowlist
+    unsigned int* counter = nullptr;  // [0] merge tickets, [1] / [3] dynamic-tail tickets of even / odd launches, [2] / [4] entries of the even / odd rowlist
+    unsigned long long list_seq = 0;  // row lists written so far (alternates the two lists)
     unsigned long long scan_seq = 0;  // launches so far (alternates the dynamic-tail ticket word)
     // Programmatic dependent launch of the scans: 0 = never; 1 = the 2nd, 3rd ... scan of ONE API call overlaps its
     // predecessor (default: the call's first launch is in plain stream order, so whatever produced the queries is
@@ -97,7 +98,7 @@ struct psx_index {
     // (queries resident on the device, or delivered by a memcpy).
     int pdl = 1;
     bool call_first = true;  // no scan launched yet in the current API call
-    uint32_t* rowlist = nullptr;      // [cap] ids of the rows that pass the current query's predicate
+    uint32_t* rowlist = nullptr;      // [2][cap] ids of the rows that pass the current / the next query's predicate
     long long rowlist_cap = 0;
     bool deal = true;        // unfiltered scans: dealt units with a dynamic tail (false: static predicate groups)
     bool dyn_tail = true;
@@ -119,6 +120,7 @@ struct psx_index {
     float max_norm = 0.f;         // host copy of its square root
     int batch_min = 4;        // smallest nq routed to the tensor-core path
     bool batch_pair = true;   // 129..256 queries: CTA-pair (cta_group::2) kernel instead of two accumulators per CTA
+    bool batch_pdl = true;    // the kernels of one batch chain by programmatic dependent launch (tunable "batch_pdl")
     bool batch_bf16 = true;   // PSX_STORE_BF16_MASTER: the batched GEMM reads the bf16 rows (kind::f16) instead of the fp32 master (kind::tf32)
     float* bq = nullptr;      // [256][ld] zero-padded query block
     int bq_dirty_rows = BATCH_MAX_Q_ROWS;  // leading rows of bq that may hold non-zero data (rows beyond nq must read as zero)
@@ -320,8 +322,8 @@ extern "C" int psx_create(int d, int metric, int store_dtype, int device, psx_in
     auto init = [&]() -> int {
         CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
         CU(cudaEventCreateWithFlags(&h->last_ev, cudaEventDisableTiming));
-        CU(cudaMalloc(&h->counter, 4 * sizeof(unsigned int)));
-        CU(cudaMemset(h->counter, 0, 4 * sizeof(unsigned int)));
+        CU(cudaMalloc(&h->counter, 8 * sizeof(unsigned int)));
+        CU(cudaMemset(h->counter, 0, 8 * sizeof(unsigned int)));
         CU(cudaMalloc(&h->dmax_sumsq, sizeof(float)));
         CU(cudaMemset(h->dmax_sumsq, 0, sizeof(float)));
         return set_max_smem(merge_keys_kernel);
@@ -711,6 +713,9 @@ static int plan_scan_with(psx_index* h, bool master, int k, int W, int mode, boo
     int S = h->stages;
     // short rows leave part of every 4 KB slot unused: keep the bytes in flight up with a third stage
     if (h->stages_auto && p.cpr == 1 && (size_t)p.rps * a.row_bytes * 5 < (size_t)PSX_SLOT_BYTES * 4) S = 3;
+    // row lists are short (that is the point of a predicate): a warp's share is a handful of rows, fetched one bulk copy
+    // each -- the number of round trips, not the bytes, sets the time, so give the ring its third slot
+    if (h->stages_auto && listed && p.cpr == 1) S = 3;
     while (S > 2 && smem_for(S) > limit) --S;
     // the merge reuses the ring: it must hold at least two lists
     while ((size_t)W * S * PSX_SLOT_BYTES / 8 < (size_t)2 * p.kpad && smem_for(S + 1) <= PSX_SMEM_LIMIT) ++S;
@@ -765,28 +770,35 @@ static int launch_scan(psx_index* h, const float* q_dev, int k, const psx_filter
     int rc = plan_scan(h, master, k, mode, listed, plan);
     if (rc) return rc;
     ScanParams& p = plan.p;
+    // may this launch start while the kernel before it in the stream still runs?  (back-to-back queries, also behind the
+    // merge kernel of a sharded query.)  Launches that consume a condition flag or a page ceiling written right before
+    // them, or that are traced, keep full stream order.
+    const bool overlap_ok = !cond_flag && !ceil_ptr && !h->trace;
+    const bool overlap_prev = (h->pdl >= 2 || (h->pdl == 1 && !h->call_first)) && overlap_ok;
+    p.list_count = h->counter + 2;
     if (listed) {
         if (h->rowlist_cap < h->cap) {
             CU(cudaStreamSynchronize(st));
             cudaFree(h->rowlist);
             h->rowlist = nullptr;
             h->rowlist_cap = 0;
-            CU(cudaMalloc(&h->rowlist, (size_t)h->cap * sizeof(uint32_t)));
+            CU(cudaMalloc(&h->rowlist, (size_t)2 * h->cap * sizeof(uint32_t)));
             h->rowlist_cap = h->cap;
         }
+        // two lists alternate, so that the list of query i+1 can be compacted while the scan of query i sorts and merges
+        const int slot = (int)(h->list_seq++ & 1ull);
+        uint32_t* list = h->rowlist + (size_t)slot * h->rowlist_cap;
+        p.list_count = h->counter + (slot ? 4 : 2);
         const long long chunks = (h->n + 2047) / 2048;  // 256 threads x 8 rows per trip
         const unsigned blocks = (unsigned)std::max<long long>(1, std::min<long long>(chunks, (long long)h->sm_count * 8));
-        filter_list_kernel<<<blocks, 256, 0, st>>>(h->attrs, h->n, *f, h->rowlist, h->counter + 2, cond_flag);
+        CU(launch_ex(filter_list_kernel, blocks, 256u, 0, st, overlap_prev, (const uint64_t*)h->attrs, (long long)h->n, *f, list, p.list_count,
+                     cond_flag));
         g_launches++;
-        CU(cudaGetLastError());
-        p.rowlist = h->rowlist;
+        p.rowlist = list;
     }
-    p.list_count = h->counter + 2;
     p.work = h->counter + ((h->scan_seq++ & 1ull) ? 3 : 1);
-    // the overlap is for back-to-back queries (also behind the merge kernel of a sharded query); launches that consume
-    // what the kernel right before them wrote (a row list, a condition flag, a page ceiling) or that are traced keep
-    // full stream order
-    plan.pdl = (h->pdl >= 2 || (h->pdl == 1 && !h->call_first)) && !listed && !cond_flag && !ceil_ptr && !h->trace;
+    // a row-list scan always overlaps the kernel that writes its list (it waits for it before reading the list)
+    plan.pdl = listed ? (h->pdl >= 1 && overlap_ok) : overlap_prev;
     h->call_first = false;
     const size_t need_lists = (size_t)plan.grid * p.kpad;
     if (need_lists > h->lists_cap) {
@@ -1095,7 +1107,7 @@ static int launch_batch(psx_index* h, const float* q_dev, int nq, int k, const p
         gp.f = *f;
     }
     // the kernels of one batch chain by programmatic dependent launch (see psx_gemm.cuh) unless a phase is being timed
-    const bool chain = !BatchTimer::enabled() && !debug_sync();
+    const bool chain = h->batch_pdl && !BatchTimer::enabled() && !debug_sync();
     auto run_gemm = [&](int grid, bool pdl) -> int {
         if (bf)
             return pair ? launch_gemm_pair<true>(h, mq, mx, gp, grid, st, pdl)
@@ -1687,6 +1699,8 @@ extern "C" int psx_set_tunable(psx_index* h, const char* key, int value) {
         h->filter_mode = value < 0 || value > 2 ? 0 : value;
     } else if (!strcmp(key, "batch_pair")) {
         h->batch_pair = value > 0;
+    } else if (!strcmp(key, "batch_pdl")) {  // 1 = the kernels of a batch overlap by programmatic dependent launch (default), 0 = plain stream order
+        h->batch_pdl = value != 0;
     } else if (!strcmp(key, "batch_bf16")) {  // bf16+master indexes: 1 = bf16 GEMM over the bf16 rows (default), 0 = TF32 GEMM over the master
         h->batch_bf16 = value > 0;
     } else if (!strcmp(key, "batch_min")) {  // smallest nq sent to the tensor-core path; 0 disables it

@@ -78,10 +78,15 @@ __device__ __forceinline__ bool gemm_attr_pass(uint64_t a, const psx_filter& f) 
 }
 
 // Programmatic dependent launch inside one batch: sample pass -> theta_kernel -> filter pass -> rescore_select_kernel are
-// launched back to back; each kernel lets its successor become resident at once (launch_dependents at its start) and
-// waits for its predecessor ("has completed, writes visible") only where it consumes what that one produced.  The
-// filter pass's TMA and MMA warps therefore stream and multiply while theta_kernel still runs -- only its epilogue
-// warps wait for the thresholds -- and every launch latency / prologue hides behind the kernel before.
+// launched back to back, each (but the first) allowed to become resident before its predecessor has drained.  Every
+// thread of a kernel executes griddepcontrol.wait ("the predecessor has completed, its writes are visible") BEFORE the
+// kernel signals its own dependents -- the order the scan kernel uses -- so "this grid has completed" keeps implying
+// "every earlier grid has":
+//   sample pass   signals at once (it is launched in plain stream order); theta_kernel's CTAs sit in their wait meanwhile;
+//   theta_kernel  waits, signals, then sorts: the filter pass launches while the thresholds are being computed;
+//   filter pass   its TMA and MMA warps run two tiles ahead before they wait, its epilogue warps wait before they read
+//                 the thresholds -- the tensor pipe is busy while theta_kernel still runs; it signals when it is done;
+//   rescore       loads its query, waits, re-scores.
 __device__ __forceinline__ void gemm_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void gemm_pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
@@ -221,7 +226,7 @@ gemm_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int kblocks = (p.d + BK - 1) / BK;
-    gemm_pdl_launch_dependents();
+    if (p.mode == GEMM_MODE_SAMPLE) gemm_pdl_launch_dependents();
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&map_q);
@@ -250,6 +255,7 @@ gemm_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
         if (lane == 0) {
             int s = 0;
             uint32_t ph = 0;
+            bool waited = false;
             for (int t = first; t < p.num_tiles; t += stride) {
                 const int row0 = t * BN;
                 for (int kb = 0; kb < kblocks; ++kb) {
@@ -266,7 +272,14 @@ gemm_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
                         ph ^= 1u;
                     }
                 }
+                if (!waited) {  // one tile ahead of the predecessor (it only reads the corpus and the staged queries)
+                    gemm_pdl_wait();
+                    waited = true;
+                }
             }
+            if (!waited) gemm_pdl_wait();
+        } else {
+            gemm_pdl_wait();
         }
     } else if (warp == 1) {
         // ===== MMA issuer (one thread) =====
@@ -274,7 +287,12 @@ gemm_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
             constexpr uint32_t idesc = umma_idesc<BF>(GEMM_M, BN);
             int s = 0, a = 0;
             uint32_t ph = 0, aph = 0;
+            bool waited = false;
             for (int t = first; t < p.num_tiles; t += stride) {
+                if (a == 1 && !waited) {  // the first accumulator is on its way: now wait for the predecessor
+                    gemm_pdl_wait();
+                    waited = true;
+                }
                 mbar_wait(smem_u32(acc_empty + a), aph ^ 1u);  // epilogue drained this accumulator
                 tc_fence_after();
                 for (int kb = 0; kb < kblocks; ++kb) {
@@ -304,9 +322,18 @@ gemm_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
                     a = 0;
                     aph ^= 1u;
                 }
+                if (ACC_STAGES == 1 && !waited) {
+                    gemm_pdl_wait();
+                    waited = true;
+                }
             }
+            if (!waited) gemm_pdl_wait();
+        } else {
+            gemm_pdl_wait();
         }
-    } else if (warp >= 4) {
+    } else if (warp < 4) {
+        gemm_pdl_wait();  // idle warps (2: TMEM allocation, 3: spare)
+    } else {
         // ===== epilogue: TMEM -> registers -> threshold test -> candidate lists =====
         const int ew = warp - 4;            // TMEM lanes [32*ew, 32*ew + 32)
         const int qlane = ew * 32 + lane;   // query row inside an accumulator tile
@@ -390,6 +417,7 @@ gemm_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
     }
     tc_fence_before();
     __syncthreads();
+    if (p.mode == GEMM_MODE_FILTER) gemm_pdl_launch_dependents();  // every thread has waited for the predecessor by now
     if (warp == 2) {
         tc_fence_after();
         tmem_dealloc(tmem_base, 512);
@@ -480,7 +508,7 @@ gemm_filter_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
     const bool leader = cta == 0;
     const int kblocks = (p.d + BK - 1) / BK;
     const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
-    gemm_pdl_launch_dependents();
+    if (p.mode == GEMM_MODE_SAMPLE) gemm_pdl_launch_dependents();
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&map_q);
@@ -509,6 +537,7 @@ gemm_filter_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
         if (lane == 0) {
             int s = 0;
             uint32_t ph = 0;
+            bool waited = false;
             for (int t = first; t < p.num_tiles; t += stride) {
                 const int row0 = t * BN + (int)cta * (BN / 2);
                 for (int kb = 0; kb < kblocks; ++kb) {
@@ -524,7 +553,14 @@ gemm_filter_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
                         ph ^= 1u;
                     }
                 }
+                if (!waited) {  // one tile ahead of the predecessor (see gemm_filter_kernel)
+                    gemm_pdl_wait();
+                    waited = true;
+                }
             }
+            if (!waited) gemm_pdl_wait();
+        } else {
+            gemm_pdl_wait();
         }
     } else if (warp == 1) {
         // ===== MMA issuer: one thread of the leader CTA drives both tensor cores =====
@@ -532,7 +568,12 @@ gemm_filter_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
             constexpr uint32_t idesc = umma_idesc<BF>(2 * GEMM_M, BN);
             int s = 0, a = 0;
             uint32_t ph = 0, aph = 0;
+            bool waited = false;
             for (int t = first; t < p.num_tiles; t += stride) {
+                if (a == 1 && !waited) {  // the first accumulator is on its way: now wait for the predecessor
+                    gemm_pdl_wait();
+                    waited = true;
+                }
                 mbar_wait(smem_u32(acc_empty + a), aph ^ 1u);
                 tc_fence_after();
                 for (int kb = 0; kb < kblocks; ++kb) {
@@ -556,8 +597,13 @@ gemm_filter_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
                     aph ^= 1u;
                 }
             }
+            if (!waited) gemm_pdl_wait();
+        } else {
+            gemm_pdl_wait();
         }
-    } else if (warp >= 4) {
+    } else if (warp < 4) {
+        gemm_pdl_wait();  // idle warps
+    } else {
         // ===== epilogue (each CTA drains its own 128 TMEM lanes = its 128 queries) =====
         const int ew = warp - 4;
         const int qi = (int)cta * GEMM_M + ew * 32 + lane;
@@ -623,6 +669,7 @@ gemm_filter_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
     }
     tc_fence_before();
     cluster_sync_all();
+    if (p.mode == GEMM_MODE_FILTER) gemm_pdl_launch_dependents();  // every thread has waited for the predecessor by now
     if (warp == 2) {
         tc_fence_after();
         tmem_dealloc_2sm(tmem_base, 512);
@@ -638,8 +685,8 @@ constexpr int THETA_SORT = 2048;
 __global__ void __launch_bounds__(512) theta_kernel(const float* __restrict__ sample, int sample_ld, int ns, int rank,
                                                     float* __restrict__ theta, int* __restrict__ cand_count) {
     __shared__ uint64_t keys[THETA_SORT];
-    gemm_pdl_launch_dependents();
     gemm_pdl_wait();  // the sample pass has completed
+    gemm_pdl_launch_dependents();
     const int qi = blockIdx.x;
     const float* s = sample + (size_t)qi * sample_ld;
     int np = 64;
@@ -685,7 +732,6 @@ rescore_select_kernel(const float* __restrict__ x, int ld, int d, long long n, c
     __shared__ int s_band;
     const int qi = blockIdx.x;
     const int qpad = (ld + 3) & ~3;
-    gemm_pdl_launch_dependents();
     float* sq = reinterpret_cast<float*>(smem_raw);                       // [qpad]
     uint64_t* keys = reinterpret_cast<uint64_t*>(smem_raw + (((size_t)qpad * 4 + 15) & ~(size_t)15));  // [np]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
@@ -700,6 +746,7 @@ rescore_select_kernel(const float* __restrict__ x, int ld, int d, long long n, c
     for (int o = 16; o > 0; o >>= 1) qq += __shfl_xor_sync(0xffffffffu, qq, o);
     if (lane == 0) s_part[warp] = qq;
     gemm_pdl_wait();  // the lists (filter pass / bf16 scan) are complete
+    gemm_pdl_launch_dependents();
     const int raw_count = cand_count[qi];
     const int count = raw_count < cand_cap ? raw_count : cand_cap;
     int np = kpad;

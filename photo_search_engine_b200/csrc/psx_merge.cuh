@@ -15,6 +15,11 @@ __global__ void __launch_bounds__(256) filter_list_kernel(const uint64_t* __rest
     __shared__ unsigned int s_warp[8];
     __shared__ unsigned int s_base;
     if (cond_flag && *cond_flag == 0) return;  // the conditional scan this list is for will not run either
+    // Programmatic dependent launch: the scan that consumes this list may become resident now (it waits for this grid
+    // before it reads the list).  This kernel itself may have started while the scan BEFORE it still sorts and merges: it
+    // only reads the attribute words and writes the list / counter slot that scan does not use (two alternate), and it
+    // waits for that scan at its very end, so "this grid has completed" keeps implying "every earlier grid has".
+    pdl_launch_dependents();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     constexpr int PER = 8;  // rows per thread and trip: four 16-byte loads in flight per thread
     const long long chunk = (long long)blockDim.x * PER;
@@ -68,6 +73,7 @@ __global__ void __launch_bounds__(256) filter_list_kernel(const uint64_t* __rest
         }
         __syncthreads();  // s_warp / s_base are reused by the next trip
     }
+    pdl_wait();
 }
 
 // K4 fused, receiving side: wait until every rank's list for query `seq` has landed in this GPU's

@@ -360,6 +360,8 @@ __global__ void __launch_bounds__(PSX_MAX_THREADS, 1) scan_topk_kernel(const Sca
     dot.load_query(q4, lane);
 
     const bool listed = MODE == PSX_SCAN_DEAL && p.rowlist != nullptr;
+    // a row-list launch follows the kernel that wrote the list: everything above overlapped it, the list is read below
+    if (listed) pdl_wait();
     bool p_exhausted = false;
     int p_chunk = 0;         // long rows: next chunk of the current row
     int in_flight = 0;

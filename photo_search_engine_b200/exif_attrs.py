@@ -145,3 +145,30 @@ def build_filter(constraints: Optional[Dict[str, Any]]) -> Tuple[Optional[PsxFil
     if not f.flags:
         return None, False
     return f, never
+
+
+def words_pass(words: np.ndarray, flt: PsxFilter) -> np.ndarray:
+    """numpy form of ``attr_pass`` (csrc/psx_scan.cuh) over packed attribute words: which rows pass ``flt``.
+    Used where the predicate has to be evaluated for a handful of candidate rows on the host (the post-filter of
+    ``searcher_ext.FusedRecallMixin``); the scan evaluates the same conjunction on the device."""
+    w = np.asarray(words, dtype=np.uint64)
+    ok = np.ones(w.shape[0], bool)
+    fl = int(flt.flags)
+    if fl & (F_SEASON | F_PERIOD | F_YEAR | F_MONTH):
+        ok &= (w >> np.uint64(63)).astype(bool)
+        if fl & F_SEASON:
+            ok &= ((w >> np.uint64(_SEASON_SHIFT)) & np.uint64(7)) == np.uint64(flt.season)
+        if fl & F_PERIOD:
+            ok &= ((w >> np.uint64(_PERIOD_SHIFT)) & np.uint64(7)) == np.uint64(flt.period)
+        if fl & F_YEAR:
+            ok &= ((w >> np.uint64(_YEAR_SHIFT)) & np.uint64(0x3FFF)) == np.uint64(flt.year)
+        if fl & F_MONTH:
+            ok &= ((w >> np.uint64(_MONTH_SHIFT)) & np.uint64(0xF)) == np.uint64(flt.month)
+    if fl & F_NEED_DT:
+        dt = w & np.uint64((1 << _DT_BITS) - 1)
+        ok &= dt != 0
+        if fl & F_START:
+            ok &= dt >= np.uint64(flt.start)
+        if fl & F_END:
+            ok &= dt <= np.uint64(flt.end)
+    return ok

@@ -24,7 +24,8 @@ Nothing here imports the reference: the mixin only relies on the method names ci
 from __future__ import annotations
 
 import threading
-from typing import Any, Dict, List, Optional, Sequence
+from collections.abc import Sequence
+from typing import Any, Dict, List, Optional
 
 import numpy as np
 
@@ -53,6 +54,19 @@ class _PrefetchingStore:
         fused = getattr(self._local, "constraints", None)
         if fused and not args and "constraints" not in kwargs:
             return self._store.search(query_embedding, top_k, constraints=fused)
+        # FusedRecallMixin: the hits stay arrays (dicts only on demand)
+        if getattr(self._local, "lazy", False) and not args and not kwargs and query_embedding is not None:
+            store = self._store
+            if getattr(store, "index", None) is None or store.get_total_items() == 0:
+                return []
+            k = min(int(top_k), int(store.get_total_items()))
+            if k <= 0:
+                return []
+            if len(query_embedding) != store.dimension:
+                return store.search(query_embedding, top_k)  # raises the reference's ValueError
+            row = np.array([store._normalize_vector(query_embedding)], dtype="float32")
+            scores, ids = store.search_batch(row, k, normalize=False)
+            return _LazyHits(store.metadata, scores[0], ids[0])
         prefetched = getattr(self._local, "prefetch", None)
         if prefetched and not args and not kwargs and query_embedding is not None:
             got = prefetched.get(_embedding_key(query_embedding))
@@ -229,3 +243,209 @@ class FusedPrefilterMixin:
             return super()._run_single_search_round(constraints=constraints, has_filter=has_filter, **kwargs)
         finally:
             self._psx_local.constraints = None
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# the Python tail of a search round
+# ---------------------------------------------------------------------------------------------------------------------
+class _LazyHits(Sequence):
+    """What ``vector_store.search`` returns under ``FusedRecallMixin``: the FAISS-shaped arrays of the search, behaving
+    as the reference's ``List[{"metadata", "distance"}]`` for any code that iterates it (dicts are built on demand)."""
+
+    def __init__(self, records: List[Dict], scores: np.ndarray, ids: np.ndarray) -> None:
+        keep = ids >= 0
+        self.records, self.ids, self.distances = records, ids[keep], scores[keep]
+
+    def __len__(self) -> int:
+        return int(self.ids.shape[0])
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [self[j] for j in range(*i.indices(len(self)))]
+        return {"metadata": self.records[int(self.ids[i])], "distance": float(self.distances[i])}
+
+
+class _LazyCombined(Sequence):
+    """``_vector_results_to_combined`` under ``FusedRecallMixin``: candidate rows, their scores (the reference's own
+    ``_distance_to_score``) in recall order, de-duplicated by path key.  Iterating it yields the reference's dicts."""
+
+    def __init__(self, owner: Any, records: List[Dict], rows: List[int], scores: List[float]) -> None:
+        self.owner, self.records, self.rows, self.scores = owner, records, rows, scores
+
+    def __len__(self) -> int:
+        return len(self.rows)
+
+    def item(self, i: int) -> Dict[str, Any]:
+        metadata = self.records[self.rows[i]] or {}
+        return {
+            "photo_path": metadata.get("photo_path"),
+            "description": metadata.get("description"),
+            "retrieval_text": metadata.get("retrieval_text"),
+            "score": self.scores[i],
+            "metadata": metadata,
+            "match_summary": self.owner._psx_match_summary(metadata),
+        }
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [self.item(j) for j in range(*i.indices(len(self)))]
+        return self.item(i)
+
+
+class FusedRecallMixin:
+    """Opt-in: once the scan takes a few milliseconds, a search round is dominated by
+    O(candidate_k) Python -- one dict, one ``normalize_local_path``, one ``build_match_summary`` and (under a time
+    filter) several ``strptime`` calls per candidate (core/searcher.py:1131-1156, :1460-1565, :1884-2001) although only
+    ``top_k`` of the 500-1333 candidates are returned.  This mixin keeps the candidates as arrays from the store
+    (``search_batch``) to the end of ``_finalize_results`` and builds dicts for the returned photos only::
+
+        class MySearcher(FusedRecallMixin, Searcher): ...
+
+    Results are identical to the unmodified Searcher: scores come from its own ``_distance_to_score``, the thresholds
+    from its own ``_calculate_dynamic_threshold`` / ``_get_round_score_floors``, path keys from its own ``_path_key``
+    (cached per row), the time filter from the packed EXIF words the fused predicate uses (same conjunction as
+    ``_check_time_match_v2``; constraints that cannot be packed go through the reference function).  Only the pure
+    vector branch without media / identity terms takes the array path; every other case (Elasticsearch hybrid rounds,
+    term matching, file-existence validation) runs the reference code on lazily materialised dicts.  Combine with the
+    other mixins by listing this one first.
+    """
+
+    def __init__(self, *args: Any, **kwargs: Any) -> None:
+        super().__init__(*args, **kwargs)
+        if not hasattr(self, "_psx_local"):
+            self._psx_local = threading.local()
+        if not isinstance(self.vector_store, _PrefetchingStore):
+            self.vector_store = _PrefetchingStore(self.vector_store, self._psx_local)
+        self._psx_key_cache: Dict[int, str] = {}
+        self._psx_key_owner: Any = None
+        self.psx_recall_stats = {"array_rounds": 0, "reference_rounds": 0}
+
+    # -- helpers ---------------------------------------------------------------------------------------------------
+    def _psx_match_summary(self, metadata: Dict[str, Any]) -> Any:
+        import sys
+
+        for klass in type(self).__mro__:
+            mod = sys.modules.get(klass.__module__)
+            fn = getattr(mod, "build_match_summary", None) if mod is not None else None
+            if callable(fn):  # the name core.searcher imported (utils/structured_analysis.py)
+                return fn(metadata)
+        return None
+
+    def _psx_row_keys(self, store: Any, rows: Sequence[int]) -> List[str]:
+        """``_path_key`` of the photo of every row, cached (the key of a row never changes while the store lives)."""
+        records = store.metadata
+        if self._psx_key_owner is not records:  # load() / clear() replaced the list
+            self._psx_key_cache, self._psx_key_owner = {}, records
+        cache, out = self._psx_key_cache, []
+        for row in rows:
+            key = cache.get(row)
+            if key is None:
+                photo_path = (records[row] or {}).get("photo_path")
+                key = self._path_key(photo_path) if photo_path else ""
+                cache[row] = key
+            out.append(key)
+        return out
+
+    # -- the three hooks --------------------------------------------------------------------------------------------
+    def _run_single_search_round(self, **kwargs: Any):
+        fast = (self.keyword_store is None and not kwargs.get("media_terms") and not kwargs.get("identity_terms")
+                and not getattr(self, "validate_file_exists", False) and hasattr(self.vector_store._store, "search_batch")
+                and not getattr(self._psx_local, "constraints", None))
+        self._psx_local.lazy = bool(fast)
+        self.psx_recall_stats["array_rounds" if fast else "reference_rounds"] += 1
+        try:
+            return super()._run_single_search_round(**kwargs)
+        finally:
+            self._psx_local.lazy = False
+
+    def _vector_results_to_combined(self, raw_results):
+        if not isinstance(raw_results, _LazyHits):
+            return super()._vector_results_to_combined(raw_results)
+        store = self.vector_store._store
+        rows = raw_results.ids.tolist()
+        keys = self._psx_row_keys(store, rows)
+        kept_rows: List[int] = []
+        kept_scores: List[float] = []
+        seen = set()
+        for row, distance, key in zip(rows, raw_results.distances.tolist(), keys):
+            # the reference drops hits without a usable path, then keeps the first hit per path key: hits arrive best
+            # first and _distance_to_score is monotone, so a later duplicate never has a strictly higher score
+            if not key or key in seen:
+                continue
+            seen.add(key)
+            kept_rows.append(row)
+            kept_scores.append(self._distance_to_score(float(distance)))
+        return _LazyCombined(self, raw_results.records, kept_rows, kept_scores)
+
+    def _finalize_results(self, combined_results, normalized_top_k, has_filter, constraints, search_text="", media_terms=None,
+                          identity_terms=None, strict_identity_filter=False, relaxation_level=0, strip_internal=True):
+        if not isinstance(combined_results, _LazyCombined) or media_terms or identity_terms or self.keyword_store is not None:
+            if isinstance(combined_results, _LazyCombined):
+                combined_results = list(combined_results)
+            return super()._finalize_results(combined_results=combined_results, normalized_top_k=normalized_top_k, has_filter=has_filter,
+                                             constraints=constraints, search_text=search_text, media_terms=media_terms,
+                                             identity_terms=identity_terms, strict_identity_filter=strict_identity_filter,
+                                             relaxation_level=relaxation_level, strip_internal=strip_internal)
+        from .exif_attrs import attr_words, build_filter, words_pass
+
+        records, rows, scores = combined_results.records, combined_results.rows, combined_results.scores
+        if has_filter:  # post-filter of the pure vector branch (core/searcher.py:1477-1480)
+            flt, never = build_filter(constraints) if constraints else (None, False)
+            if never:  # not representable as packed words: the reference function, candidate by candidate
+                keep = [self._check_time_match_v2(records[r] or {}, constraints) for r in rows]
+            elif flt is None:
+                keep = [True] * len(rows)
+            else:
+                store = self.vector_store._store
+                words = getattr(store, "_attr_words", None)
+                if words is not None and getattr(store, "_attrs_built", 0) == len(records) and len(words) == len(records):
+                    cand_words = np.asarray(words)[np.asarray(rows, dtype=np.int64)] if rows else np.zeros(0, np.uint64)
+                else:
+                    cand_words = attr_words([records[r] or {} for r in rows])
+                keep = words_pass(cand_words, flt).tolist()
+            rows = [r for r, ok in zip(rows, keep) if ok]
+            scores = [s for s, ok in zip(scores, keep) if ok]
+        # thresholds and buckets: the reference's own arithmetic on the same list of scores
+        strict_floor, broad_floor = self._get_round_score_floors(relaxation_level)
+        if scores:
+            dynamic_threshold = self._calculate_dynamic_threshold(scores, normalized_top_k)
+            strict_threshold = max(dynamic_threshold, strict_floor)
+            broad_threshold = min(strict_threshold - 0.05, max(broad_floor, strict_threshold * 0.84))
+            broad_threshold = round(max(broad_floor, broad_threshold), 6)
+        else:
+            strict_threshold, broad_threshold = strict_floor, broad_floor
+        buckets = [3 if s >= strict_threshold else 2 if s >= broad_threshold else 1 for s in scores]
+        reliable = [i for i, b in enumerate(buckets) if b >= 3]
+        generalized = [i for i, b in enumerate(buckets) if b == 2]
+        prioritized = reliable + generalized
+        # _fill_results_to_top_k: prioritised first, then the remaining candidates in recall order (path keys are unique here)
+        chosen = prioritized[:normalized_top_k]
+        if len(chosen) < normalized_top_k:
+            taken = set(chosen)
+            for i in range(len(rows)):
+                if i not in taken:
+                    chosen.append(i)
+                    if len(chosen) >= normalized_top_k:
+                        break
+        prioritized_set = set(prioritized)
+        level = max(0, int(relaxation_level))
+        self._last_round_quality = {
+            "raw_count": len(rows),
+            "returned_count": len(chosen),
+            "reliable_count": len(reliable),
+            "generalized_count": len(prioritized),
+            "fallback_used_count": sum(1 for i in chosen if i not in prioritized_set),
+            "strict_threshold": round(strict_threshold, 6),
+            "broad_threshold": round(broad_threshold, 6),
+            "relaxation_level": level,
+            "top_score": round(float(scores[0]), 6) if scores else 0.0,
+        }
+        view = _LazyCombined(self, records, rows, scores)
+        final_results = []
+        for rank, i in enumerate(chosen, start=1):
+            item = view.item(i)
+            item["_confidence_bucket"] = buckets[i]
+            item["_relaxation_level"] = level
+            item["rank"] = rank
+            final_results.append(item)
+        return self._sanitize_results(final_results) if strip_internal else final_results

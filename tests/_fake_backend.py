@@ -16,27 +16,9 @@ from photo_search_engine_b200 import _native as N
 
 def attr_pass_np(words: np.ndarray, f: N.PsxFilter) -> np.ndarray:
     """numpy restatement of ``attr_pass`` (csrc/psx_scan.cuh) over packed attribute words."""
-    w = words.astype(np.uint64)
-    ok = np.ones(w.shape[0], bool)
-    fl = int(f.flags)
-    if fl & (N.F_SEASON | N.F_PERIOD | N.F_YEAR | N.F_MONTH):
-        ok &= (w >> np.uint64(63)).astype(bool)
-        if fl & N.F_SEASON:
-            ok &= ((w >> np.uint64(60)) & np.uint64(7)) == np.uint64(f.season)
-        if fl & N.F_PERIOD:
-            ok &= ((w >> np.uint64(57)) & np.uint64(7)) == np.uint64(f.period)
-        if fl & N.F_YEAR:
-            ok &= ((w >> np.uint64(43)) & np.uint64(0x3FFF)) == np.uint64(f.year)
-        if fl & N.F_MONTH:
-            ok &= ((w >> np.uint64(39)) & np.uint64(0xF)) == np.uint64(f.month)
-    if fl & N.F_NEED_DT:
-        dt = w & np.uint64((1 << 39) - 1)
-        ok &= dt != 0
-        if fl & N.F_START:
-            ok &= dt >= np.uint64(f.start)
-        if fl & N.F_END:
-            ok &= dt <= np.uint64(f.end)
-    return ok
+    from photo_search_engine_b200.exif_attrs import words_pass
+
+    return words_pass(words, f)
 
 
 class FakeIndex:

@@ -14,7 +14,7 @@ import ref_inject_plugin  # noqa: F401  (installs utils.vector_store -> the drop
 from core.searcher import Searcher  # the reference, unmodified
 from tests.helpers import FakeQueryFormatter, FakeTimeParser  # the reference's own fakes
 
-from photo_search_engine_b200.searcher_ext import BatchedExpansionMixin, FusedPrefilterMixin
+from photo_search_engine_b200.searcher_ext import BatchedExpansionMixin, FusedPrefilterMixin, FusedRecallMixin
 from photo_search_engine_b200.vector_store import VectorStore
 
 D = 16
@@ -61,6 +61,80 @@ class BatchedSearcher(BatchedExpansionMixin, Searcher):
 
 class PrefilterSearcher(FusedPrefilterMixin, BatchedExpansionMixin, Searcher):
     pass
+
+
+class RecallSearcher(FusedRecallMixin, Searcher):
+    pass
+
+
+def recall_case(tmp):
+    """FusedRecallMixin: candidates stay arrays through _vector_results_to_combined / _finalize_results; every round
+    (plain, time-filtered, relaxed, tiny top_k, duplicates by path, rows without a path) must return exactly what the
+    unmodified Searcher returns, including _last_round_quality, and materialise far fewer dicts."""
+    import time as _time
+
+    rng = np.random.default_rng(21)
+    n = 3000
+    rows = rng.standard_normal((n, D)).astype(np.float32)
+    rows[1500] = rows[7]                                  # same vector under another path
+    metas = []
+    for i in range(n):
+        stamp = f"20{10 + i % 15:02d}-{1 + i % 12:02d}-{1 + i % 27:02d}T{i % 24:02d}:30:00"
+        has_exif = i % 5 != 0
+        metas.append({
+            "photo_path": f"/photos/album{i % 31}/IMG_{i}.JPG" if i % 97 != 3 else ("" if i % 2 else None),
+            "description": f"photo {i}", "retrieval_text": f"text {i}",
+            "exif_data": {"datetime": stamp} if has_exif else {},
+            "time_info": ({"year": 2010 + i % 15, "month": 1 + i % 12, "season": ["春天", "夏天", "秋天", "冬天"][i % 4],
+                           "time_period": ["凌晨", "早晨", "上午", "中午", "下午", "傍晚", "夜晚"][i % 7], "datetime_str": stamp}
+                          if has_exif else {}),
+        })
+    metas[40]["photo_path"] = metas[41]["photo_path"].lower()   # normcase-equal on Windows only; distinct here
+    metas[60]["photo_path"] = metas[61]["photo_path"]           # an exact duplicate path
+    rounds = [
+        dict(constraints={}, has_filter=False, normalized_top_k=10, relaxation_level=0),
+        dict(constraints={}, has_filter=False, normalized_top_k=50, relaxation_level=2),
+        dict(constraints={"start_date": "2015-01-01", "end_date": "2018-12-31", "precision": "year"}, has_filter=True,
+             normalized_top_k=10, relaxation_level=0),
+        dict(constraints={"season": "夏天", "time_period": "下午"}, has_filter=True, normalized_top_k=5, relaxation_level=1),
+        dict(constraints={"year": 2013, "month": 4}, has_filter=True, normalized_top_k=12, relaxation_level=3),
+        dict(constraints={"season": "雨季"}, has_filter=True, normalized_top_k=5, relaxation_level=0),   # not representable
+        dict(constraints={"start_date": "not a date"}, has_filter=True, normalized_top_k=5, relaxation_level=0),
+        dict(constraints={}, has_filter=False, normalized_top_k=1, relaxation_level=0),
+    ]
+    out = {"rounds": []}
+    timing = {}
+    for tag, cls in (("plain", Searcher), ("recall", RecallSearcher)):
+        store = CountingStore(D, os.path.join(tmp, tag + "_rc.index"), os.path.join(tmp, tag + "_rc.json"))
+        store.add_batch(rows, metas)
+        qs = np.random.default_rng(5).standard_normal((len(rounds) + 4, D)).astype(np.float32)
+        qs[0] = rows[7]
+        emb = CountingEmbedding()
+        s = cls(embedding=emb, time_parser=FakeTimeParser(), vector_store=store, keyword_store=None, query_formatter=None)
+        s.index_loaded = True
+        res = []
+        t0 = _time.perf_counter()
+        for rep in range(3):
+            for qi, kw in enumerate(rounds):
+                emb._vec = lambda text, _q=qs[qi]: _q.tolist()
+                r = s._run_single_search_round(query="q", intent={"search_text": "q"}, embedding_query="q", media_terms=[],
+                                               identity_terms=[], strict_identity_filter=False, **kw)
+                if rep == 0:
+                    res.append({"results": [[x.get("photo_path"), x.get("score"), x.get("rank"), x.get("_confidence_bucket"),
+                                             x.get("_relaxation_level"), x.get("description"), x.get("retrieval_text"),
+                                             x.get("match_summary"), x.get("metadata", {}).get("description")] for x in r],
+                                "quality": s._get_last_round_quality()})
+        timing[tag] = (_time.perf_counter() - t0) / (3 * len(rounds)) * 1e3
+        # a round with media terms takes the reference path under the mixin too
+        emb._vec = lambda text, _q=qs[-1]: _q.tolist()
+        r = s._run_single_search_round(query="q", intent={"search_text": "q"}, embedding_query="q", media_terms=["photo"],
+                                       identity_terms=[], strict_identity_filter=False, constraints={}, has_filter=False, normalized_top_k=10)
+        res.append({"results": [[x.get("photo_path"), x.get("score"), x.get("rank"), x.get("_confidence_bucket")] for x in r],
+                    "quality": s._get_last_round_quality()})
+        out[tag] = res
+        out[tag + "_stats"] = getattr(s, "psx_recall_stats", None)
+    out["ms_per_round"] = timing
+    return out
 
 
 def prefilter_case(tmp):
@@ -145,6 +219,7 @@ def main():
                         "stats": getattr(s, "psx_batch_stats", None),
                         "expansion_triggered_full": bool(s._last_search_debug.get("expansion_triggered"))}
         out["prefilter_case"] = prefilter_case(tmp)
+        out["recall_case"] = recall_case(tmp)
     print("RESULT " + json.dumps(out))
 
 

@@ -47,6 +47,16 @@ def _check(out):
     assert set(got_plain) <= set(truth) | set(got_pre)
     assert set(got_pre) == set(truth) and len(got_pre) == 10
     assert len(got_plain) <= len(got_pre)
+    # FusedRecallMixin: identical rounds -- results, ranks, buckets, summaries and round quality --
+    # with the candidates kept as arrays; only the round with media terms takes the reference path
+    rc = out["recall_case"]
+    assert len(rc["plain"]) == len(rc["recall"]) == 9
+    for i, (a, b) in enumerate(zip(rc["plain"], rc["recall"])):
+        assert a["results"] == b["results"], i
+        assert a["quality"] == b["quality"], i
+    assert any(len(r["results"]) > 0 for r in rc["plain"][2:7])            # the filtered rounds do return photos
+    assert rc["recall_stats"]["array_rounds"] == 24 and rc["recall_stats"]["reference_rounds"] == 1
+    assert rc["ms_per_round"]["recall"] < rc["ms_per_round"]["plain"]        # and the Python tail got shorter
 
 
 @pytest.mark.skipif(not os.path.isdir(os.path.join(REFERENCE, "core")), reason="reference checkout not present")
