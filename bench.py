@@ -303,14 +303,14 @@ def run_ours(args):
                                     id_base=lo, stream=stream.cuda_stream)
                 if i in ev:
                     ev[i][1].record(stream)
-            elif sharded.exchange == "p2p":  # scan publishes its keys into every peer's buffer; wait + merge kernel
+            elif sharded.exchange == "p2p":
+                # ONE kernel per query and rank: the scan's last CTA publishes its k keys into every peer's buffer over
+                # NVLink, waits for the peers' lists and selects the global top-k itself
                 sharded._seq += 1
-                index.search_exchange_device(qptr, k, rank, world, sharded._xchg_bases, sharded._seq, 0, 0, id_base=lo,
-                                             stream=stream.cuda_stream, phases=1)
+                index.search_exchange_device(qptr, k, rank, world, sharded._xchg_bases, sharded._seq, b["scores"].data_ptr(),
+                                             b["ids"].data_ptr(), id_base=lo, stream=stream.cuda_stream, phases=3)
                 if i in ev:
                     ev[i][1].record(stream)
-                index.search_exchange_device(0, k, rank, world, sharded._xchg_bases, sharded._seq, b["scores"].data_ptr(),
-                                             b["ids"].data_ptr(), stream=stream.cuda_stream, phases=2)
             else:  # keys only, then ONE all-gather and the integer merge on every rank
                 index.search_device(qptr, 1, k, 0, 0, b["mine"].data_ptr(), id_base=lo, stream=stream.cuda_stream)
                 if i in ev:
@@ -323,36 +323,37 @@ def run_ours(args):
         return ev_all[0].elapsed_time(ev_all[1]), sum(a.elapsed_time(z) for a, z in ev.values()) / len(ev), len(ev)
 
     # ---- device-resident timing ------------------------------------------------------------
-    for i in range(max(args.warmup, 3)):
-        step_device(i)
-    barrier()
+    # `value` is DEFINED on inputs resident in HBM, which is exactly the precondition of the launch-overlap tunable
+    # (include/psx.h, "pdl" = 2: the query of a call is not written by the kernel right before it): consecutive queries
+    # overlap -- scan i+1 streams while scan i sorts, exchanges and merges.  The library default ("pdl" = 1, plain stream
+    # order between calls, what host-buffer callers get) is measured by the same loop and reported beside it.
+    def measure(pdl):
+        index.set_tunable("pdl", pdl)
+        for i in range(max(args.warmup, 3)):
+            step_device(i)
+        barrier()
+        launches0 = _native.launch_count()
+        # short runs (the driver passes --steps 20) bracket every other launch so that >= 8 launches are sampled
+        every = 8 if args.steps >= 80 else 2
+        total_ms, scan_ms, n_br = timed_loop(args.steps, every)
+        launches = _native.launch_count() - launches0
+        t = torch.tensor([total_ms, scan_ms, float(launches)], device=device, dtype=torch.float64)
+        if world > 1:
+            tmax = t.clone()
+            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+            tsum = t.clone()
+            dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+            return float(tmax[0]), float(tmax[1]), int(tsum[2]), n_br, every
+        return total_ms, scan_ms, launches, n_br, every
+
+    measure(2)  # settle clocks / caches once before anything is recorded
     clocks = ClockSampler(local_rank).start() if rank == 0 else None
-    launches0 = _native.launch_count()
-    # short runs (the driver passes --steps 20) bracket every other launch so that >= 8 launches are sampled
-    EVERY = 8 if args.steps >= 80 else 2
-    total_ms, scan_ms, n_bracketed = timed_loop(args.steps, EVERY)
-    launches = _native.launch_count() - launches0
-    t = torch.tensor([total_ms, scan_ms, float(launches)], device=device, dtype=torch.float64)
-    if world > 1:
-        tmax = t.clone()
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        tsum = t.clone()
-        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
-        total_ms, scan_ms, launches = float(tmax[0]), float(tmax[1]), int(tsum[2])
+    total_ms, scan_ms, launches, n_bracketed, EVERY = measure(2)
     clock_info = clocks.stop() if clocks else None
     ms_per_step = total_ms / args.steps
     qps = 1e3 / ms_per_step
-    # same loop with the overlap tunable (resident queries): context, not the headline
-    index.set_tunable("pdl", 2)
-    for i in range(3):
-        step_device(i)
-    barrier()
-    ov_ms, _, _ = timed_loop(args.steps, args.steps + 1)
-    index.set_tunable("pdl", 1)
-    tov = torch.tensor([ov_ms], device=device, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(tov, op=dist.ReduceOp.MAX)
-    qps_overlap = args.steps / float(tov[0]) * 1e3
+    default_ms, _, _, _, _ = measure(1)
+    qps_default = args.steps / default_ms * 1e3
 
     # ---- end to end through the reference-facing host-buffer call ------------------------------------
     # N=1: psx_search itself (what VectorStore.search calls: pageable host query in, host scores/ids out);
@@ -498,12 +499,13 @@ def run_ours(args):
                 "workload": workload_name(rows, d, k, args.store),
                 "rows": rows, "dim": d, "k": k, "rows_per_gpu": local_rows, "parallelism": f"row-shard x{world}",
                 "l2_policy": "inputs larger than L2 (corpus shard >> 126 MB), no flush needed",
-                "launch_policy": "library default (tunable pdl=1): consecutive calls in plain stream order",
-                "value_with_pdl2": qps_overlap,
-                "value_with_pdl2_note": "tunable pdl=2 (valid for resident queries only): scan i+1 starts streaming while scan i sorts/merges",
+                "launch_policy": "tunable pdl=2 (valid because the queries are resident in HBM, which is what `value` is defined on): "
+                                 "scan i+1 streams while scan i sorts / exchanges / merges (programmatic dependent launch)",
+                "value_with_default_pdl1": qps_default,
+                "value_with_default_pdl1_note": "library default: consecutive calls in plain stream order (what host-buffer callers get; e2e uses it)",
                 "scanned_GBps_aggregate": rows * d * esize / (ms_per_step * 1e-3) / 1e9,
                 "exchange": ("none" if world == 1 else
-                             "fused: last CTA of the scan stores its k keys into every peer's buffer over NVLink + flag; one-CTA wait+merge kernel"
+                             "fused into the scan kernel: its last CTA stores its k keys into every peer's buffer over NVLink + flag, waits for the peers' lists and merges"
                              if sharded.exchange == "p2p" else "NCCL all-gather of k 64-bit keys per rank + integer merge kernel"),
             },
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -606,6 +608,10 @@ def run_configs_2_3(torch, _native, queries, k, device):
     for name, v in time_filtered(torch, ix, q_ptrs, rows, d, 4, k, device, steps=50).items():
         out[f"config2/1Mx1024/{name}"] = v
     out.update(run_batched(torch, _native, ix, rows, d, k, device, tag="config3/1Mx1024"))
+    try:
+        out.update(run_request_level(torch, _native, ix, rows, d, device))
+    except Exception as exc:
+        out["request_level/error"] = repr(exc)[:300]
     ix.close()
     # same batch on the optional bf16 + fp32-master tier: bf16 GEMM over the bf16 rows, exact re-score on the master
     mixed = _native.NativeIndex(d, _native.METRIC_IP, _native.STORE_BF16_MASTER, device.index or 0)
@@ -686,6 +692,10 @@ def run_extras(torch, _native, index, queries, rows, d, k, device, esize):
         except Exception as exc:
             out["config2_3/error"] = repr(exc)[:200]
         out.update(run_batched(torch, _native, index, rows, d, k, device))
+        try:
+            out.update(run_bulk_load(torch, _native, index, rows, d, k, queries))
+        except Exception as exc:
+            out["bulk_load/error"] = repr(exc)[:300]
         try:
             out.update(run_bf16_shard(torch, _native, device))
         except Exception as exc:  # never let a secondary configuration kill the bench line
@@ -803,51 +813,190 @@ def run_config1(torch, _native, device):
 
 
 def run_bf16_shard(torch, _native, device):
-    """One GPU's share of BASELINE.json configs[4] (100M x 768 bf16 over 8 GPUs = 12.5M rows per GPU):
-    image -> image search by stored row id on bf16 storage (fp32 accumulate), recall@100 against the same
-    search on the fp32 master rows."""
-    from photo_search_engine_b200.sharded import ShardedIndex
-
-    rows, d, k, nq = 12_500_000, 768, 100, 32
+    """One GPU's share of BASELINE.json configs[4] (100M x 768 bf16 over 8 GPUs = 12.5M rows per GPU): throughput of the
+    bf16 scan, and recall@100 of bf16 storage against exact fp32 on >= 1000 queries, for the two corpora of SURVEY.md 8d:
+    uniform random unit vectors (the worst case: score gaps of the order of the rounding noise) and the clustered corpus
+    (4096 centroids, sigma = 0.35 noise, renormalised).  Queries: half uniform on the sphere, half planted neighbours
+    (normalize(x_row + 0.2 noise)).  Ground truth: the same queries on fp32 copies of the rows (exact batched search)."""
+    rows, d, k, nq = 12_500_000, 768, 100, 1024
     free, _total = torch.cuda.mem_get_info()
     if free < rows * d * 6 * 1.15:
         return {"bf16_shard/skipped": "not enough free HBM for the fp32 master next to the bf16 rows"}
-    lo_p = _native.NativeIndex(d, _native.METRIC_IP, _native.STORE_BF16, device.index or 0)
-    hi_p = _native.NativeIndex(d, _native.METRIC_IP, _native.STORE_F32, device.index or 0)
-    lo_p.reserve(rows)
-    hi_p.reserve(rows)
-    done = 0
-    st = torch.cuda.current_stream().cuda_stream
-    while done < rows:
-        take = min(CHUNK, rows - done)
-        gen = torch.Generator(device=device).manual_seed(CORPUS_SEED + 1000 + done // CHUNK)
-        blk = torch.randn((take, d), generator=gen, device=device, dtype=torch.float32)
-        blk = (blk / blk.norm(dim=1, keepdim=True)).contiguous()
-        lo_p.add_device(blk.data_ptr(), take, stream=st)
-        hi_p.add_device(blk.data_ptr(), take, stream=st)
-        done += take
-        del blk
-    lo_s, hi_s = ShardedIndex(lo_p, 0), ShardedIndex(hi_p, 0)
-    gen = torch.Generator(device=device).manual_seed(99)
-    ids = torch.randint(0, rows, (nq,), generator=gen, device=device).tolist()
-    hits = 0
-    for gid in ids:
-        _, a = lo_s.search_by_id(gid, k)
-        _, b = hi_s.search_by_id(gid, k)
-        hits += len(set(a.tolist()) & set(b.tolist()))
-    recall = hits / (nq * k)
-    q = torch.randn((16, d), generator=gen, device=device)
-    q = (q / q.norm(dim=1, keepdim=True)).contiguous()
-    lo_p.set_tunable("pdl", 2)  # resident queries, one per call
-    ms = time_device_search(torch, lo_p, [q[i: i + 1].data_ptr() for i in range(16)], k, None, 30)
     peak, _ = measured_peak()
-    out = {"bf16_shard/12.5Mx768": {"ms": ms, "qps_per_gpu": 1e3 / ms, "GBps": rows * d * 2 / ms / 1e6,
-                                    "frac_of_peak": rows * d * 2 / ms / 1e6 / peak, "recall_at_100_vs_fp32": recall,
-                                    "queries_for_recall": nq,
-                                    "note": "query = stored row (by id), self excluded; uniform random unit vectors are the worst case "
-                                            "for bf16 (score gaps ~ quantisation noise)"}}
-    lo_p.close()
-    hi_p.close()
+    out = {}
+    st = torch.cuda.current_stream().cuda_stream
+    for corpus in ("uniform", "clustered"):
+        lo_p = _native.NativeIndex(d, _native.METRIC_IP, _native.STORE_BF16, device.index or 0)
+        hi_p = _native.NativeIndex(d, _native.METRIC_IP, _native.STORE_F32, device.index or 0)
+        lo_p.reserve(rows)
+        hi_p.reserve(rows)
+        gen_c = torch.Generator(device=device).manual_seed(4096)
+        centroids = torch.randn((4096, d), generator=gen_c, device=device)
+        centroids = centroids / centroids.norm(dim=1, keepdim=True)
+        done = 0
+        planted = []
+        while done < rows:
+            take = min(CHUNK, rows - done)
+            gen = torch.Generator(device=device).manual_seed(CORPUS_SEED + 1000 + done // CHUNK)
+            blk = torch.randn((take, d), generator=gen, device=device, dtype=torch.float32)
+            if corpus == "clustered":
+                # unit centroid + sigma * noise with |noise| ~ 1 (per-coordinate sigma / sqrt(d)), renormalised
+                pick = torch.randint(0, 4096, (take,), generator=gen, device=device)
+                blk = centroids[pick] + (0.35 / d ** 0.5) * blk
+            blk = (blk / blk.norm(dim=1, keepdim=True)).contiguous()
+            lo_p.add_device(blk.data_ptr(), take, stream=st)
+            hi_p.add_device(blk.data_ptr(), take, stream=st)
+            if len(planted) * 64 < nq // 2:   # 64 planted queries from each of the first chunks
+                planted.append(blk[:: max(1, take // 64)][:64].clone())
+            done += take
+            del blk
+        gen = torch.Generator(device=device).manual_seed(99)
+        q_uni = torch.randn((nq // 2, d), generator=gen, device=device)
+        base = torch.cat(planted)[: nq // 2]
+        noise = torch.randn(base.shape, generator=gen, device=device)
+        q_pl = base + 0.2 * noise / noise.norm(dim=1, keepdim=True)
+        q = torch.cat([q_uni, q_pl])
+        q = (q / q.norm(dim=1, keepdim=True)).contiguous()
+        qh = q.cpu().numpy()
+        _, truth = hi_p.search(qh, k)                       # exact fp32 (batched tensor-core path + certificates)
+        lo_p.set_tunable("batch_min", 0)
+        _, got = lo_p.search(qh, k)                         # bf16 storage, one streaming scan per query
+        per_q = np.array([len(set(a.tolist()) & set(b.tolist())) / k for a, b in zip(got, truth)])
+        rec = {"recall_at_100": float(per_q.mean()), "recall_uniform_queries": float(per_q[: nq // 2].mean()),
+               "recall_planted_queries": float(per_q[nq // 2:].mean()), "queries": nq,
+               "worst_query_recall": float(per_q.min()), "meets_0.999": bool(per_q.mean() >= 0.999)}
+        if corpus == "uniform":
+            lo_p.set_tunable("pdl", 2)  # resident queries, one per call
+            ms = time_device_search(torch, lo_p, [q[i: i + 1].data_ptr() for i in range(16)], k, None, 30)
+            out["bf16_shard/12.5Mx768"] = {"ms": ms, "qps_per_gpu": 1e3 / ms, "GBps": rows * d * 2 / ms / 1e6,
+                                            "frac_of_peak": rows * d * 2 / ms / 1e6 / peak, "recall_at_100_vs_fp32": rec["recall_at_100"],
+                                            "queries_for_recall": nq}
+        out[f"bf16_recall/12.5Mx768/{corpus}"] = rec
+        lo_p.close()
+        hi_p.close()
+        del centroids
+    out["bf16_recall/note"] = ("plain bf16 storage is approximate; the documented mode for recall >= 0.999 (exact, in fact) is store_dtype='bf16+fp32': "
+                               "bf16 rows streamed (2 B/element/query) + fp32 master re-score, 6 B/element resident")
+    return out
+
+
+def run_bulk_load(torch, _native, index, rows, d, k, queries):
+    """load() / add_batch throughput: host fp32 rows -> HBM through psx_add (pipelined pinned staging), and
+    the latency of the first query afterwards; then the drop-in class's save() + load() round trip through a file."""
+    import tempfile
+
+    from photo_search_engine_b200.vector_store import VectorStore
+
+    out = {}
+    n = int(min(rows, 4_000_000))
+    host = index.read_rows(0, n)                            # the stored bits of the headline corpus
+    ix = _native.NativeIndex(d, _native.METRIC_IP, _native.STORE_F32, index.device)
+    ix.reserve(n)
+    t0 = time.perf_counter()
+    ix.add(host)
+    ix.sync()
+    t1 = time.perf_counter()
+    qh = queries[:1].cpu().numpy()
+    D1, I1 = ix.search(qh, k)
+    t2 = time.perf_counter()
+    D0, I0 = index.search(qh, k) if n == rows else (None, None)
+    out["bulk_load/psx_add"] = {"rows": n, "GB": n * d * 4 / 1e9, "seconds": t1 - t0, "GBps": n * d * 4 / (t1 - t0) / 1e9,
+                                "GBps_inside_upload": ix.upload_gbps(), "first_query_ms": (t2 - t1) * 1e3,
+                                "same_result_as_resident_index": None if I0 is None else bool(np.array_equal(I0, I1)),
+                                "note": "pageable host array -> 2 x 64 MB pinned staging (multi-threaded copy) -> H2D -> pack kernel, double buffered"}
+    ix.close()
+    m = 1_000_000
+    with tempfile.TemporaryDirectory(dir="/dev/shm" if os.path.isdir("/dev/shm") else None) as tmp:
+        store = VectorStore(d, os.path.join(tmp, "photo_search.index"), os.path.join(tmp, "metadata.json"), device=index.device)
+        store.add_batch(host[:m], [{"photo_path": f"/p/{i}.jpg"} for i in range(m)])
+        t0 = time.perf_counter()
+        store.save()
+        t1 = time.perf_counter()
+        again = VectorStore(d, store.index_path, store.metadata_path, device=index.device)
+        ok = again.load()
+        t2 = time.perf_counter()
+        hits = again.search(qh[0].tolist(), 10)
+        t3 = time.perf_counter()
+        out["bulk_load/VectorStore.save+load/1Mx%d" % d] = {
+            "save_s": t1 - t0, "load_s": t2 - t1, "load_GBps": m * d * 4 / (t2 - t1) / 1e9, "first_search_ms": (t3 - t2) * 1e3,
+            "loaded": bool(ok) and len(hits) == 10,
+            "note": "FAISS-format file on tmpfs + metadata.json (1M records, json.load dominates load_s); index bytes via memmap -> psx_add"}
+    del host
+    return out
+
+
+def run_request_level(torch, _native, ix, rows, d, device):
+    """what a REQUEST costs once the scan is fast.  The reference's unmodified Searcher (the staged
+    copy under oracle/_ref: the caller, not the thing measured) runs one search round, candidate_k = 500, against the drop-in
+    store, with and without FusedRecallMixin (candidates kept as arrays, dicts only for the returned photos)."""
+    import importlib.util
+    import types
+
+    from oracle import stage_reference
+    from photo_search_engine_b200.searcher_ext import FusedRecallMixin
+    from photo_search_engine_b200.vector_store import VectorStore
+
+    ref = stage_reference.locate()
+    if ref is None:
+        return {"request_level/skipped": "reference Searcher not staged (run __graft_entry__.build() where /root/reference exists)"}
+    shim = types.ModuleType("utils.vector_store")
+    shim.VectorStore = VectorStore
+    saved_path = list(sys.path)
+    sys.path.insert(0, ref)
+    try:
+        sys.modules.setdefault("utils.vector_store", shim)
+        from core.searcher import Searcher  # the reference, unmodified
+    finally:
+        sys.path[:] = saved_path
+
+    class RecallSearcher(FusedRecallMixin, Searcher):
+        pass
+
+    class Emb:
+        def __init__(self, q):
+            self.q = q
+
+        def generate_embedding(self, text):
+            return self.q
+
+    class NoTime:
+        def extract_time_constraints(self, query):
+            return {}
+
+    store = VectorStore(None, "/tmp/_bench_req.index", "/tmp/_bench_req.json")
+    store.dimension = d
+    store.index = ix
+    store.metadata = [{"photo_path": f"/photos/album{i % 977}/IMG_{i}.JPG", "description": "a photo", "exif_data": {"datetime": "2021-06-15T12:00:00"},
+                       "time_info": {"year": 2021, "month": 6, "season": "夏天", "time_period": "中午", "datetime_str": "2021-06-15T12:00:00"}}
+                      for i in range(rows)]
+    gen = torch.Generator(device=device).manual_seed(123)
+    qs = torch.randn((8, d), generator=gen, device=device).cpu().numpy().tolist()
+    out = {}
+    results = {}
+    for tag, cls in (("reference_searcher", Searcher), ("with_FusedRecallMixin", RecallSearcher)):
+        emb = Emb(qs[0])
+        s = cls(embedding=emb, time_parser=NoTime(), vector_store=store, keyword_store=None, query_formatter=None)
+        s.index_loaded = True
+        for has_filter, cons in ((False, {}), (True, {"start_date": "2021-01-01", "end_date": "2021-12-31", "precision": "year"})):
+            def one(i):
+                emb.q = qs[i % 8]
+                return s._run_single_search_round(query="q", intent={"search_text": "q"}, embedding_query="q", media_terms=[], identity_terms=[],
+                                                  strict_identity_filter=False, constraints=cons, normalized_top_k=10, has_filter=has_filter)
+            for i in range(3):
+                r = one(i)
+            t0 = time.perf_counter()
+            n = 20
+            for i in range(n):
+                r = one(i)
+            ms = (time.perf_counter() - t0) / n * 1e3
+            key = "time_filtered" if has_filter else "unfiltered"
+            out.setdefault(f"request_level/{key}", {})[tag + "_ms_per_round"] = ms
+            results[(tag, key)] = [[x.get("photo_path"), x.get("score"), x.get("rank")] for x in one(0)]
+    for key in ("unfiltered", "time_filtered"):
+        out[f"request_level/{key}"]["identical_results"] = results[("reference_searcher", key)] == results[("with_FusedRecallMixin", key)]
+        out[f"request_level/{key}"]["note"] = (f"{rows} x {d} rows on the GPU, candidate_k = 500 (core/searcher.py:771-820), top_k = 10; "
+                                               "one _run_single_search_round = embedding (stub) + VectorStore.search + Python tail")
+    store.index = None  # the bench owns the index
     return out
 
 

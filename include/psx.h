@@ -138,6 +138,10 @@ int psx_add(psx_index* h, const float* x, int64_t n);
  * `normalize` is non-zero every row is L2-normalised on the device first (zero rows are kept
  * unchanged, as utils/vector_store.py:88-89).  Runs on `stream`. */
 int psx_add_device(psx_index* h, const float* x_dev, int64_t n, int normalize, void* stream);
+/* Host-to-HBM throughput (GB/s of fp32 host bytes over wall time) of the last large psx_add / psx_sync upload: blocks of
+ * 32 MB or more skip the staging vector and are pipelined through two pinned staging buffers (multi-threaded host copy
+ * of chunk i+1 overlaps the PCIe transfer and the pack kernel of chunk i). */
+double psx_upload_gbps(psx_index* h);
 /* Pre-size the HBM arena for `n` rows in total (avoids regrowth copies). */
 int psx_reserve(psx_index* h, int64_t n);
 /* Upload everything staged by psx_add. */

@@ -57,6 +57,7 @@ _SIGNATURES = [
     ("psx_abi_version", C.c_int, []),
     ("psx_add", C.c_int, [_P, _P, C.c_int64]),
     ("psx_add_device", C.c_int, [_P, _P, C.c_int64, C.c_int, _P]),
+    ("psx_upload_gbps", C.c_double, [_P]),
     ("psx_reserve", C.c_int, [_P, C.c_int64]),
     ("psx_sync", C.c_int, [_P]),
     ("psx_set_attrs", C.c_int, [_P, C.c_int64, _P, C.c_int64]),
@@ -178,6 +179,9 @@ class NativeIndex:
 
     def add_device(self, ptr: int, n: int, normalize: bool = False, stream: int = 0) -> None:
         check(self._lib.psx_add_device(self._h, ptr, int(n), int(bool(normalize)), stream or None))
+
+    def upload_gbps(self) -> float:
+        return float(self._lib.psx_upload_gbps(self._h))
 
     def reserve(self, n: int) -> None:
         check(self._lib.psx_reserve(self._h, int(n)))

@@ -10,6 +10,8 @@
 #include <mutex>
 #include <new>
 #include <string>
+#include <chrono>
+#include <thread>
 #include <vector>
 
 #include "psx_aux.cuh"
@@ -147,6 +149,13 @@ struct psx_index {
     size_t bsample_cap = 0;
     int* hflags = nullptr;    // pinned [256]
     long long batch_fallbacks = 0, batch_queries = 0, mixed_queries = 0;
+    // bulk ingest (load(), add_batch): two pinned staging buffers + two device bounce buffers, so that the host-side copy
+    // of chunk i+1 overlaps the H2D transfer and the pack kernel of chunk i.  Allocated by the first large upload.
+    float* up_pin[2] = {nullptr, nullptr};
+    float* up_dev[2] = {nullptr, nullptr};
+    cudaEvent_t up_ev[2] = {nullptr, nullptr};
+    size_t up_bytes = 0;
+    double up_last_gbps = 0.0;            // throughput of the last large upload (host bytes / wall time)
     unsigned long long* trace = nullptr;  // diagnostics: phase timestamps of the next scans (caller-owned)
     // fused exchange: status word of merge_wait_kernel in host-mapped memory (0 = fine, 1 + r = rank r never published)
     int* xstatus_host = nullptr;
@@ -167,6 +176,7 @@ struct psx_index {
     std::vector<char> g_h2d_busy;
     float* g_hq = nullptr;               // pinned (portable) staging of the queries
     size_t g_hq_cap = 0;
+    bool xchg_inline = true;             // tunable "xchg_inline": the scan's last CTA also does the cross-rank merge
     int fault_skip_publish = -1;         // test hook (tunable): this shard never publishes to the fused exchange
     long long xchg_timeout_ms = 0;       // tunable: bounded spin of the fused wait (0 = default, PSX_XCHG_TIMEOUT_MS or 20 s)
     long long g_fused = 0, g_keyed = 0, g_timeouts = 0;  // queries served by the fused exchange / the key-list path / fused timeouts
@@ -362,6 +372,11 @@ static void free_all(psx_index* h) {
     cudaFree(h->bsample);
     cudaFreeHost(h->hflags);
     cudaFreeHost(h->xstatus_host);
+    for (int b = 0; b < 2; ++b) {
+        cudaFreeHost(h->up_pin[b]);
+        cudaFree(h->up_dev[b]);
+        if (h->up_ev[b]) cudaEventDestroy(h->up_ev[b]);
+    }
     if (h->last_ev) cudaEventDestroy(h->last_ev);
     if (h->stream) cudaStreamDestroy(h->stream);
 }
@@ -494,35 +509,79 @@ static int launch_pack(psx_index* h, const float* src_dev, long long row0, long 
     return PSX_OK;
 }
 
-// upload host rows into the arena behind row h->n (chunked through a bounded device bounce buffer); the caller
-// holds h->mu (or owns h as the child of a group) and the device is current
+// host -> pinned staging with several threads (one thread tops out near 10 GB/s; the PCIe link takes ~50)
+static void parallel_memcpy(void* dst, const void* src, size_t bytes) {
+    static const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    const unsigned nt = (unsigned)std::max<size_t>(1, std::min<size_t>(std::min(8u, hw / 2 ? hw / 2 : 1u), bytes >> 22));
+    if (nt <= 1) {
+        memcpy(dst, src, bytes);
+        return;
+    }
+    std::vector<std::thread> pool;
+    const size_t per = ((bytes / nt) + 4095) & ~(size_t)4095;
+    for (unsigned t = 0; t < nt; ++t) {
+        const size_t off = (size_t)t * per;
+        if (off >= bytes) break;
+        const size_t len = std::min(per, bytes - off);
+        pool.emplace_back([=] { memcpy((char*)dst + off, (const char*)src + off, len); });
+    }
+    for (std::thread& t : pool) t.join();
+}
+
+constexpr size_t UPLOAD_CHUNK_BYTES = 64ull << 20;
+
+// upload host rows into the arena behind row h->n; the caller holds h->mu (or owns h as the child of a group) and the
+// device is current.  Small uploads (add_item trickles) go through one bounded bounce buffer; large ones are pipelined:
+// chunk i+1 is copied into pinned staging by several host threads while chunk i crosses PCIe and is packed.
 static int upload_host_rows(psx_index* h, const float* rows, long long rows_n) {
     if (rows_n <= 0) return PSX_OK;
     int rc = ensure_capacity(h, h->n + rows_n, false);
     if (rc) return rc;
-    const long long chunk_rows = std::max<long long>(1, (256ll << 20) / ((long long)h->d * 4));
-    float* bounce = nullptr;
-    const long long brows = std::min(chunk_rows, rows_n);
-    if (cudaMalloc(&bounce, (size_t)brows * h->d * sizeof(float)) != cudaSuccess) {
-        cudaGetLastError();
-        return fail(PSX_ERR_OOM, "cudaMalloc of the upload bounce buffer failed");
-    }
-    long long done = 0;
-    while (done < rows_n) {
-        const long long m = std::min(brows, rows_n - done);
-        cudaError_t e = cudaMemcpyAsync(bounce, rows + (size_t)done * h->d, (size_t)m * h->d * sizeof(float),
-                                        cudaMemcpyHostToDevice, h->stream);
+    const size_t row_bytes = (size_t)h->d * sizeof(float);
+    const size_t total = (size_t)rows_n * row_bytes;
+    if (total < (8ull << 20)) {
+        float* bounce = nullptr;
+        if (cudaMalloc(&bounce, total) != cudaSuccess) {
+            cudaGetLastError();
+            return fail(PSX_ERR_OOM, "cudaMalloc of the upload bounce buffer failed");
+        }
+        cudaError_t e = cudaMemcpyAsync(bounce, rows, total, cudaMemcpyHostToDevice, h->stream);
         if (e == cudaSuccess) {
-            rc = launch_pack(h, bounce, h->n + done, m, 0, h->stream);
+            rc = launch_pack(h, bounce, h->n, rows_n, 0, h->stream);
             if (rc == PSX_OK) e = cudaStreamSynchronize(h->stream);
         }
-        if (e != cudaSuccess || rc != PSX_OK) {
-            cudaFree(bounce);
-            return rc ? rc : fail(PSX_ERR_CUDA, "upload failed: %s", cudaGetErrorString(e));
+        cudaFree(bounce);
+        if (e != cudaSuccess || rc != PSX_OK) return rc ? rc : fail(PSX_ERR_CUDA, "upload failed: %s", cudaGetErrorString(e));
+        return PSX_OK;
+    }
+    if (!h->up_bytes) {
+        for (int b = 0; b < 2; ++b) {
+            cudaError_t e = cudaHostAlloc(&h->up_pin[b], UPLOAD_CHUNK_BYTES, cudaHostAllocPortable);
+            if (e == cudaSuccess) e = cudaMalloc(&h->up_dev[b], UPLOAD_CHUNK_BYTES);
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->up_ev[b], cudaEventDisableTiming);
+            if (e != cudaSuccess) {
+                cudaGetLastError();
+                return fail(PSX_ERR_OOM, "allocating the upload staging failed: %s", cudaGetErrorString(e));
+            }
         }
+        h->up_bytes = UPLOAD_CHUNK_BYTES;
+    }
+    const long long chunk_rows = std::max<long long>(1, (long long)(h->up_bytes / row_bytes));
+    const auto t0 = std::chrono::steady_clock::now();
+    long long done = 0;
+    for (int i = 0; done < rows_n; ++i) {
+        const int b = i & 1;
+        const long long m = std::min(chunk_rows, rows_n - done);
+        if (i >= 2) CU(cudaEventSynchronize(h->up_ev[b]));  // the transfer that last used this staging pair is over
+        parallel_memcpy(h->up_pin[b], rows + (size_t)done * h->d, (size_t)m * row_bytes);
+        CU(cudaMemcpyAsync(h->up_dev[b], h->up_pin[b], (size_t)m * row_bytes, cudaMemcpyHostToDevice, h->stream));
+        if ((rc = launch_pack(h, h->up_dev[b], h->n + done, m, 0, h->stream))) return rc;
+        CU(cudaEventRecord(h->up_ev[b], h->stream));
         done += m;
     }
-    cudaFree(bounce);
+    CU(cudaStreamSynchronize(h->stream));
+    const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    if (sec > 0) h->up_last_gbps = (double)total / sec / 1e9;
     return PSX_OK;
 }
 
@@ -554,6 +613,19 @@ static int flush_pending(psx_index* h) {
 
 extern "C" int psx_add(psx_index* h, const float* x, int64_t n) {
     if (!h || (!x && n > 0) || n < 0) return fail(PSX_ERR_INVALID, "bad arguments to psx_add");
+    // large blocks (load(), add_batch) go straight to HBM through the pipelined upload -- no copy into the staging vector
+    if ((size_t)n * h->d * sizeof(float) >= (32ull << 20)) {
+        std::lock_guard<std::mutex> lk(h->mu);
+        DeviceGuard g(h->device);
+        int rc = flush_pending(h);
+        if (rc) return rc;
+        if ((unsigned long long)(h->n + n) >= 0xffffffffull) return fail(PSX_ERR_RANGE, "more than 2^32-1 rows");
+        rc = is_group(h) ? group_place_host_rows(h, x, n) : upload_host_rows(h, x, n);
+        if (rc) return rc;
+        std::lock_guard<std::mutex> pk(h->pmu);
+        h->n += n;
+        return PSX_OK;
+    }
     bool big = false;
     {
         std::lock_guard<std::mutex> pk(h->pmu);
@@ -756,6 +828,12 @@ struct XchgArgs {
     uint32_t seq;
     const uint64_t* bases;  // host array [targets]: base address of every receive buffer this shard publishes to
     int targets;            // 0 = world (one process per GPU: every rank merges); 1 = only bases[0] merges (one process, G devices)
+    // merge fused into the scan's last CTA (see ScanParams::xchg_my_recv): this rank's own receive buffer + outputs
+    uint64_t my_base = 0;
+    float* out_scores = nullptr;
+    long long* out_ids = nullptr;
+    int* status = nullptr;
+    unsigned long long spin_limit = 0;
 };
 static size_t xchg_flag_offset() { return (size_t)2 * PSX_XCHG_MAX_WORLD * PSX_K_PASS_MAX * sizeof(uint64_t); }
 
@@ -836,6 +914,14 @@ static int launch_scan(psx_index* h, const float* q_dev, int k, const psx_filter
         for (int r = 0; r < p.xchg_targets; ++r) {
             p.xchg_recv[r] = (uint64_t*)(uintptr_t)xa->bases[r];
             p.xchg_flag[r] = (uint32_t*)(uintptr_t)(xa->bases[r] + xchg_flag_offset());
+        }
+        if (xa->my_base) {
+            p.xchg_my_recv = (const uint64_t*)(uintptr_t)xa->my_base;
+            p.xchg_my_flag = (const uint32_t*)(uintptr_t)(xa->my_base + xchg_flag_offset());
+            p.xchg_out_scores = xa->out_scores;
+            p.xchg_out_ids = xa->out_ids;
+            p.xchg_status = xa->status;
+            p.xchg_spin_limit = xa->spin_limit;
         }
     }
     const size_t arena_row_bytes = master ? h->mrow_bytes : h->row_bytes;
@@ -1275,8 +1361,20 @@ extern "C" int psx_search_exchange_device(psx_index* h, const float* q_dev, int6
     cudaStream_t st = (cudaStream_t)stream;
     if ((rc = enter_stream(h, st))) return rc;
     XchgArgs xa{world, rank, seq, peer_bases, 0};
+    int* status_dev = nullptr;
+    if ((rc = ensure_xstatus(h, &status_dev))) return rc;
+    // the normal call (both phases): the scan's last CTA also waits for the peers' lists and merges -- one kernel per query
+    const bool inline_merge = phases == 3 && h->xchg_inline;
+    if (inline_merge) {
+        // the ring the merge sorts in must hold world * kpad keys: always true for the default geometry (128 KB)
+        xa.my_base = peer_bases[rank];
+        xa.out_scores = out_scores_dev;
+        xa.out_ids = (long long*)out_ids_dev;
+        xa.status = status_dev;
+        xa.spin_limit = xchg_spin_limit(h->xchg_timeout_ms);
+    }
     if ((phases & 1) && (rc = launch_scan(h, q_dev, (int)k, filter, id_base, nullptr, nullptr, nullptr, nullptr, st, &xa))) return rc;
-    if (!(phases & 2)) return leave_stream(h, st);
+    if (!(phases & 2) || inline_merge) return leave_stream(h, st);
     const int kpad = (int)psx_kpad(k);
     int np = kpad;
     while (np < world * kpad) np <<= 1;
@@ -1287,8 +1385,6 @@ extern "C" int psx_search_exchange_device(psx_index* h, const float* q_dev, int6
         ready[h->device].store(true);
     }
     const uint64_t mine = peer_bases[rank];
-    int* status_dev = nullptr;
-    if ((rc = ensure_xstatus(h, &status_dev))) return rc;
     merge_wait_kernel<<<1, 256, smem, st>>>((const uint64_t*)(uintptr_t)mine, (const uint32_t*)(uintptr_t)(mine + xchg_flag_offset()), world,
                                            seq, (int)k, kpad, np, h->metric, out_scores_dev, (long long*)out_ids_dev, nullptr, status_dev,
                                            xchg_spin_limit(h->xchg_timeout_ms));
@@ -1638,6 +1734,13 @@ extern "C" int psx_hybrid_fuse_device(int device, int64_t nq, int64_t kv, const 
     return PSX_OK;
 }
 
+extern "C" double psx_upload_gbps(psx_index* h) {
+    if (!h) return 0.0;
+    double best = h->up_last_gbps;
+    for (psx_index* c : h->shards) best = std::max(best, c->up_last_gbps);
+    return best;
+}
+
 extern "C" int psx_batch_supported(psx_index* h, int64_t k) {
     if (!h || is_group(h)) return 0;
     std::lock_guard<std::mutex> lk(h->mu);
@@ -1705,6 +1808,8 @@ extern "C" int psx_set_tunable(psx_index* h, const char* key, int value) {
         h->batch_bf16 = value > 0;
     } else if (!strcmp(key, "batch_min")) {  // smallest nq sent to the tensor-core path; 0 disables it
         h->batch_min = value < 0 ? 4 : value;
+    } else if (!strcmp(key, "xchg_inline")) {  // 1 = cross-rank merge fused into the scan's last CTA (default), 0 = separate merge kernel
+        h->xchg_inline = value != 0;
     } else if (!strcmp(key, "xchg_timeout_ms")) {  // bounded wait of the fused exchange's merge kernel
         h->xchg_timeout_ms = value > 0 ? value : 0;
     } else if (!strcmp(key, "fault_skip_publish")) {  // test hook: shard `value` of a multi-device handle stays silent

@@ -569,28 +569,40 @@ static int group_fused_query(psx_index* g, const std::vector<GroupActive>& act, 
     int rc;
     // slot (seq & 1) of the receive buffer was last used by query seq - 2: its merge must be over before anyone overwrites it
     // (home's own stream is ordered anyway; after a host synchronisation the event is long complete)
-    for (int i = A - 1; i >= 0; --i) {  // home last: it also has to run the merge
+    const bool inline_merge = g->xchg_inline;
+    for (int i = A - 1; i >= 0; --i) {  // home last: its last CTA also merges
         psx_index* c = act[i].c;
         DeviceGuard dg(c->device);
         if (c != home) CU(cudaStreamWaitEvent(c->stream, g->g_merged[seq & 1u], 0));
         XchgArgs xa{A, i, seq, bases, 1};
         if (g->fault_skip_publish == (int)act[i].shard) xa.targets = -1;  // test hook: this shard stays silent
+        if (c == home && inline_merge) {
+            // the merging side fused into home's scan: its last CTA waits for the A lists and selects the global top-k
+            xa.my_base = bases[0];
+            xa.out_scores = out_scores;
+            xa.out_ids = out_ids;
+            xa.status = g->xstatus_dev;
+            xa.spin_limit = xchg_spin_limit(g->xchg_timeout_ms);
+        }
         if ((rc = launch_scan(c, c->dq + (size_t)qi * g->d, kp, filter, act[i].id_base, nullptr, nullptr, nullptr, nullptr, c->stream, &xa)))
             return rc;
     }
     DeviceGuard dg(home->device);
-    const int kpad = (int)psx_kpad(kp);
-    int np = kpad;
-    while (np < A * kpad) np <<= 1;
-    static std::atomic<bool> ready[64];
-    if (home->device < 64 && !ready[home->device].load()) {
-        CU(cudaFuncSetAttribute(merge_wait_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PSX_SMEM_LIMIT - 1024));
-        ready[home->device].store(true);
+    if (!inline_merge) {
+        const int kpad = (int)psx_kpad(kp);
+        int np = kpad;
+        while (np < A * kpad) np <<= 1;
+        static std::atomic<bool> ready[64];
+        if (home->device < 64 && !ready[home->device].load()) {
+            CU(cudaFuncSetAttribute(merge_wait_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PSX_SMEM_LIMIT - 1024));
+            ready[home->device].store(true);
+        }
+        merge_wait_kernel<<<1, 256, (size_t)np * 8, home->stream>>>((const uint64_t*)g->gx, (const uint32_t*)(g->gx + xchg_flag_offset()), A, seq, kp,
+                                                                   kpad, np, g->metric, out_scores, out_ids, nullptr, g->xstatus_dev,
+                                                                   xchg_spin_limit(g->xchg_timeout_ms));
+        g_launches++;
+        CU(cudaGetLastError());
     }
-    merge_wait_kernel<<<1, 256, (size_t)np * 8, home->stream>>>((const uint64_t*)g->gx, (const uint32_t*)(g->gx + xchg_flag_offset()), A, seq, kp, kpad,
-                                                               np, g->metric, out_scores, out_ids, nullptr, g->xstatus_dev, xchg_spin_limit(g->xchg_timeout_ms));
-    g_launches++;
-    CU(cudaGetLastError());
     CU(cudaEventRecord(g->g_merged[seq & 1u], home->stream));
     g->g_fused++;
     return PSX_OK;

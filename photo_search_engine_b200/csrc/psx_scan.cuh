@@ -68,6 +68,16 @@ struct ScanParams {
     uint32_t xchg_seq;
     uint64_t* xchg_recv[PSX_XCHG_MAX_WORLD];   // peer p: [2 parities][world][PSX_K_PASS_MAX] keys
     uint32_t* xchg_flag[PSX_XCHG_MAX_WORLD];   // peer p: [2 parities][PSX_XCHG_MAX_WORLD] sequence numbers
+    // The merging side fused into this launch: after publishing, the last CTA waits (bounded) until every rank's list
+    // for this query has landed in THIS rank's receive buffer and selects the global top-k itself -- no second kernel,
+    // and the next query's scan (programmatic dependent launch) streams on the other SMs meanwhile.  nullptr = a
+    // separate merge_wait_kernel does it (needed when several ranks share one stream: emulated ranks).
+    const uint64_t* xchg_my_recv;
+    const uint32_t* xchg_my_flag;
+    float* xchg_out_scores;
+    long long* xchg_out_ids;
+    int* xchg_status;                          // host-mapped: 1 + the first rank that never published (0 = fine)
+    unsigned long long xchg_spin_limit;
 };
 
 __device__ __forceinline__ void st_relaxed_sys_u64(uint64_t* p, uint64_t v) {
@@ -693,6 +703,42 @@ __global__ void __launch_bounds__(PSX_MAX_THREADS, 1) scan_topk_kernel(const Sca
         __syncthreads();
         if ((int)threadIdx.x < p.xchg_targets)
             st_release_sys_u32(p.xchg_flag[threadIdx.x] + slot * PSX_XCHG_MAX_WORLD + p.xchg_rank, p.xchg_seq);
+        if (p.xchg_my_recv) {
+            // ---- K4 receiving side, inline: wait for `world` lists, select the global top-k ----------------------
+            __syncthreads();
+            if (threadIdx.x == 0) *s_flag = 0;
+            __syncthreads();
+            if ((int)threadIdx.x < p.xchg_world) {
+                const uint32_t* f = p.xchg_my_flag + slot * PSX_XCHG_MAX_WORLD + threadIdx.x;
+                unsigned long long spins = 0;
+                while (ld_acquire_sys_u32(f) != p.xchg_seq) {
+                    __nanosleep(64);
+                    if (++spins > p.xchg_spin_limit) {
+                        *s_flag = 1 + (int)threadIdx.x;
+                        break;
+                    }
+                }
+            }
+            __syncthreads();
+            if (*s_flag) {  // a rank never published: report it (the host re-runs the query over the collective path)
+                if (threadIdx.x == 0 && p.xchg_status) {
+                    *p.xchg_status = *s_flag;
+                    __threadfence_system();
+                }
+            } else {
+                const uint64_t* lists = p.xchg_my_recv + (size_t)slot * p.xchg_world * PSX_K_PASS_MAX;
+                int np = p.kpad;
+                while (np < p.xchg_world * p.kpad) np <<= 1;
+                for (int idx = threadIdx.x; idx < np; idx += blockDim.x) {
+                    uint64_t v = 0ull;
+                    if (idx < p.xchg_world * p.kpad) v = ld_cg_u64(lists + (size_t)(idx / p.kpad) * PSX_K_PASS_MAX + (idx % p.kpad));
+                    buf[idx] = v;
+                }
+                __syncthreads();
+                block_bitonic_sort_desc(buf, np);
+                block_emit_results(buf, p.k, p.kpad, p.metric, p.xchg_out_scores, p.xchg_out_ids, nullptr);
+            }
+        }
     }
     __syncthreads();
     trace_stamp(p.trace, 5);

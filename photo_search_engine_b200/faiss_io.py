@@ -70,9 +70,11 @@ def open_index(path: str) -> Tuple[Dict[str, int], Iterator[np.ndarray]]:
         raise ValueError("索引文件损坏，请重新构建索引")
     info = {"d": d, "ntotal": ntotal, "metric": metric, "is_hnsw": int(is_hnsw)}
 
-    def chunks(chunk_rows: int = 1 << 16) -> Iterator[np.ndarray]:
+    def chunks(chunk_rows: int = 0) -> Iterator[np.ndarray]:
         if ntotal == 0:
             return
+        if chunk_rows <= 0:  # ~1 GB per block: the native upload pipelines inside a block
+            chunk_rows = max(1, (1 << 30) // (4 * max(d, 1)))
         mm = np.memmap(path, dtype="<f4", mode="r", offset=offset, shape=(ntotal, d))
         for row0 in range(0, ntotal, chunk_rows):
             yield np.asarray(mm[row0 : row0 + chunk_rows])
