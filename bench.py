@@ -1143,7 +1143,7 @@ def run_config5(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
     rows = args.rows if args.rows != ROWS else 100_000_000
-    d, k, nq = 768, 100, 32
+    d, k, nq = 768, 100, 256
     bounds = shard_bounds(rows, world)
     lo, hi = bounds[rank], bounds[rank + 1]
     tier = _native.STORE_BF16_MASTER if args.tier == "mixed" else _native.STORE_BF16

@@ -233,6 +233,17 @@ int psx_hybrid_fuse_device(int device, int64_t nq, int64_t kv, const float* vec_
                            int allow_keyword_only, int keyword_filtered, int64_t* out_ids_dev, double* out_fused_dev,
                            double* out_vscore_dev, double* out_kscore_dev, int* out_count_dev, void* stream);
 
+/* On-device form of the numeric part of Searcher._finalize_results (core/searcher.py:1497-1526): per query, over its
+ * fused scores in candidate order (scores_dev [nq][m] descending, counts_dev [nq] valid entries -- the out_fused /
+ * out_count of psx_hybrid_fuse_device), the dynamic threshold of Searcher._calculate_dynamic_threshold (:627-674;
+ * np.percentile's linear interpolation, np.median and round(x, 6) reproduced bit for bit), the strict / broad
+ * thresholds from the round's floors (Searcher._get_round_score_floors, :822-826, computed by the caller) and the
+ * confidence bucket of every hit by score (3 reliable, 2 generalised, 1 rest; :828-840 without the term matching, which
+ * stays on the host).  out_counts_dev [nq][2] = hits in bucket 3 and in bucket 2. */
+int psx_finalize_device(int device, int64_t nq, int64_t m, const double* scores_dev, const int* counts_dev, int top_k,
+                        double strict_floor, double broad_floor, double threshold_floor, double* out_strict_dev,
+                        double* out_broad_dev, int* out_bucket_dev, int* out_counts_dev, void* stream);
+
 /* Replaces index.reconstruct(i) (utils/vector_store.py:207): the stored row as fp32. */
 int psx_reconstruct(psx_index* h, int64_t id, float* out);
 /* Replaces the flat payload of faiss.write_index (utils/vector_store.py:234): rows

@@ -580,3 +580,42 @@ def hybrid_fuse(
         out.append((i, round(score, 6), round(vs, 6), round(ks, 6)))
     out.sort(key=lambda t: (-t[1], t[0]))
     return out
+
+
+def calculate_dynamic_threshold(scores: Sequence[float], top_k: int, threshold_floor: float = 0.05) -> float:
+    """``Searcher._calculate_dynamic_threshold`` (core/searcher.py:627-674) restated: ``scores`` in candidate order
+    (best first), numpy percentiles / median exactly as the reference calls them."""
+    if not scores:
+        return 0.1
+    n = len(scores)
+    if n <= top_k * 2:
+        return max(scores[-1] * 0.9, threshold_floor)
+    q25 = np.percentile(scores, 25)
+    q75 = np.percentile(scores, 75)
+    median = np.median(scores)
+    cv = (q75 - q25) / median if median > 0 else 1.0
+    if cv < 0.2:
+        threshold = max(median * 0.85, q25 * 0.9)
+    elif cv < 0.5:
+        threshold = q25
+    else:
+        threshold = max(q25 * 0.7, median * 0.7)
+    if n >= top_k:
+        threshold = max(threshold, scores[top_k - 1] * 0.8)
+    return round(max(threshold, threshold_floor), 6)
+
+
+def finalize_thresholds(scores: Sequence[float], top_k: int, strict_floor: float, broad_floor: float,
+                        threshold_floor: float = 0.05) -> Tuple[float, float, List[int]]:
+    """The numeric part of ``Searcher._finalize_results`` (core/searcher.py:1497-1526) and the score-only part of
+    ``_assign_confidence_bucket`` (:828-840): ``(strict_threshold, broad_threshold, bucket per score)``."""
+    scores = [float(s) for s in scores]
+    if scores:
+        dynamic_threshold = calculate_dynamic_threshold(scores, top_k, threshold_floor)
+        strict_threshold = max(dynamic_threshold, strict_floor)
+        broad_threshold = min(strict_threshold - 0.05, max(broad_floor, strict_threshold * 0.84))
+        broad_threshold = round(max(broad_floor, broad_threshold), 6)
+    else:
+        strict_threshold, broad_threshold = strict_floor, broad_floor
+    buckets = [3 if s >= strict_threshold else 2 if s >= broad_threshold else 1 for s in scores]
+    return float(strict_threshold), float(broad_threshold), buckets

@@ -75,6 +75,7 @@ _SIGNATURES = [
     ("psx_exchange_status", C.c_int, [_P, C.POINTER(C.c_int)]),
     ("psx_hybrid_fuse_device", C.c_int, [C.c_int, C.c_int64, C.c_int64, _P, _P, _P, C.c_int64, _P, _P, _P, C.c_double, C.c_double,
                                           C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P, _P]),
+    ("psx_finalize_device", C.c_int, [C.c_int, C.c_int64, C.c_int64, _P, _P, C.c_int, C.c_double, C.c_double, C.c_double, _P, _P, _P, _P, _P]),
     ("psx_reconstruct", C.c_int, [_P, C.c_int64, _P]),
     ("psx_read_rows", C.c_int, [_P, C.c_int64, C.c_int64, _P]),
     ("psx_storage_device", C.c_int, [_P, C.POINTER(_P), C.POINTER(C.c_int64), C.POINTER(C.c_int)]),

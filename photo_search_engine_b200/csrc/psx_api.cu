@@ -1734,6 +1734,32 @@ extern "C" int psx_hybrid_fuse_device(int device, int64_t nq, int64_t kv, const 
     return PSX_OK;
 }
 
+extern "C" int psx_finalize_device(int device, int64_t nq, int64_t m, const double* scores_dev, const int* counts_dev, int top_k,
+                                   double strict_floor, double broad_floor, double threshold_floor, double* out_strict_dev,
+                                   double* out_broad_dev, int* out_bucket_dev, int* out_counts_dev, void* stream) {
+    if (nq < 0 || m < 1 || top_k < 1 || !scores_dev || !counts_dev || !out_strict_dev || !out_broad_dev || !out_bucket_dev || !out_counts_dev)
+        return fail(PSX_ERR_INVALID, "bad arguments to psx_finalize_device");
+    if (nq == 0) return PSX_OK;
+    DeviceGuard g(device);
+    if (!g.ok) return fail(PSX_ERR_CUDA, "cudaSetDevice(%d) failed", device);
+    FinalizeParams p;
+    p.scores = scores_dev;
+    p.counts = counts_dev;
+    p.m = (int)m;
+    p.top_k = top_k;
+    p.strict_floor = strict_floor;
+    p.broad_floor = broad_floor;
+    p.threshold_floor = threshold_floor;
+    p.out_strict = out_strict_dev;
+    p.out_broad = out_broad_dev;
+    p.out_bucket = out_bucket_dev;
+    p.out_counts = out_counts_dev;
+    finalize_kernel<<<(unsigned)nq, 128, 0, (cudaStream_t)stream>>>(p);
+    g_launches++;
+    CU(cudaGetLastError());
+    return PSX_OK;
+}
+
 extern "C" double psx_upload_gbps(psx_index* h) {
     if (!h) return 0.0;
     double best = h->up_last_gbps;

@@ -162,4 +162,98 @@ __global__ void __launch_bounds__(256) hybrid_fuse_kernel(const FuseParams p) {
     }
 }
 
+// ---- K5b: the numeric part of Searcher._finalize_results on the device --------------------------------------------------
+// Per query, over its fused scores in candidate order (best first, as hybrid_fuse_kernel leaves them):
+//   dynamic threshold   Searcher._calculate_dynamic_threshold (core/searcher.py:627-674): np.percentile(25 / 75) with
+//                       numpy's linear interpolation (a + (b-a) t, or b - (b-a)(1-t) for t >= 1/2), np.median, the
+//                       coefficient-of-variation rule, the top_k guard, round(., 6);
+//   strict / broad      core/searcher.py:1497-1509 from the round's score floors (_get_round_score_floors, host);
+//   bucket per hit      the score-only part of _assign_confidence_bucket (:828-840): 3 reliable, 2 generalised, 1 rest.
+// Python floats are doubles: every operation is an explicit round-to-nearest double intrinsic, round(x, 6) is round6().
+struct FinalizeParams {
+    const double* scores;   // [nq][m]  fused scores, descending
+    const int* counts;      // [nq]     valid entries per query
+    int m, top_k;
+    double strict_floor, broad_floor, threshold_floor;
+    double* out_strict;     // [nq]
+    double* out_broad;      // [nq]
+    int* out_bucket;        // [nq][m]  (0 beyond count)
+    int* out_counts;        // [nq][2]  reliable, generalised
+};
+
+// numpy's _lerp between the order statistics around virtual index (n-1) q of an ASCENDING view of the scores
+__device__ __forceinline__ double np_percentile_desc(const double* desc, int n, double q) {
+    const double vi = __dmul_rn((double)(n - 1), q);
+    const double pf = floor(vi);
+    const int prev = (int)pf;
+    const int next = prev + 1 < n ? prev + 1 : n - 1;
+    const double gamma = __dadd_rn(vi, -pf);
+    const double a = desc[n - 1 - prev], b = desc[n - 1 - next];
+    const double diff = __dadd_rn(b, -a);
+    if (gamma >= 0.5) return __dadd_rn(b, -__dmul_rn(diff, __dadd_rn(1.0, -gamma)));
+    return __dadd_rn(a, __dmul_rn(diff, gamma));
+}
+__device__ __forceinline__ double py_max(double a, double b) { return b > a ? b : a; }  // max(a, b): first maximal element
+__device__ __forceinline__ double py_min(double a, double b) { return b < a ? b : a; }
+
+__global__ void __launch_bounds__(128) finalize_kernel(const FinalizeParams p) {
+    __shared__ double s_strict, s_broad;
+    __shared__ int s_cnt[2];
+    const int qi = blockIdx.x;
+    const double* sc = p.scores + (size_t)qi * p.m;
+    int n = p.counts[qi];
+    n = n < 0 ? 0 : (n > p.m ? p.m : n);
+    if (threadIdx.x == 0) {
+        double strict = p.strict_floor, broad = p.broad_floor;
+        if (n > 0) {
+            double dyn;
+            if (n <= p.top_k * 2) {
+                dyn = py_max(__dmul_rn(sc[n - 1], 0.9), p.threshold_floor);  // (not rounded in the reference either)
+            } else {
+                const double q25 = np_percentile_desc(sc, n, 0.25), q75 = np_percentile_desc(sc, n, 0.75);
+                // np.median: mean of the middle element(s)
+                const double median = (n & 1) ? sc[n - 1 - n / 2] : __ddiv_rn(__dadd_rn(sc[n - 1 - (n / 2 - 1)], sc[n - 1 - n / 2]), 2.0);
+                const double cv = median > 0 ? __ddiv_rn(__dadd_rn(q75, -q25), median) : 1.0;
+                double thr;
+                if (cv < 0.2)
+                    thr = py_max(__dmul_rn(median, 0.85), __dmul_rn(q25, 0.9));
+                else if (cv < 0.5)
+                    thr = q25;
+                else
+                    thr = py_max(__dmul_rn(q25, 0.7), __dmul_rn(median, 0.7));
+                if (n >= p.top_k) thr = py_max(thr, __dmul_rn(sc[p.top_k - 1], 0.8));
+                dyn = round6(py_max(thr, p.threshold_floor), nullptr);
+            }
+            strict = py_max(dyn, p.strict_floor);
+            broad = py_min(__dadd_rn(strict, -0.05), py_max(p.broad_floor, __dmul_rn(strict, 0.84)));
+            broad = round6(py_max(p.broad_floor, broad), nullptr);
+        }
+        s_strict = strict;
+        s_broad = broad;
+        s_cnt[0] = s_cnt[1] = 0;
+        p.out_strict[qi] = strict;
+        p.out_broad[qi] = broad;
+    }
+    __syncthreads();
+    const double strict = s_strict, broad = s_broad;
+    int rel = 0, gen = 0;
+    for (int i = threadIdx.x; i < p.m; i += blockDim.x) {
+        int b = 0;
+        if (i < n) {
+            const double s = sc[i];
+            b = s >= strict ? 3 : s >= broad ? 2 : 1;
+            rel += b == 3;
+            gen += b == 2;
+        }
+        p.out_bucket[(size_t)qi * p.m + i] = b;
+    }
+    if (rel) atomicAdd(&s_cnt[0], rel);
+    if (gen) atomicAdd(&s_cnt[1], gen);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        p.out_counts[2 * qi] = s_cnt[0];
+        p.out_counts[2 * qi + 1] = s_cnt[1];
+    }
+}
+
 }  // namespace psx

@@ -43,3 +43,26 @@ def hybrid_fuse(vec_dist, vec_ids, kw_ids, kw_scores, *, vector_weight: float = 
         int(bool(allow_keyword_only)), int(bool(keyword_filtered)), out_ids.data_ptr(), out_fused.data_ptr(), out_v.data_ptr(),
         out_k.data_ptr(), count.data_ptr(), torch.cuda.current_stream(dev).cuda_stream or None))
     return out_ids, out_fused, out_v, out_k, count
+
+
+def finalize(fused, count, top_k: int, strict_floor: float, broad_floor: float, threshold_floor: float = 0.05):
+    """The numeric part of ``Searcher._finalize_results`` (core/searcher.py:1497-1526) for a batch of queries on the
+    device: ``fused`` float64 ``[nq, m]`` (descending per query) and ``count`` int32 ``[nq]`` as ``hybrid_fuse`` returns
+    them; the floors are the round's ``Searcher._get_round_score_floors(relaxation_level)``.  Returns
+    ``(strict_threshold [nq], broad_threshold [nq], bucket [nq, m], counts [nq, 2])`` -- thresholds bit-identical to the
+    reference's Python arithmetic (``_calculate_dynamic_threshold`` included), buckets 3 / 2 / 1 by score."""
+    import torch
+
+    fused = fused.contiguous().double()
+    count = count.contiguous().int()
+    nq, m = fused.shape
+    dev = fused.device
+    strict = torch.empty((nq,), dtype=torch.float64, device=dev)
+    broad = torch.empty((nq,), dtype=torch.float64, device=dev)
+    bucket = torch.empty((nq, m), dtype=torch.int32, device=dev)
+    counts = torch.empty((nq, 2), dtype=torch.int32, device=dev)
+    _native.check(_native.load_library().psx_finalize_device(
+        dev.index or 0, nq, m, fused.data_ptr(), count.data_ptr(), int(top_k), float(strict_floor), float(broad_floor),
+        float(threshold_floor), strict.data_ptr(), broad.data_ptr(), bucket.data_ptr(), counts.data_ptr(),
+        torch.cuda.current_stream(dev).cuda_stream or None))
+    return strict, broad, bucket, counts

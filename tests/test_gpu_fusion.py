@@ -94,3 +94,43 @@ def test_distance_to_score_bit_exact_on_a_dense_grid():
         got = {int(i): float(v) for i, v in zip(oid[qi, :kv], vs[qi, :kv])}
         for j in range(kv):
             assert got[j] == O.distance_to_score(float(dist[qi, j]))
+
+
+def test_finalize_thresholds_and_buckets_match_the_reference_arithmetic():
+    """psx_finalize_device vs the oracle restatement of Searcher._calculate_dynamic_threshold / _finalize_results
+    (core/searcher.py:627-674, :1497-1526): thresholds equal as doubles (np.percentile interpolation, np.median,
+    round(x, 6)), buckets and bucket counts equal -- over score lists of every length class (empty, <= 2 top_k, odd /
+    even, concentrated / dispersed distributions, scores on the 6-digit grid the fusion produces)."""
+    import torch
+
+    from oracle import flat_ip as O
+    from photo_search_engine_b200.fusion import finalize
+
+    rng = np.random.default_rng(77)
+    m = 700
+    lists = [[], [0.5], [0.9, 0.1]]
+    for t in range(400):
+        n = int(rng.integers(1, m + 1))
+        kind = t % 4
+        if kind == 0:
+            x = rng.random(n)
+        elif kind == 1:
+            x = 0.55 + 0.05 * rng.random(n)          # concentrated: cv < 0.2
+        elif kind == 2:
+            x = 0.3 + 0.5 * rng.random(n) ** 3        # skewed
+        else:
+            x = np.clip(rng.normal(0.4, 0.25, n), 0, 1)
+        lists.append(sorted(np.round(x, 6).tolist(), reverse=True))
+    for top_k, (sf, bf), floor in ((10, (0.4, 0.28), 0.05), (50, (0.24, 0.12), 0.05), (1, (0.32, 0.2), 0.3), (12, (0.22, 0.12), 0.0)):
+        fused = torch.zeros((len(lists), m), dtype=torch.float64)
+        count = torch.zeros((len(lists),), dtype=torch.int32)
+        for i, l in enumerate(lists):
+            fused[i, : len(l)] = torch.tensor(l, dtype=torch.float64)
+            count[i] = len(l)
+        strict, broad, bucket, counts = finalize(fused.cuda(), count.cuda(), top_k, sf, bf, floor)
+        strict, broad, bucket, counts = strict.cpu().numpy(), broad.cpu().numpy(), bucket.cpu().numpy(), counts.cpu().numpy()
+        for i, l in enumerate(lists):
+            ws, wb, wbuckets = O.finalize_thresholds(l, top_k, sf, bf, floor)
+            assert strict[i] == ws and broad[i] == wb, (top_k, i, len(l), strict[i], ws, broad[i], wb)
+            assert bucket[i, : len(l)].tolist() == wbuckets and (bucket[i, len(l):] == 0).all()
+            assert counts[i].tolist() == [wbuckets.count(3), wbuckets.count(2)]

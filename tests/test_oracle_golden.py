@@ -112,3 +112,44 @@ def test_call_site_arithmetic():
     assert O.calculate_candidate_k(10_000_000, 12, False) == 500
     assert O.calculate_candidate_k(10_000_000, 50, True, 3) == 1333
     assert O.calculate_candidate_k(40, 12, False) == 40
+
+
+def test_oracle_thresholds_equal_the_reference_searcher():
+    """oracle.calculate_dynamic_threshold / finalize_thresholds restate core/searcher.py:627-674, :822-853, :1497-1526:
+    pinned here against the reference's own methods (checkout or staged copy) on random score lists."""
+    import sys
+    import types
+
+    import pytest
+
+    from oracle import flat_ip as O
+    from oracle import stage_reference
+
+    ref = stage_reference.locate()
+    if ref is None:
+        pytest.skip("reference Searcher neither checked out nor staged")
+    saved = list(sys.path)
+    sys.path.insert(0, ref)
+    try:
+        if "utils.vector_store" not in sys.modules:
+            shim = types.ModuleType("utils.vector_store")
+            shim.VectorStore = object
+            sys.modules["utils.vector_store"] = shim
+        from core.searcher import Searcher
+    finally:
+        sys.path[:] = saved
+    s = Searcher.__new__(Searcher)
+    s.query_dynamic_threshold_floor, s.query_strict_floor_min, s.query_broad_floor_min = 0.05, 0.22, 0.12
+    rng = np.random.default_rng(3)
+    for t in range(300):
+        n = int(rng.integers(0, 600))
+        x = rng.random(n) if t % 2 else 0.5 + 0.1 * rng.random(n)
+        scores = sorted(np.round(x, 6).tolist(), reverse=True)
+        top_k = int(rng.integers(1, 51))
+        level = int(rng.integers(0, 4))
+        assert O.calculate_dynamic_threshold(scores, top_k, 0.05) == s._calculate_dynamic_threshold(scores, top_k)
+        sf, bf = s._get_round_score_floors(level)
+        strict, broad, buckets = O.finalize_thresholds(scores, top_k, sf, bf, 0.05)
+        want = [s._assign_confidence_bucket(item={"score": v}, strict_threshold=strict, broad_threshold=broad, media_terms=[],
+                                            identity_terms=[], strict_identity_filter=False) for v in scores]
+        assert buckets == want
