@@ -104,7 +104,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.device_index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+                                          "-i", str(self.device_index), "-lms", "50"], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:
             self.proc = None
@@ -346,8 +346,11 @@ def run_ours(args):
             return float(tmax[0]), float(tmax[1]), int(tsum[2]), n_br, every
         return total_ms, scan_ms, launches, n_br, every
 
-    measure(2)  # settle clocks / caches once before anything is recorded
+    # nvidia-smi needs ~0.1 s before its first sample and the driver's run (--steps 20) times ~0.1 s: the sampler starts in
+    # front of an identical settle pass (same loop, same load) so that the timed pass itself is covered by samples
     clocks = ClockSampler(local_rank).start() if rank == 0 else None
+    time.sleep(0.15 if rank == 0 else 0.0)
+    measure(2)  # settle clocks / caches once before anything is recorded
     total_ms, scan_ms, launches, n_bracketed, EVERY = measure(2)
     clock_info = clocks.stop() if clocks else None
     ms_per_step = total_ms / args.steps

@@ -168,6 +168,7 @@ struct psx_index {
     long long shard_min_rows = 8192;     // never split a corpus into shards smaller than this (tunable "shard_min_rows")
     unsigned char* gx = nullptr;         // home device: receive buffer of the fused exchange (psx_exchange_bytes())
     uint32_t gseq = 0;
+    uint32_t g_synced_seq = 0;           // fused queries up to this sequence number are known complete (host synchronised)
     uint64_t* gkeys = nullptr;           // home device: [nq][active shards][kpad] key lists (batches, paging, mixed tier)
     size_t gkeys_cap = 0;
     cudaEvent_t g_merged[2] = {nullptr, nullptr};  // home stream: the merge of query i (slot i & 1) has completed

@@ -448,8 +448,11 @@ static int group_ensure_keys(psx_index* g, size_t words) {
     return PSX_OK;
 }
 
-// queries [q0, q0+gq) from the pinned staging to every active child (each on its own stream)
+// Queries [q0, q0+gq): ONE copy from the pinned staging to the home device; every other child reads home's copy through
+// its peer mapping (a query is 4 KB per CTA: nothing next to the rows it scans) and only orders its stream behind the
+// copy with an event.  Per query and child that is one cudaStreamWaitEvent instead of a memcpy + an event record.
 static int group_send_queries(psx_index* g, const std::vector<GroupActive>& act, const float* q, int64_t gq) {
+    psx_index* home = g->shards[0];
     const size_t floats = (size_t)gq * g->d;
     if (floats > g->g_hq_cap) {
         cudaFreeHost(g->g_hq);
@@ -458,20 +461,24 @@ static int group_send_queries(psx_index* g, const std::vector<GroupActive>& act,
         CU(cudaHostAlloc(&g->g_hq, floats * sizeof(float), cudaHostAllocPortable));
         g->g_hq_cap = floats;
     }
-    // the staging may still be the source of the previous step's copies (paged calls issue several steps per sync)
-    for (const GroupActive& a : act)
-        if (g->g_h2d_busy[a.shard]) {
-            CU(cudaEventSynchronize(g->g_h2d[a.shard]));
-            g->g_h2d_busy[a.shard] = 0;
-        }
+    // the staging may still be the source of the previous step's copy (paged calls issue several steps per sync)
+    if (g->g_h2d_busy[0]) {
+        CU(cudaEventSynchronize(g->g_h2d[0]));
+        g->g_h2d_busy[0] = 0;
+    }
     memcpy(g->g_hq, q, floats * sizeof(float));
-    for (const GroupActive& a : act) {
-        DeviceGuard dg(a.c->device);
-        int rc = ensure_io(a.c, floats, 1);
+    {
+        DeviceGuard dg(home->device);
+        int rc = ensure_io(home, floats, 1);
         if (rc) return rc;
-        CU(cudaMemcpyAsync(a.c->dq, g->g_hq, floats * sizeof(float), cudaMemcpyHostToDevice, a.c->stream));
-        CU(cudaEventRecord(g->g_h2d[a.shard], a.c->stream));
-        g->g_h2d_busy[a.shard] = 1;
+        CU(cudaMemcpyAsync(home->dq, g->g_hq, floats * sizeof(float), cudaMemcpyHostToDevice, home->stream));
+        CU(cudaEventRecord(g->g_h2d[0], home->stream));
+        g->g_h2d_busy[0] = 1;
+    }
+    for (const GroupActive& a : act) {
+        if (a.c == home) continue;
+        DeviceGuard dg(a.c->device);
+        CU(cudaStreamWaitEvent(a.c->stream, g->g_h2d[0], 0));
     }
     return PSX_OK;
 }
@@ -525,7 +532,7 @@ static int group_keyed_step(psx_index* g, const std::vector<GroupActive>& act, i
         uint64_t* slot0 = g->gkeys + i * kpad;  // query qi's list of this child: slot0 + qi * A * kpad
         if (batched && !ceil_base && batch_shape_ok(c, kp)) {
             if ((rc = ensure_batch_scratch(c, 0))) return rc;
-            if ((rc = launch_batch(c, c->dq, (int)gq, kp, filter, act[i].id_base, 0.f, nullptr, nullptr, slot0, c->bflags, c->stream,
+            if ((rc = launch_batch(c, home->dq, (int)gq, kp, filter, act[i].id_base, 0.f, nullptr, nullptr, slot0, c->bflags, c->stream,
                                    (long long)(A * kpad))))
                 return rc;
             CU(cudaMemcpyAsync(c->hflags, c->bflags, (size_t)gq * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
@@ -534,7 +541,7 @@ static int group_keyed_step(psx_index* g, const std::vector<GroupActive>& act, i
         } else {
             for (int64_t qi = 0; qi < gq; ++qi) {
                 const uint64_t* ceil_ptr = ceil_base ? ceil_base + (size_t)qi * ceil_stride : nullptr;
-                if ((rc = launch_query(c, c->dq + (size_t)qi * g->d, kp, filter, act[i].id_base, ceil_ptr, nullptr, nullptr,
+                if ((rc = launch_query(c, home->dq + (size_t)qi * g->d, kp, filter, act[i].id_base, ceil_ptr, nullptr, nullptr,
                                        slot0 + (size_t)qi * A * kpad, c->stream)))
                     return rc;
             }
@@ -549,7 +556,7 @@ static int group_keyed_step(psx_index* g, const std::vector<GroupActive>& act, i
         for (int64_t qi = 0; qi < gq; ++qi) {
             if (!c->hflags[qi]) continue;
             c->batch_fallbacks++;
-            if ((rc = launch_exact_scan(c, c->dq + (size_t)qi * g->d, kp, filter, act[i].id_base, nullptr, nullptr, nullptr,
+            if ((rc = launch_exact_scan(c, home->dq + (size_t)qi * g->d, kp, filter, act[i].id_base, nullptr, nullptr, nullptr,
                                         g->gkeys + ((size_t)qi * A + i) * kpad, c->stream)))
                 return rc;
         }
@@ -563,7 +570,10 @@ static int group_fused_query(psx_index* g, const std::vector<GroupActive>& act, 
                              long long* out_ids) {
     psx_index* home = g->shards[0];
     const int A = (int)act.size();
-    if (++g->gseq == 0) g->gseq = 1;
+    if (++g->gseq == 0) {
+        g->gseq = 1;
+        g->g_synced_seq = 0;
+    }
     const uint32_t seq = g->gseq;
     const uint64_t bases[1] = {(uint64_t)(uintptr_t)g->gx};
     int rc;
@@ -573,7 +583,8 @@ static int group_fused_query(psx_index* g, const std::vector<GroupActive>& act, 
     for (int i = A - 1; i >= 0; --i) {  // home last: its last CTA also merges
         psx_index* c = act[i].c;
         DeviceGuard dg(c->device);
-        if (c != home) CU(cudaStreamWaitEvent(c->stream, g->g_merged[seq & 1u], 0));
+        // (nothing to wait for when the host has synchronised with home since that merge -- the one-query-per-call case)
+        if (c != home && seq >= 3 && seq - 2 > g->g_synced_seq) CU(cudaStreamWaitEvent(c->stream, g->g_merged[seq & 1u], 0));
         XchgArgs xa{A, i, seq, bases, 1};
         if (g->fault_skip_publish == (int)act[i].shard) xa.targets = -1;  // test hook: this shard stays silent
         if (c == home && inline_merge) {
@@ -584,7 +595,7 @@ static int group_fused_query(psx_index* g, const std::vector<GroupActive>& act, 
             xa.status = g->xstatus_dev;
             xa.spin_limit = xchg_spin_limit(g->xchg_timeout_ms);
         }
-        if ((rc = launch_scan(c, c->dq + (size_t)qi * g->d, kp, filter, act[i].id_base, nullptr, nullptr, nullptr, nullptr, c->stream, &xa)))
+        if ((rc = launch_scan(c, home->dq + (size_t)qi * g->d, kp, filter, act[i].id_base, nullptr, nullptr, nullptr, nullptr, c->stream, &xa)))
             return rc;
     }
     DeviceGuard dg(home->device);
@@ -633,10 +644,7 @@ static int group_search(psx_index* g, const float* q, int64_t nq, int64_t k, con
     const bool batched = g->batch_min > 0 && nq >= g->batch_min && pages == 1;
     const bool fused = !batched && pages == 1 && g->dtype != PSX_STORE_BF16_MASTER && act.size() <= PSX_XCHG_MAX_WORLD;
     const int64_t group = std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(nq, BATCH_MAX_Q), (8ll << 20) / kslot));
-    for (const GroupActive& a : act) {
-        DeviceGuard dg(a.c->device);
-        if ((rc = enter_stream(a.c, a.c->stream))) return rc;
-    }
+    for (const GroupActive& a : act) a.c->call_first = true;  // (children only ever use their own stream: no cross-stream event)
     {
         DeviceGuard dg(home->device);
         if ((rc = ensure_io(home, (size_t)group * g->d, (size_t)group * kslot))) return rc;
@@ -674,6 +682,7 @@ static int group_search(psx_index* g, const float* q, int64_t nq, int64_t k, con
         CU(cudaMemcpyAsync(home->hscores, home->dscores, (size_t)gq * per_q * sizeof(float), cudaMemcpyDeviceToHost, home->stream));
         CU(cudaMemcpyAsync(home->hids, home->dids, (size_t)gq * per_q * sizeof(long long), cudaMemcpyDeviceToHost, home->stream));
         CU(cudaStreamSynchronize(home->stream));
+        g->g_synced_seq = g->gseq;  // every fused merge issued so far has completed
         if (fused && *g->xstatus_host) {
             // a device never published: say which, and answer the group of queries over the event-ordered path
             g->g_timeouts++;
@@ -698,10 +707,6 @@ static int group_search(psx_index* g, const float* q, int64_t nq, int64_t k, con
                 oi[i] = -1;
             }
         }
-    }
-    for (const GroupActive& a : act) {
-        DeviceGuard dg(a.c->device);
-        if ((rc = leave_stream(a.c, a.c->stream))) return rc;
     }
     return PSX_OK;
 }
