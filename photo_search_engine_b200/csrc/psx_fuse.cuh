@@ -193,8 +193,25 @@ __device__ __forceinline__ double np_percentile_desc(const double* desc, int n, 
     if (gamma >= 0.5) return __dadd_rn(b, -__dmul_rn(diff, __dadd_rn(1.0, -gamma)));
     return __dadd_rn(a, __dmul_rn(diff, gamma));
 }
-__device__ __forceinline__ double py_max(double a, double b) { return b > a ? b : a; }  // max(a, b): first maximal element
-__device__ __forceinline__ double py_min(double a, double b) { return b < a ? b : a; }
+// The reference mixes Python floats and numpy float64 scalars (np.percentile / np.median return the latter, and
+// arithmetic keeps the numpy type), and `round(x, 6)` means different algorithms for the two: CPython rounds the EXACT
+// binary value correctly (round6), numpy computes rint(x * 1e6) / 1e6.  They differ when x * 1e6 rounds onto a tie --
+// frequent here, where x is 0.85 x (a score on the 6-digit grid).  So every value carries its type, and max() / min()
+// return the OBJECT Python would return (the first argument unless the second is strictly greater / smaller).
+struct PyNum {
+    double v;
+    bool is_np;
+};
+__device__ __forceinline__ PyNum py_float(double v) { return PyNum{v, false}; }
+__device__ __forceinline__ PyNum np_float(double v) { return PyNum{v, true}; }
+__device__ __forceinline__ PyNum py_max(PyNum a, PyNum b) { return b.v > a.v ? b : a; }
+__device__ __forceinline__ PyNum py_min(PyNum a, PyNum b) { return b.v < a.v ? b : a; }
+__device__ __forceinline__ PyNum py_mul(PyNum a, double c) { return PyNum{__dmul_rn(a.v, c), a.is_np}; }
+__device__ __forceinline__ PyNum py_add(PyNum a, double c) { return PyNum{__dadd_rn(a.v, c), a.is_np}; }
+__device__ __forceinline__ PyNum py_round6(PyNum x) {
+    if (x.is_np) return PyNum{__ddiv_rn(rint(__dmul_rn(x.v, 1e6)), 1e6), true};  // np.float64.__round__
+    return PyNum{round6(x.v, nullptr), false};                                     // float.__round__
+}
 
 __global__ void __launch_bounds__(128) finalize_kernel(const FinalizeParams p) {
     __shared__ double s_strict, s_broad;
@@ -204,35 +221,38 @@ __global__ void __launch_bounds__(128) finalize_kernel(const FinalizeParams p) {
     int n = p.counts[qi];
     n = n < 0 ? 0 : (n > p.m ? p.m : n);
     if (threadIdx.x == 0) {
-        double strict = p.strict_floor, broad = p.broad_floor;
+        double strict_v = p.strict_floor, broad_v = p.broad_floor;
         if (n > 0) {
-            double dyn;
+            PyNum dyn;
             if (n <= p.top_k * 2) {
-                dyn = py_max(__dmul_rn(sc[n - 1], 0.9), p.threshold_floor);  // (not rounded in the reference either)
+                dyn = py_max(py_float(__dmul_rn(sc[n - 1], 0.9)), py_float(p.threshold_floor));  // (not rounded in the reference either)
             } else {
-                const double q25 = np_percentile_desc(sc, n, 0.25), q75 = np_percentile_desc(sc, n, 0.75);
+                const PyNum q25 = np_float(np_percentile_desc(sc, n, 0.25)), q75 = np_float(np_percentile_desc(sc, n, 0.75));
                 // np.median: mean of the middle element(s)
-                const double median = (n & 1) ? sc[n - 1 - n / 2] : __ddiv_rn(__dadd_rn(sc[n - 1 - (n / 2 - 1)], sc[n - 1 - n / 2]), 2.0);
-                const double cv = median > 0 ? __ddiv_rn(__dadd_rn(q75, -q25), median) : 1.0;
-                double thr;
+                const PyNum median = np_float((n & 1) ? sc[n - 1 - n / 2]
+                                                      : __ddiv_rn(__dadd_rn(sc[n - 1 - (n / 2 - 1)], sc[n - 1 - n / 2]), 2.0));
+                const double cv = median.v > 0 ? __ddiv_rn(__dadd_rn(q75.v, -q25.v), median.v) : 1.0;
+                PyNum thr;
                 if (cv < 0.2)
-                    thr = py_max(__dmul_rn(median, 0.85), __dmul_rn(q25, 0.9));
+                    thr = py_max(py_mul(median, 0.85), py_mul(q25, 0.9));
                 else if (cv < 0.5)
                     thr = q25;
                 else
-                    thr = py_max(__dmul_rn(q25, 0.7), __dmul_rn(median, 0.7));
-                if (n >= p.top_k) thr = py_max(thr, __dmul_rn(sc[p.top_k - 1], 0.8));
-                dyn = round6(py_max(thr, p.threshold_floor), nullptr);
+                    thr = py_max(py_mul(q25, 0.7), py_mul(median, 0.7));
+                if (n >= p.top_k) thr = py_max(thr, py_float(__dmul_rn(sc[p.top_k - 1], 0.8)));
+                dyn = py_round6(py_max(thr, py_float(p.threshold_floor)));
             }
-            strict = py_max(dyn, p.strict_floor);
-            broad = py_min(__dadd_rn(strict, -0.05), py_max(p.broad_floor, __dmul_rn(strict, 0.84)));
-            broad = round6(py_max(p.broad_floor, broad), nullptr);
+            const PyNum strict = py_max(dyn, py_float(p.strict_floor));
+            PyNum broad = py_min(py_add(strict, -0.05), py_max(py_float(p.broad_floor), py_mul(strict, 0.84)));
+            broad = py_round6(py_max(py_float(p.broad_floor), broad));
+            strict_v = strict.v;
+            broad_v = broad.v;
         }
-        s_strict = strict;
-        s_broad = broad;
+        s_strict = strict_v;
+        s_broad = broad_v;
         s_cnt[0] = s_cnt[1] = 0;
-        p.out_strict[qi] = strict;
-        p.out_broad[qi] = broad;
+        p.out_strict[qi] = strict_v;
+        p.out_broad[qi] = broad_v;
     }
     __syncthreads();
     const double strict = s_strict, broad = s_broad;
