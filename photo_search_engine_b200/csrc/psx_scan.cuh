@@ -386,6 +386,12 @@ __global__ void __launch_bounds__(PSX_MAX_THREADS, 1) scan_topk_kernel(const Sca
     uint32_t rid_batch = 0;           // list launches: lane l holds list[u_first * R + l]
     uint32_t grab_base = 0, grab_cnt = 0;  // dynamic batch requested ahead of time (base valid in lane 0)
     bool grab_pending = false;
+    // list launches, statically dealt part: the ids of this warp's next batches are fetched 32 entries at a time (one
+    // independent load per lane) instead of one dependent load per batch -- a short list gives a warp a handful of
+    // single-row batches, and their id loads in series were a third of such a query
+    uint32_t pf_ids = 0;              // lane e holds entry e of the prefetched run
+    uint32_t pf_first = 0;            // static batch index (multiple of Wt past gw) the run starts at
+    uint32_t pf_batches = 0, pf_used = 0;  // batches in the run / already opened
     // ---- PSX_SCAN_GROUPS producer state ------------------------------------------------------
     const int G = p.gsize;
     const uint32_t rmask = R >= 32 ? 0xffffffffu : ((1u << R) - 1u);
@@ -419,7 +425,8 @@ __global__ void __launch_bounds__(PSX_MAX_THREADS, 1) scan_topk_kernel(const Sca
         grab_pending = true;
     };
     auto open_batch = [&]() -> bool {
-        if ((uint64_t)s_next * bs < n_static) {
+        const bool was_static = (uint64_t)s_next * bs < n_static;
+        if (was_static) {
             u_cur = s_next * bs;
             u_end = u_cur + bs < n_static ? u_cur + bs : n_static;
             s_next += Wt;
@@ -436,8 +443,24 @@ __global__ void __launch_bounds__(PSX_MAX_THREADS, 1) scan_topk_kernel(const Sca
         }
         if (listed) {  // the row ids of the whole batch: (u_end - u_cur) * R <= 32 entries
             u_first = u_cur;
-            const uint32_t idx = u_cur * (uint32_t)R + lane;
-            rid_batch = (lane < (u_end - u_cur) * (uint32_t)R && idx < n_rows) ? __ldg(p.rowlist + idx) : 0u;
+            const uint32_t per = bs * (uint32_t)R;  // list entries per static batch (<= 32)
+            if (was_static && per <= 16u) {
+                if (pf_used == pf_batches) {  // fetch the ids of the next 32 / per static batches of this warp
+                    pf_first = u_cur / bs;    // (= the batch index just opened)
+                    pf_batches = 32u / per;
+                    pf_used = 0;
+                    const uint32_t j = (uint32_t)lane / per, o = (uint32_t)lane % per;
+                    const uint64_t b = (uint64_t)pf_first + (uint64_t)j * Wt;
+                    const uint64_t idx = b * per + o;
+                    pf_ids = (j < pf_batches && b * bs < n_static && idx < n_rows && (b * bs + o / (uint32_t)R) < n_static)
+                                 ? __ldg(p.rowlist + idx) : 0u;
+                }
+                rid_batch = __shfl_sync(0xffffffffu, pf_ids, (pf_used * per + (uint32_t)lane) & 31u);
+                ++pf_used;
+            } else {
+                const uint32_t idx = u_cur * (uint32_t)R + lane;
+                rid_batch = (lane < (u_end - u_cur) * (uint32_t)R && idx < n_rows) ? __ldg(p.rowlist + idx) : 0u;
+            }
         }
         return true;
     };

@@ -163,13 +163,15 @@ def test_batches_take_the_tensor_core_path_per_shard(devices):
     many.close()
 
 
-def test_appends_rebalance_and_keep_ids():
+@pytest.mark.parametrize("dtype", ["fp32", "bf16+fp32"])
+def test_appends_rebalance_and_keep_ids(dtype):
     """add_item-style growth (core/indexer.py:858): rows trickle in, the tail shard grows, the layout is re-split with
-    device-to-device copies -- ids, reconstruct, read_rows and attribute words follow their rows."""
+    device-to-device copies -- ids, reconstruct, read_rows and attribute words follow their rows (and, on the
+    bf16 + fp32-master tier, both copies of every row)."""
     rng = np.random.default_rng(41)
     d, total = 32, 6000
     x = unit_rows(rng, total, d)
-    one, many = pair(d, [0, 0, 0], min_rows=64)
+    one, many = pair(d, [0, 0, 0], dtype=N().STORE_F32 if dtype == "fp32" else N().STORE_BF16_MASTER, min_rows=64)
     words = (np.arange(total, dtype=np.uint64) % np.uint64(7)) + np.uint64(1)
     done = 0
     layouts = set()
