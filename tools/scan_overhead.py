@@ -111,6 +111,8 @@ def main():
                     ix.set_tunable("filter_mode", mode)
                     us = timed(ix, qs, a.k, a.steps, flt)
                     res.setdefault(f"filter_mode={mode}", []).append([round(us, 1), round(algo / us / 1e3)])
+                ix.set_tunable("filter_mode", 2)
+                res["trace_row_list_scan"] = trace_once(ix, qs[0], a.k, flt)   # phase times of the listed scan (no overlap while traced)
                 print(json.dumps(res), flush=True)
         ix.close()
         del ix
