@@ -379,6 +379,28 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_qps = args.steps / float(te[0])
+    # the same end-to-end work with two queries in flight (ShardedIndex.submit / collect): every step still copies its
+    # query from pinned host memory and reads its result back, but the host side of query i+1 overlaps the scan of
+    # query i -- what a server with several request threads gets.  Reported beside the one-at-a-time number.
+    e2e_pipelined_qps = None
+    if world > 1:
+        for i in range(3):
+            sharded.collect(sharded.submit(queries_host[i], k), k)
+        barrier()
+        t0 = time.perf_counter()
+        pending = sharded.submit(queries_host[0], k)
+        for i in range(1, args.steps):
+            nxt = sharded.submit(queries_host[i % N_QUERIES], k)
+            S_p, I_p = sharded.collect(pending, k)
+            pending = nxt
+        S_p, I_p = sharded.collect(pending, k)
+        torch.cuda.synchronize()
+        tp = torch.tensor([time.perf_counter() - t0], device=device, dtype=torch.float64)
+        dist.all_reduce(tp, op=dist.ReduceOp.MAX)
+        e2e_pipelined_qps = args.steps / float(tp[0])
+        last = (args.steps - 1) % N_QUERIES
+        S_chk, I_chk = sharded.search(queries_host[last], k)
+        assert np.array_equal(I_p, I_chk) and np.array_equal(S_p, S_chk), "pipelined result differs from the one-at-a-time result"
 
     # ---- parity spot check at every N.  A fused predicate selects every P-th GLOBAL row (dt word = 1 + row % P,
     # filter dt <= 1), i.e. a stripe of EVERY shard; the selected rows are read back from the index' own HBM arena,
@@ -517,8 +539,14 @@ def run_ours(args):
                          "kernel_ms": scan_ms, "kernel_ms_note": f"CUDA events around every {EVERY}th scan launch of the timed region ({n_bracketed} launches)",
                          "peak_source": peak_src, "frac_of_8TBps_spec": achieved / 8000.0},
             "cpu_baseline": cpu,
-            "e2e": {"value": e2e_qps, "unit": "queries/s", "h2d_bytes_per_step": world * d * 4, "d2h_bytes_per_step": world * k * 12,
-                    "api": e2e_api},
+            # N > 1: the throughput API (two queries in flight) is the end-to-end number, the one-at-a-time call beside it
+            "e2e": ({"value": e2e_pipelined_qps, "unit": "queries/s", "h2d_bytes_per_step": world * d * 4, "d2h_bytes_per_step": world * k * 12,
+                     "api": "ShardedIndex.submit / collect (host query -> host scores, ids), every rank, two queries in flight: every step copies "
+                            "its query from pinned host memory and reads its result back; the host side of query i+1 overlaps the scan of query i",
+                     "value_one_at_a_time": e2e_qps, "one_at_a_time_api": e2e_api}
+                    if e2e_pipelined_qps else
+                    {"value": e2e_qps, "unit": "queries/s", "h2d_bytes_per_step": world * d * 4, "d2h_bytes_per_step": world * k * 12,
+                     "api": e2e_api}),
             "gpu_launches": launches,
             "clocks": clock_info,
         }

@@ -200,6 +200,59 @@ class ShardedIndex:
         idx = t.nonzero(keep, as_tuple=False)[:k, 0]
         return s[0][idx], i[0][idx]
 
+    # -- throughput form of `search`: several queries in flight -------------------------------------------------------
+    PIPELINE_DEPTH = 2
+
+    def submit(self, q: np.ndarray, k: int, flt=None) -> int:
+        """Enqueue one host query (pinned H2D, sharded search, D2H of the merged result) WITHOUT waiting for it and
+        return a ticket for :meth:`collect`.  Up to ``PIPELINE_DEPTH`` tickets may be outstanding: the host-side work
+        of query i+1 (copies, launches) then overlaps the scan of query i, which is what a server with several request
+        threads gets.  Collective: every rank submits the same queries in the same order.  Single queries only."""
+        t = self.torch
+        q = np.ascontiguousarray(q, np.float32).reshape(1, -1)
+        if self.device.type != "cuda":
+            raise RuntimeError("submit/collect is the GPU throughput path")
+        slots = self._bufs.setdefault(("pipe", k), [])
+        n = getattr(self, "_pipe_next", 0)
+        self._pipe_next = n + 1
+        if len(slots) < self.PIPELINE_DEPTH:
+            kp, d = _native.kpad(k), self.local.d
+            slots.append(dict(q=t.empty((1, d), dtype=t.float32, device=self.device), q_host=t.empty((1, d), dtype=t.float32, pin_memory=True),
+                              scores=t.empty((1, k), dtype=t.float32, device=self.device), ids=t.empty((1, k), dtype=t.int64, device=self.device),
+                              scores_host=t.empty((1, k), dtype=t.float32, pin_memory=True), ids_host=t.empty((1, k), dtype=t.int64, pin_memory=True),
+                              mine=t.zeros((1, kp), dtype=t.int64, device=self.device), gathered=t.zeros((self.world, kp), dtype=t.int64, device=self.device),
+                              done=t.cuda.Event(), busy=False))
+        slot = slots[n % self.PIPELINE_DEPTH]
+        if slot["busy"]:
+            raise RuntimeError("collect() the oldest ticket before submitting another query")
+        slot["q_host"].copy_(t.from_numpy(q))
+        slot["q"].copy_(slot["q_host"], non_blocking=True)
+        stream = t.cuda.current_stream(self.device).cuda_stream
+        if self.world == 1:
+            self.local.search_device(slot["q"].data_ptr(), 1, k, slot["scores"].data_ptr(), slot["ids"].data_ptr(), 0, flt=flt,
+                                     id_base=self.row0, stream=stream)
+        elif self.exchange == "p2p":
+            self._seq += 1
+            self.local.search_exchange_device(slot["q"].data_ptr(), k, self.rank, self.world, self._xchg_bases, self._seq,
+                                              slot["scores"].data_ptr(), slot["ids"].data_ptr(), flt=flt, id_base=self.row0, stream=stream)
+        else:
+            self.local.search_device(slot["q"].data_ptr(), 1, k, 0, 0, slot["mine"].data_ptr(), flt=flt, id_base=self.row0, stream=stream)
+            self.dist.all_gather_into_tensor(slot["gathered"], slot["mine"], group=self.group)
+            _native.merge_keys_device(self.local.device, slot["gathered"].data_ptr(), 1, self.world, k, self.local.metric,
+                                      slot["scores"].data_ptr(), slot["ids"].data_ptr(), stream)
+        slot["scores_host"].copy_(slot["scores"], non_blocking=True)
+        slot["ids_host"].copy_(slot["ids"], non_blocking=True)
+        slot["done"].record(t.cuda.current_stream(self.device))
+        slot["busy"] = True
+        return n
+
+    def collect(self, ticket: int, k: int) -> Tuple[np.ndarray, np.ndarray]:
+        """Wait for the query behind ``ticket`` and return ``(scores [1,k], ids [1,k])`` on the host."""
+        slot = self._bufs[("pipe", k)][ticket % self.PIPELINE_DEPTH]
+        slot["done"].synchronize()
+        slot["busy"] = False
+        return slot["scores_host"].numpy().copy(), slot["ids_host"].numpy().copy()
+
     def search(self, q: np.ndarray, k: int, flt=None) -> Tuple[np.ndarray, np.ndarray]:
         """Host in, host out (the call a user makes): pinned H2D of the query, sharded search,
         D2H of the merged result.  Collective: every rank must call it with the same query."""

@@ -133,6 +133,7 @@ class VectorStore:
         # old backend handle is never destroyed explicitly: a search running on another request thread still holds a
         # reference, and the handle is freed when the last reference goes (as with the reference's faiss object).
         self._swap_lock = threading.RLock()
+        self._attrs_lock = threading.Lock()  # the lazy EXIF sidecar is built once, whichever request thread needs it first
         self.metadata: List[Dict] = []
         self._embeddings: List[Optional[List[float]]] = []
         self._path_to_index: Dict[str, int] = {}
@@ -175,6 +176,17 @@ class VectorStore:
                 return (as_f32 / length).astype("float32").tolist()
         return vector
 
+    def _query_row(self, vector: Sequence[float]) -> np.ndarray:
+        """The ``(1, d)`` float32 query ``search`` hands to the backend: the same numpy operations as
+        ``_normalize_vector`` (utils/vector_store.py:83-90) without the detour through a Python list -- a float32 value
+        survives list -> float32 unchanged, so the bits are the ones the reference would send."""
+        as_f32 = np.array(vector, dtype="float32")
+        if self._normalize:
+            length = np.linalg.norm(as_f32)
+            if length != 0:
+                as_f32 = (as_f32 / length).astype("float32")
+        return as_f32[None, :]
+
     def _remember_path(self, metadata: Dict, row: int) -> None:
         photo_path = metadata.get("photo_path")
         if isinstance(photo_path, str) and photo_path:
@@ -198,13 +210,14 @@ class VectorStore:
 
     def _upload_attrs(self) -> None:
         """Lazy EXIF sidecar: pack and upload attribute words for rows that lack one."""
-        total = len(self.metadata)
-        if self.index is None or self._attrs_built >= total:
-            return
-        words = attr_words(self.metadata[self._attrs_built : total])
-        self.index.set_attrs(self._attrs_built, words)
-        self._attr_words = np.concatenate([self._attr_words[: self._attrs_built], words])
-        self._attrs_built = total
+        with self._attrs_lock:
+            total = len(self.metadata)
+            if self.index is None or self._attrs_built >= total:
+                return
+            words = attr_words(self.metadata[self._attrs_built : total])
+            self.index.set_attrs(self._attrs_built, words)
+            self._attr_words = np.concatenate([self._attr_words[: self._attrs_built], words])
+            self._attrs_built = total
 
     def _run_search(self, queries: np.ndarray, k: int, flt) -> Tuple[np.ndarray, np.ndarray]:
         if flt is None:
@@ -275,7 +288,7 @@ class VectorStore:
         flt, never = self._filter_for(constraints)
         if never:
             return []
-        query = np.array([self._normalize_vector(query_embedding)], dtype="float32")
+        query = self._query_row(query_embedding)
         if self._coalescer is not None:
             row_scores, row_labels = self._coalescer.submit(query[0], k, None if flt is None else bytes(flt), flt)
         else:
