@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define PSX_ABI_VERSION 1
+#define PSX_ABI_VERSION 2
 
 typedef enum psx_status {
     PSX_OK = 0,

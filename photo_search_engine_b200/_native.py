@@ -103,7 +103,7 @@ def load_library() -> C.CDLL:
         fn = getattr(lib, name)  # AttributeError -> the .so is stale
         fn.restype = restype
         fn.argtypes = argtypes
-    if lib.psx_abi_version() != 1:
+    if lib.psx_abi_version() != 2:
         raise ImportError("libpsx.so ABI version mismatch; rebuild")
     _lib = lib
     return lib

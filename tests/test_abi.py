@@ -29,7 +29,7 @@ def test_header_symbols_are_exported_and_bound():
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in psx.h but not exported by libpsx.so"
     assert sorted(_native.EXPORTED_SYMBOLS) == declared  # the ctypes table covers the whole header
-    assert lib.psx_abi_version() == 1
+    assert lib.psx_abi_version() == 2
     assert _native.kpad(100) == 128 and _native.kpad(1) == 32 and _native.kpad(2048) == 2048
 
 
