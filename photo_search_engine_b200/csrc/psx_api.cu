@@ -252,7 +252,7 @@ static cudaError_t launch_ex(void (*kernel)(KArgs...), unsigned grid, unsigned b
 template <bool BF>
 static int launch_gemm_pair(psx_index* h, const CUtensorMap& mq, const CUtensorMap& mx, const GemmParams& gp, int pairs, cudaStream_t st,
                             bool pdl) {
-    constexpr size_t smem = (size_t)PAIR_STAGES * (GEMM_M + 128) * GEMM_KB_BYTES + 256;
+    constexpr size_t smem = (size_t)PAIR_STAGES * (GEMM_M + 128) * GEMM_KB_BYTES + 256 + GEMM_STAGE_BYTES_PER_ACC;
     static std::atomic<bool> ready[64];
     if (h->device < 64 && !ready[h->device].load()) {
         CU(cudaFuncSetAttribute(gemm_filter_pair_kernel<PAIR_STAGES, BF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1096,7 +1096,7 @@ static int launch_gemm(psx_index* h, const CUtensorMap& mq, const CUtensorMap& m
     constexpr int STAGES = BatchCfg<MT>::STAGES;
     constexpr int BATCH_BN = BatchCfg<MT>::BN;
     constexpr int STAGE_BYTES = (MT * GEMM_M + BATCH_BN) * GEMM_KB_BYTES;
-    constexpr size_t smem = (size_t)STAGES * STAGE_BYTES + 256;
+    constexpr size_t smem = (size_t)STAGES * STAGE_BYTES + 256 + (size_t)MT * GEMM_STAGE_BYTES_PER_ACC;
     static std::atomic<bool> ready[64];
     if (h->device < 64 && !ready[h->device].load()) {
         CU(cudaFuncSetAttribute(gemm_filter_kernel<MT, BATCH_BN, STAGES, BF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

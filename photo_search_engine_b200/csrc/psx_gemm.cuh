@@ -174,6 +174,28 @@ __device__ __forceinline__ uint64_t cand_entry(uint32_t score_bits, uint32_t row
 __device__ __forceinline__ float cand_score(uint64_t e) { return ord_to_f32((uint32_t)(e >> 32)); }
 __device__ __forceinline__ uint32_t cand_row(uint64_t e) { return (uint32_t)e; }
 
+// Survivors are staged per epilogue thread (= per query) in shared memory and appended to the query's global list in runs
+// of GEMM_STAGE_N: ONE atomicAdd -- whose reply the thread has to wait for -- per run instead of per survivor.  With ~1400
+// listed rows per query (bf16 tier) the per-survivor atomics paced the epilogue, and through it the tensor pipe
+// (78 % active; 89 % with a third of the survivors).
+constexpr int GEMM_STAGE_N = 8;
+constexpr int GEMM_STAGE_BYTES_PER_ACC = 128 * GEMM_STAGE_N * 8;  // 128 epilogue threads per accumulator tile
+struct SurvivorStage {
+    uint64_t* slot;  // this thread's GEMM_STAGE_N entries in shared memory
+    int n;
+    __device__ __forceinline__ void flush(uint64_t* list, int* count, int cap) {
+        if (n == 0) return;
+        const int pos = atomicAdd(count, n);
+        for (int i = 0; i < n; ++i)
+            if (pos + i < cap) list[pos + i] = slot[i];
+        n = 0;
+    }
+    __device__ __forceinline__ void push(uint64_t entry, uint64_t* list, int* count, int cap) {
+        slot[n++] = entry;
+        if (n == GEMM_STAGE_N) flush(list, count, cap);
+    }
+};
+
 // Sample pass: the 8 largest scores one (CTA, query) has seen, kept sorted in registers.  Only these
 // reach memory -- the thresholds need the ~16th largest score of the whole sample, and no CTA holds more
 // than 8 of the top 16 (probability < 3e-4 even with 9 CTAs; the error only lowers theta, i.e. admits more
@@ -223,6 +245,7 @@ gemm_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
     uint64_t* acc_full = empty_bar + STAGES;
     uint64_t* acc_empty = acc_full + ACC_STAGES;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + ACC_STAGES);
+    uint64_t* stage_mem = reinterpret_cast<uint64_t*>(tiles + (size_t)STAGES * STAGE_BYTES + 256);  // [MT][128][GEMM_STAGE_N]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int kblocks = (p.d + BK - 1) / BK;
@@ -340,11 +363,14 @@ gemm_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
         gemm_pdl_wait();                    // thresholds / zeroed list counters come from the kernel before
         float theta[MT];
         SampleTop top[MT];
+        SurvivorStage stage[MT];
 #pragma unroll
         for (int m = 0; m < MT; ++m) {
             const int qi = m * GEMM_M + qlane;
             theta[m] = (p.mode == GEMM_MODE_FILTER && qi < p.nq) ? p.theta[qi] : INFINITY;
             top[m].init();
+            stage[m].slot = stage_mem + ((size_t)m * GEMM_M + qlane) * GEMM_STAGE_N;
+            stage[m].n = 0;
         }
         int a = 0, tile_no = 0;
         uint32_t aph = 0;
@@ -376,10 +402,9 @@ gemm_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
                                 const int j = __ffs(hit) - 1;
                                 hit &= hit - 1;
                                 const long long row = row0 + c * 32 + j;
-                                if (row < p.n && (!p.attrs || gemm_attr_pass(__ldg(p.attrs + row), p.f))) {
-                                    const int pos = atomicAdd(p.cand_count + qi, 1);
-                                    if (pos < p.cand_cap) p.cand[(size_t)qi * p.cand_cap + pos] = cand_entry(pick32(r, j), (uint32_t)row);
-                                }
+                                if (row < p.n && (!p.attrs || gemm_attr_pass(__ldg(p.attrs + row), p.f)))
+                                    stage[m].push(cand_entry(pick32(r, j), (uint32_t)row), p.cand + (size_t)qi * p.cand_cap, p.cand_count + qi,
+                                                  p.cand_cap);
                             }
                         }
                     } else if (qi < p.nq) {
@@ -412,6 +437,12 @@ gemm_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
             for (int m = 0; m < MT; ++m) {
                 const int qi = m * GEMM_M + qlane;
                 if (qi < p.nq) top[m].store(p.sample_scores + (size_t)qi * p.sample_ld + (size_t)blockIdx.x * SAMPLE_KEEP);
+            }
+        } else {
+#pragma unroll
+            for (int m = 0; m < MT; ++m) {
+                const int qi = m * GEMM_M + qlane;
+                stage[m].flush(p.cand + (size_t)qi * p.cand_cap, p.cand_count + qi, p.cand_cap);
             }
         }
     }
@@ -502,6 +533,7 @@ gemm_filter_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
     uint64_t* acc_full = empty_bar + STAGES;
     uint64_t* acc_empty = acc_full + ACC_STAGES;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + ACC_STAGES);
+    uint64_t* stage_mem = reinterpret_cast<uint64_t*>(tiles + (size_t)STAGES * STAGE_BYTES + 256);  // [128][GEMM_STAGE_N]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t cta = cluster_ctarank();
@@ -611,6 +643,9 @@ gemm_filter_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
         const float theta = (p.mode == GEMM_MODE_FILTER && qi < p.nq) ? p.theta[qi] : INFINITY;
         SampleTop top;
         top.init();
+        SurvivorStage stage;
+        stage.slot = stage_mem + (size_t)(ew * 32 + lane) * GEMM_STAGE_N;
+        stage.n = 0;
         const uint32_t leader_acc_empty = mapa_shared(smem_u32(acc_empty), 0);
         int a = 0, tile_no = 0;
         uint32_t aph = 0;
@@ -636,10 +671,8 @@ gemm_filter_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
                             const int j = __ffs(hit) - 1;
                             hit &= hit - 1;
                             const long long row = row0 + c * 32 + j;
-                            if (row < p.n && (!p.attrs || gemm_attr_pass(__ldg(p.attrs + row), p.f))) {
-                                const int pos = atomicAdd(p.cand_count + qi, 1);
-                                if (pos < p.cand_cap) p.cand[(size_t)qi * p.cand_cap + pos] = cand_entry(pick32(r, j), (uint32_t)row);
-                            }
+                            if (row < p.n && (!p.attrs || gemm_attr_pass(__ldg(p.attrs + row), p.f)))
+                                stage.push(cand_entry(pick32(r, j), (uint32_t)row), p.cand + (size_t)qi * p.cand_cap, p.cand_count + qi, p.cand_cap);
                         }
                     }
                 } else if (qi < p.nq) {
@@ -666,6 +699,7 @@ gemm_filter_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
             }
         }
         if (p.mode == GEMM_MODE_SAMPLE && qi < p.nq) top.store(p.sample_scores + (size_t)qi * p.sample_ld + (size_t)pair * SAMPLE_KEEP);
+        if (p.mode == GEMM_MODE_FILTER) stage.flush(p.cand + (size_t)qi * p.cand_cap, p.cand_count + qi, p.cand_cap);
     }
     tc_fence_before();
     cluster_sync_all();
