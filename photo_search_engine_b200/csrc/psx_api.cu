@@ -1244,7 +1244,7 @@ static int launch_batch(psx_index* h, const float* q_dev, int nq, int k, const p
     // The kernel multiplies the coefficient by the query's own norm and the largest stored row norm (both on the device).
     (void)qnorm_max;
     const float eps_coef = bf ? 8.2e-3f : 2.2e-3f;
-    CU(launch_ex(rescore_select_kernel, (unsigned)nq, 256u, smem, st, chain, fp32_rows(h), fld, h->d, (long long)h->n, q_dev, k, kpad,
+    CU(launch_ex(rescore_select_kernel, (unsigned)nq, 512u, smem, st, chain, fp32_rows(h), fld, h->d, (long long)h->n, q_dev, k, kpad,
                  (const uint64_t*)h->bcand, (const int*)h->bcount, cand_cap, (const float*)h->btheta, eps_coef, (const float*)h->dmax_sumsq,
                  (const float*)nullptr, id_base, out_scores, out_ids, out_keys, (long long)(keys_stride > 0 ? keys_stride : kpad), flags_dev));
     g_launches++;
@@ -1284,7 +1284,7 @@ static int launch_mixed(psx_index* h, const float* q_dev, int k, const psx_filte
         CU(cudaFuncSetAttribute(rescore_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PSX_SMEM_LIMIT - 1024));
         ready[h->device].store(true);
     }
-    rescore_select_kernel<<<1, 256, smem, st>>>((const float*)h->xm, h->ldm, h->d, h->n, q_dev, k, kpad, h->bcand, h->bcount, h->bcand_cap,
+    rescore_select_kernel<<<1, 512, smem, st>>>((const float*)h->xm, h->ldm, h->d, h->n, q_dev, k, kpad, h->bcand, h->bcount, h->bcand_cap,
                                                 h->btheta, 0.f, h->dmax_sumsq, h->meps, id_base, out_scores, out_ids, out_keys, kpad, h->bflags);
     g_launches++;
     CU(cudaGetLastError());

@@ -754,14 +754,14 @@ __global__ void __launch_bounds__(512) theta_kernel(const float* __restrict__ sa
 //   2  fewer than k rows above a finite threshold;
 //   3  rows OUTSIDE the list could matter: neither  tau - 2 eps >= theta  (the band is complete inside the list)
 //      nor  k-th exact score >= theta + eps  (every unlisted row has s < theta + eps) holds.
-__global__ void __launch_bounds__(256, 3)
+__global__ void __launch_bounds__(512, 2)
 rescore_select_kernel(const float* __restrict__ x, int ld, int d, long long n, const float* __restrict__ q, int k, int kpad,
                       const uint64_t* __restrict__ cand, const int* __restrict__ cand_count, int cand_cap,
                       const float* __restrict__ theta, float eps_coef, const float* __restrict__ max_sumsq,
                       const float* __restrict__ eps_dev, uint32_t id_base,
                       float* out_scores, long long* out_ids, uint64_t* out_keys, long long keys_stride, int* flags) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    __shared__ float s_part[8];
+    __shared__ float s_part[16];
     __shared__ float s_eps;
     __shared__ int s_band;
     const int qi = blockIdx.x;
@@ -806,7 +806,7 @@ rescore_select_kernel(const float* __restrict__ x, int ld, int d, long long n, c
         if (cand_score(keys[i]) >= beta && (i + 1 == count || !(cand_score(keys[i + 1]) >= beta))) s_band = i + 1;
     __syncthreads();
     const int m = s_band;
-    // 3. exact scores of the band, two rows per warp and trip (8 independent 16-byte loads in flight per lane)
+    // 3. exact scores of the band, two rows per warp and trip (16 warps per query, two queries per SM)
     const float4* q4 = reinterpret_cast<const float4*>(sq);
     const int pieces = ld >> 2;
     for (int c = 2 * warp; c < m; c += 2 * nwarps) {
@@ -815,7 +815,7 @@ rescore_select_kernel(const float* __restrict__ x, int ld, int d, long long n, c
         const float4* x0 = reinterpret_cast<const float4*>(x + (size_t)r0 * ld);
         const float4* x1 = reinterpret_cast<const float4*>(x + (size_t)r1 * ld);
         float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f, b3 = 0.f;
-#pragma unroll 4
+#pragma unroll 2
         for (int pc = lane; pc < pieces; pc += 32) {
             const float4 v = __ldg(x0 + pc);
             const float4 u = __ldg(x1 + pc);
