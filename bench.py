@@ -1065,6 +1065,7 @@ def run_batched(torch, _native, index, rows, d, k, device, tag="batched", bf16_g
         Dfb = torch.empty((1, k), device=device)
         Ifb = torch.empty((1, k), dtype=torch.int64, device=device)
         flags_host = torch.empty((nq,), dtype=torch.int32).pin_memory()
+        flags_np = flags_host.numpy()  # a view of the pinned buffer: checking it costs a microsecond
 
         def run(complete: bool):
             index.search_batch_device(q.data_ptr(), nq, k, sc.data_ptr(), ids.data_ptr(), flags.data_ptr(), stream=stream.cuda_stream)
@@ -1073,10 +1074,13 @@ def run_batched(torch, _native, index, rows, d, k, device, tag="batched", bf16_g
                 # re-run the unproven queries on the streaming scan (what psx_search does for host callers)
                 flags_host.copy_(flags, non_blocking=True)
                 stream.synchronize()
-                for qi in flags_host.nonzero().flatten().tolist():
+                if not flags_np.any():
+                    return 0
+                bad = np.flatnonzero(flags_np).tolist()
+                for qi in bad:
                     index.search_device(q[qi: qi + 1].data_ptr(), 1, k, sc[qi: qi + 1].data_ptr(), ids[qi: qi + 1].data_ptr(), 0,
                                         stream=stream.cuda_stream)
-                return int((flags_host != 0).sum())
+                return len(bad)
             return 0
 
         for _ in range(2):
