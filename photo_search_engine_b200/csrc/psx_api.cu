@@ -122,6 +122,9 @@ struct psx_index {
     float max_norm = 0.f;         // host copy of its square root
     int batch_min = 4;        // smallest nq routed to the tensor-core path
     bool batch_pair = true;   // 129..256 queries: CTA-pair (cta_group::2) kernel instead of two accumulators per CTA
+    bool batch_fold = true;   // the threshold sample folded into the filter kernel where the shape allows (tunable "batch_fold")
+    unsigned int* gbar = nullptr;     // device: grid-barrier counter of the folded kernel (monotonic)
+    unsigned int gbar_epoch = 0;      // host: arrivals consumed by the launches so far
     bool batch_pdl = true;    // the kernels of one batch chain by programmatic dependent launch (tunable "batch_pdl")
     bool batch_bf16 = true;   // PSX_STORE_BF16_MASTER: the batched GEMM reads the bf16 rows (kind::f16) instead of the fp32 master (kind::tf32)
     float* bq = nullptr;      // [256][ld] zero-padded query block
@@ -371,6 +374,7 @@ static void free_all(psx_index* h) {
     cudaFree(h->mkeys);
     cudaFree(h->meps);
     cudaFree(h->bsample);
+    cudaFree(h->gbar);
     cudaFreeHost(h->hflags);
     cudaFreeHost(h->xstatus_host);
     for (int b = 0; b < 2; ++b) {
@@ -1136,7 +1140,13 @@ static int launch_batch(psx_index* h, const float* q_dev, int nq, int k, const p
     int tile_step = num_tiles / sample_tiles;
     if (tile_step < 1) tile_step = 1;
     sample_tiles = (num_tiles + tile_step - 1) / tile_step;
-    const int grid_s = pair ? std::min(h->sm_count / 2, sample_tiles) : std::min(h->sm_count, sample_tiles);
+    const int grid_f = pair ? std::min(h->sm_count / 2, num_tiles) : std::min(h->sm_count, num_tiles);
+    // Fold the sample into the filter kernel (CTA-pair kernel): every pair's first tile -- a full 256-row tile -- is its
+    // sample.  Possible when one tile per pair is sample enough (want_rows <= grid_f tiles) and a tile holds no more than
+    // ~1.5 rows above theta (else a pair's 8 kept scores saturate).  At k = 100 that is 160k .. 1.46M rows per GPU.
+    const bool fold = pair && h->batch_fold && !BatchTimer::enabled() && !debug_sync() && frac * 256.0 <= 1.5 &&
+                      want_rows <= (double)grid_f * 256.0 && grid_f >= 8;
+    const int grid_s = fold ? grid_f : pair ? std::min(h->sm_count / 2, sample_tiles) : std::min(h->sm_count, sample_tiles);
     const int sample_ld = grid_s * SAMPLE_KEEP;  // every sample CTA (pair) leaves its 8 best scores per query
     const int cand_cap = batch_cand_cap(T);
     int rc = ensure_batch_scratch(h, (size_t)MT * GEMM_M * sample_ld, cand_cap);
@@ -1203,30 +1213,58 @@ static int launch_batch(psx_index* h, const float* q_dev, int nq, int k, const p
                     : MT == 2 ? launch_gemm<2, false>(h, mq, mx, gp, grid, st, pdl) : launch_gemm<1, false>(h, mq, mx, gp, grid, st, pdl);
     };
     BatchTimer bt(st);
-    // pass 1: sample
-    gp.mode = GEMM_MODE_SAMPLE;
-    gp.tile_step = tile_step;
-    DBG_SYNC(st, "query staging");
-    rc = run_gemm(grid_s, false);  // behind the staging copies in plain stream order
-    if (rc) return rc;
-    DBG_SYNC(st, "gemm_filter_kernel(sample)");
-    bt.mark("sample pass");
-    // rows actually sampled: sample_cols of every visited tile (the last tile may be short)
-    long long sample_rows = 0;
-    for (int t = 0; t < num_tiles; t += tile_step)
-        sample_rows += std::max<long long>(0, std::min<long long>(sample_cols, h->n - (long long)t * BATCH_BN));
-    int rank = (int)((double)T * (double)sample_rows / (double)h->n + 0.5);
-    if (rank < 2) rank = 2;
-    CU(launch_ex(theta_kernel, (unsigned)nq, 512u, 0, st, chain, (const float*)h->bsample, sample_ld, sample_ld, rank, h->btheta, h->bcount));
-    g_launches++;
-    DBG_SYNC(st, "theta_kernel");
-    bt.mark("theta");
-    // pass 2: every tile, threshold test fused into the epilogue
-    gp.mode = GEMM_MODE_FILTER;
-    gp.tile_step = 1;
-    const int grid_f = pair ? std::min(h->sm_count / 2, num_tiles) : std::min(h->sm_count, num_tiles);
-    rc = run_gemm(grid_f, chain);
-    if (rc) return rc;
+    if (fold) {
+        // ONE kernel: sample (first tile of every pair, kept in TMEM) -> grid barrier -> thresholds -> grid barrier -> filter
+        if (!h->gbar) {
+            CU(cudaMalloc(&h->gbar, sizeof(unsigned int)));
+            CU(cudaMemsetAsync(h->gbar, 0, sizeof(unsigned int), st));
+            h->gbar_epoch = 0;
+        }
+        long long sample_rows = 0;  // the first tile of pair p under the kernel's rotation of the pair's tile sequence
+        for (int pr = 0; pr < grid_f; ++pr) {
+            const int n_mine = pr < num_tiles ? (num_tiles - pr + grid_f - 1) / grid_f : 0;
+            if (n_mine == 0) continue;
+            const int t0 = pr + grid_f * (int)((long long)pr * n_mine / grid_f);
+            sample_rows += std::max<long long>(0, std::min<long long>(BATCH_BN, h->n - (long long)t0 * BATCH_BN));
+        }
+        int rank = (int)((double)T * (double)sample_rows / (double)h->n + 0.5);
+        if (rank < 2) rank = 2;
+        gp.mode = GEMM_MODE_FILTER;
+        gp.tile_step = 1;
+        gp.fold = 1;
+        gp.theta_rank = rank;
+        gp.theta_out = h->btheta;
+        gp.gbar = h->gbar;
+        gp.gbar_base = h->gbar_epoch;
+        h->gbar_epoch += 2u * 2u * (unsigned)grid_f;  // two barriers x (2 CTAs per pair)
+        DBG_SYNC(st, "query staging");
+        rc = run_gemm(grid_f, false);  // behind the staging copies in plain stream order
+        if (rc) return rc;
+    } else {
+        // pass 1: sample
+        gp.mode = GEMM_MODE_SAMPLE;
+        gp.tile_step = tile_step;
+        DBG_SYNC(st, "query staging");
+        rc = run_gemm(grid_s, false);  // behind the staging copies in plain stream order
+        if (rc) return rc;
+        DBG_SYNC(st, "gemm_filter_kernel(sample)");
+        bt.mark("sample pass");
+        // rows actually sampled: sample_cols of every visited tile (the last tile may be short)
+        long long sample_rows = 0;
+        for (int t = 0; t < num_tiles; t += tile_step)
+            sample_rows += std::max<long long>(0, std::min<long long>(sample_cols, h->n - (long long)t * BATCH_BN));
+        int rank = (int)((double)T * (double)sample_rows / (double)h->n + 0.5);
+        if (rank < 2) rank = 2;
+        CU(launch_ex(theta_kernel, (unsigned)nq, 512u, 0, st, chain, (const float*)h->bsample, sample_ld, sample_ld, rank, h->btheta, h->bcount));
+        g_launches++;
+        DBG_SYNC(st, "theta_kernel");
+        bt.mark("theta");
+        // pass 2: every tile, threshold test fused into the epilogue
+        gp.mode = GEMM_MODE_FILTER;
+        gp.tile_step = 1;
+        rc = run_gemm(grid_f, chain);
+        if (rc) return rc;
+    }
     DBG_SYNC(st, "gemm_filter_kernel(filter)");
     bt.mark("filter pass");
     // exact re-score of the survivors + top-k + proof obligation
@@ -1829,6 +1867,8 @@ extern "C" int psx_set_tunable(psx_index* h, const char* key, int value) {
         h->filter_mode = value < 0 || value > 2 ? 0 : value;
     } else if (!strcmp(key, "batch_pair")) {
         h->batch_pair = value > 0;
+    } else if (!strcmp(key, "batch_fold")) {  // 1 = threshold sample folded into the filter kernel where possible (default), 0 = separate passes
+        h->batch_fold = value != 0;
     } else if (!strcmp(key, "batch_pdl")) {  // 1 = the kernels of a batch overlap by programmatic dependent launch (default), 0 = plain stream order
         h->batch_pdl = value != 0;
     } else if (!strcmp(key, "batch_bf16")) {  // bf16+master indexes: 1 = bf16 GEMM over the bf16 rows (default), 0 = TF32 GEMM over the master

@@ -54,6 +54,15 @@ struct GemmParams {
     float* sample_scores;    // [nq][sample_ld] (MODE_SAMPLE): SAMPLE_KEEP scores per sample CTA (pair)
     int sample_ld;
     int sample_cols;         // MODE_SAMPLE: only the first sample_cols rows of a visited tile are sampled (multiple of 32)
+    // MODE_FILTER with the threshold sample FOLDED IN (gemm_filter_pair_kernel): every CTA pair's first tile doubles as its
+    // sample tile.  Its accumulator stays in TMEM while the grid agrees on the thresholds -- sample scores to memory, grid
+    // barrier, each CTA selects theta for its share of the queries, grid barrier -- and is then read a second time, as a
+    // filter tile; the MMA warp computes the second tile meanwhile.  No sample kernel, no theta kernel, no recomputation.
+    int fold;
+    int theta_rank;          // fold: theta = the theta_rank-th largest sample score of a query
+    float* theta_out;        // fold: [nq] thresholds, written here
+    unsigned int* gbar;      // fold: grid barrier counter (monotonic; the launch owns [gbar_base, gbar_base + 2 * gridDim.x))
+    unsigned int gbar_base;
     const uint64_t* attrs;   // EXIF words [n], or nullptr: rows failing `f` are neither sampled nor kept
     psx_filter f;
 };
@@ -516,6 +525,30 @@ __device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap*
         : "memory");
 }
 
+__device__ __forceinline__ unsigned int ld_acquire_gpu_u32(const unsigned int* p) {
+    unsigned int v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ float ld_cg_f32(const float* p) {
+    float v;
+    asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
+// barrier among the 128 epilogue threads of a CTA (named barrier 1; __syncthreads would involve the TMA / MMA warps)
+__device__ __forceinline__ void epilogue_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+// One thread per CTA: arrive at the grid barrier and wait until `target` arrivals are visible.  All CTAs of the grid are
+// resident (one per SM, grid <= SM count), so the wait ends; it is bounded anyway -- false = gave up.
+__device__ __forceinline__ bool grid_barrier(unsigned int* gbar, unsigned int target) {
+    __threadfence();
+    atomicAdd(gbar, 1u);
+    for (unsigned int spin = 0; (int)(ld_acquire_gpu_u32(gbar) - target) < 0; ++spin) {
+        __nanosleep(32);
+        if (spin > (1u << 24)) return false;
+    }
+    return true;
+}
+
 template <int STAGES, bool BF>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm_filter_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_x, const GemmParams p) {
@@ -563,6 +596,12 @@ gemm_filter_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
 
     const int first = pair * p.tile_step;
     const int stride = npairs * p.tile_step;
+    // This pair's tiles: first, first + stride, ... -- n_mine of them, visited from position `rot` on (wrapping).  Folded
+    // launches rotate every pair's sequence by a different amount so that the FIRST tiles of the pairs (= the threshold
+    // sample) are spread evenly over the corpus instead of being its first rows.
+    const int n_mine = first < p.num_tiles ? (p.num_tiles - first + stride - 1) / stride : 0;
+    const int rot = p.fold && n_mine > 0 ? (int)((long long)pair * n_mine / npairs) : 0;
+    auto tile_at = [&](int j) { const int jj = j + rot; return first + stride * (jj >= n_mine ? jj - n_mine : jj); };
 
     if (warp == 0) {
         // ===== TMA producer (both CTAs; bytes land on the leader's full barrier) =====
@@ -570,8 +609,8 @@ gemm_filter_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
             int s = 0;
             uint32_t ph = 0;
             bool waited = false;
-            for (int t = first; t < p.num_tiles; t += stride) {
-                const int row0 = t * BN + (int)cta * (BN / 2);
+            for (int j = 0; j < n_mine; ++j) {
+                const int row0 = tile_at(j) * BN + (int)cta * (BN / 2);
                 for (int kb = 0; kb < kblocks; ++kb) {
                     mbar_wait(smem_u32(empty_bar + s), ph ^ 1u);
                     const uint32_t bar = smem_u32(full_bar + s);
@@ -601,7 +640,7 @@ gemm_filter_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
             int s = 0, a = 0;
             uint32_t ph = 0, aph = 0;
             bool waited = false;
-            for (int t = first; t < p.num_tiles; t += stride) {
+            for (int j = 0; j < n_mine; ++j) {
                 if (a == 1 && !waited) {  // the first accumulator is on its way: now wait for the predecessor
                     gemm_pdl_wait();
                     waited = true;
@@ -638,44 +677,50 @@ gemm_filter_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
     } else {
         // ===== epilogue (each CTA drains its own 128 TMEM lanes = its 128 queries) =====
         const int ew = warp - 4;
-        const int qi = (int)cta * GEMM_M + ew * 32 + lane;
+        const int etid = ew * 32 + lane;
+        const int qi = (int)cta * GEMM_M + etid;
         gemm_pdl_wait();  // thresholds / zeroed list counters come from the kernel before
-        const float theta = (p.mode == GEMM_MODE_FILTER && qi < p.nq) ? p.theta[qi] : INFINITY;
+        float theta = (p.mode == GEMM_MODE_FILTER && !p.fold && qi < p.nq) ? p.theta[qi] : INFINITY;
         SampleTop top;
         top.init();
         SurvivorStage stage;
-        stage.slot = stage_mem + (size_t)(ew * 32 + lane) * GEMM_STAGE_N;
+        stage.slot = stage_mem + (size_t)etid * GEMM_STAGE_N;
         stage.n = 0;
         const uint32_t leader_acc_empty = mapa_shared(smem_u32(acc_empty), 0);
-        int a = 0, tile_no = 0;
-        uint32_t aph = 0;
-        for (int t = first; t < p.num_tiles; t += stride, ++tile_no) {
-            mbar_wait(smem_u32(acc_full + a), aph);
-            tc_fence_after();
+        // one accumulator tile against the threshold (survivors -> the query's list) ...
+        auto filter_tile = [&](int t, int a) {
             const long long row0 = (long long)t * BN;
             const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(a * BN);
-            const int nblocks = p.mode == GEMM_MODE_FILTER ? BN / 32 : p.sample_cols / 32;
+#pragma unroll 1
+            for (int c = 0; c < BN / 32; ++c) {
+                uint32_t r[32];
+                tmem_ld_32x32(taddr + c * 32, r);
+                float mx = __uint_as_float(r[0]);
+#pragma unroll
+                for (int j = 1; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(r[j]));
+                if (mx >= theta) {
+                    uint32_t hit = 0;  // see gemm_filter_kernel
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) hit |= (__uint_as_float(r[j]) >= theta ? 1u : 0u) << j;
+                    while (hit) {
+                        const int j = __ffs(hit) - 1;
+                        hit &= hit - 1;
+                        const long long row = row0 + c * 32 + j;
+                        if (row < p.n && (!p.attrs || gemm_attr_pass(__ldg(p.attrs + row), p.f)))
+                            stage.push(cand_entry(pick32(r, j), (uint32_t)row), p.cand + (size_t)qi * p.cand_cap, p.cand_count + qi, p.cand_cap);
+                    }
+                }
+            }
+        };
+        // ... or into the query's running top-8 (threshold sample)
+        auto sample_tile = [&](int t, int a, int nblocks) {
+            const long long row0 = (long long)t * BN;
+            const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(a * BN);
 #pragma unroll 1
             for (int c = 0; c < nblocks; ++c) {
                 uint32_t r[32];
                 tmem_ld_32x32(taddr + c * 32, r);
-                if (p.mode == GEMM_MODE_FILTER) {
-                    float mx = __uint_as_float(r[0]);
-#pragma unroll
-                    for (int j = 1; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(r[j]));
-                    if (mx >= theta) {
-                        uint32_t hit = 0;  // see gemm_filter_kernel
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) hit |= (__uint_as_float(r[j]) >= theta ? 1u : 0u) << j;
-                        while (hit) {
-                            const int j = __ffs(hit) - 1;
-                            hit &= hit - 1;
-                            const long long row = row0 + c * 32 + j;
-                            if (row < p.n && (!p.attrs || gemm_attr_pass(__ldg(p.attrs + row), p.f)))
-                                stage.push(cand_entry(pick32(r, j), (uint32_t)row), p.cand + (size_t)qi * p.cand_cap, p.cand_count + qi, p.cand_cap);
-                        }
-                    }
-                } else if (qi < p.nq) {
+                if (qi < p.nq) {
                     float mx = __uint_as_float(r[0]);
 #pragma unroll
                     for (int j = 1; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(r[j]));
@@ -690,6 +735,65 @@ gemm_filter_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
                     }
                 }
             }
+        };
+        int a = 0;
+        uint32_t aph = 0;
+        int j0 = 0;
+        if (p.fold) {
+            // ---- the pair's first tile is its share of the threshold sample; its accumulator is kept -----------------
+            if (n_mine > 0) {
+                mbar_wait(smem_u32(acc_full + 0), 0);
+                tc_fence_after();
+                sample_tile(tile_at(0), 0, BN / 32);
+            }
+            if (qi < p.nq) top.store(p.sample_scores + (size_t)qi * p.sample_ld + (size_t)pair * SAMPLE_KEEP);
+            __shared__ int s_ok;
+            epilogue_bar();
+            if (etid == 0) s_ok = grid_barrier(p.gbar, p.gbar_base + gridDim.x) ? 1 : 0;
+            epilogue_bar();
+            // this CTA selects theta for queries blockIdx.x, blockIdx.x + gridDim.x, ...: the theta_rank-th largest of the
+            // npairs * 8 kept sample scores, by counting (a few microseconds; the MMA warp is computing the second tile)
+            float* vals = reinterpret_cast<float*>(stage_mem);
+            const int ns = npairs * SAMPLE_KEEP;
+            for (int q = blockIdx.x; q < p.nq; q += gridDim.x) {
+                for (int i = etid; i < ns; i += 128) vals[i] = ld_cg_f32(p.sample_scores + (size_t)q * p.sample_ld + i);
+                epilogue_bar();
+                for (int i = etid; i < ns; i += 128) {
+                    const float v = vals[i];
+                    int above = 0;
+                    for (int jj = 0; jj < ns; ++jj) {
+                        const float w = vals[jj];
+                        above += (w > v || (w == v && jj < i)) ? 1 : 0;
+                    }
+                    if (above == p.theta_rank - 1) p.theta_out[q] = v > -INFINITY ? v : -INFINITY;
+                }
+                if (etid == 0) {
+                    if (ns < p.theta_rank) p.theta_out[q] = -INFINITY;  // fewer samples than the rank: take everything
+                    // a failed barrier leaves the sample incomplete: overflow the list on purpose -> the query is re-run by the scan
+                    p.cand_count[q] = s_ok ? 0 : p.cand_cap + 1;
+                }
+                epilogue_bar();
+            }
+            if (etid == 0) s_ok = (grid_barrier(p.gbar, p.gbar_base + 2u * gridDim.x) && s_ok) ? 1 : 0;
+            epilogue_bar();
+            theta = (qi < p.nq && s_ok) ? ld_cg_f32(p.theta_out + qi) : INFINITY;
+            // ---- the kept accumulator again, as a filter tile ----------------------------------------------------------
+            if (n_mine > 0) {
+                filter_tile(tile_at(0), 0);
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(leader_acc_empty + 0 * 8);
+                a = 1;
+                j0 = 1;
+            }
+        }
+        for (int j = j0; j < n_mine; ++j) {
+            mbar_wait(smem_u32(acc_full + a), aph);
+            tc_fence_after();
+            if (p.mode == GEMM_MODE_FILTER)
+                filter_tile(tile_at(j), a);
+            else
+                sample_tile(tile_at(j), a, p.sample_cols / 32);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(leader_acc_empty + a * 8);
