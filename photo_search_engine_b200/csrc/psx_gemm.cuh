@@ -752,27 +752,42 @@ gemm_filter_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
             if (etid == 0) s_ok = grid_barrier(p.gbar, p.gbar_base + gridDim.x) ? 1 : 0;
             epilogue_bar();
             // this CTA selects theta for queries blockIdx.x, blockIdx.x + gridDim.x, ...: the theta_rank-th largest of the
-            // npairs * 8 kept sample scores, by counting (a few microseconds; the MMA warp is computing the second tile)
-            float* vals = reinterpret_cast<float*>(stage_mem);
+            // npairs * 8 kept sample scores, by bisection on the orderable 32-bit image of the scores (32 rounds of "how
+            // many keys are >= mid", each a register count + warp reduction + 4 partial sums: ~1.5 us per query, while the
+            // MMA warp is computing the second tile)
+            __shared__ int s_cnt[2][4];
             const int ns = npairs * SAMPLE_KEEP;
+            constexpr int PER = 8;  // keys per epilogue thread: ns <= 128 * PER (at most 128 pairs)
             for (int q = blockIdx.x; q < p.nq; q += gridDim.x) {
-                for (int i = etid; i < ns; i += 128) vals[i] = ld_cg_f32(p.sample_scores + (size_t)q * p.sample_ld + i);
-                epilogue_bar();
-                for (int i = etid; i < ns; i += 128) {
-                    const float v = vals[i];
-                    int above = 0;
-                    for (int jj = 0; jj < ns; ++jj) {
-                        const float w = vals[jj];
-                        above += (w > v || (w == v && jj < i)) ? 1 : 0;
-                    }
-                    if (above == p.theta_rank - 1) p.theta_out[q] = v > -INFINITY ? v : -INFINITY;
+                uint32_t key[PER];
+#pragma unroll
+                for (int i = 0; i < PER; ++i) {
+                    const int idx = etid + 128 * i;
+                    const float v = idx < ns ? ld_cg_f32(p.sample_scores + (size_t)q * p.sample_ld + idx) : -INFINITY;
+                    key[i] = (idx < ns && v > -INFINITY) ? f32_to_ord(v) : 0u;  // 0 = "no sample" (below every real score)
+                }
+                uint32_t lo = 0u, hi = 0xffffffffu;  // invariant: count(key >= lo) >= rank (lo = 0 counts everything)
+                for (int it = 0; it < 32 && lo < hi; ++it) {
+                    const uint32_t mid = lo + ((hi - lo) >> 1) + 1u;  // upper middle, so that lo = mid makes progress
+                    int c = 0;
+#pragma unroll
+                    for (int i = 0; i < PER; ++i) c += key[i] >= mid ? 1 : 0;
+                    c = __reduce_add_sync(0xffffffffu, c);
+                    if (lane == 0) s_cnt[it & 1][ew] = c;
+                    epilogue_bar();
+                    const int total = s_cnt[it & 1][0] + s_cnt[it & 1][1] + s_cnt[it & 1][2] + s_cnt[it & 1][3];
+                    if (total >= p.theta_rank)
+                        lo = mid;
+                    else
+                        hi = mid - 1u;
                 }
                 if (etid == 0) {
-                    if (ns < p.theta_rank) p.theta_out[q] = -INFINITY;  // fewer samples than the rank: take everything
+                    // lo = the theta_rank-th largest key; 0 when there are fewer real samples than the rank: take everything
+                    p.theta_out[q] = lo ? ord_to_f32(lo) : -INFINITY;
                     // a failed barrier leaves the sample incomplete: overflow the list on purpose -> the query is re-run by the scan
                     p.cand_count[q] = s_ok ? 0 : p.cand_cap + 1;
                 }
-                epilogue_bar();
+                epilogue_bar();  // s_cnt is reused by the next query
             }
             if (etid == 0) s_ok = (grid_barrier(p.gbar, p.gbar_base + 2u * gridDim.x) && s_ok) ? 1 : 0;
             epilogue_bar();
