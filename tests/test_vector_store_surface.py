@@ -451,3 +451,21 @@ def test_coalesced_concurrent_searches_equal_sequential(fake_backend, tmp_path, 
         shared.search(queries[0], 3)
     monkeypatch.setattr(fake_backend, "search", real)
     assert len(shared.search(queries[0], 3)) == 3
+
+
+def test_query_row_has_the_bits_of_the_reference_normalisation(fake_backend, tmp_path):
+    """search() converts the query without the list round trip of _normalize_vector (utils/vector_store.py:83-90): the
+    float32 bits handed to the backend must be the ones the reference would send, for cosine and l2, zero vectors too."""
+    from photo_search_engine_b200.vector_store import VectorStore
+
+    rng = np.random.default_rng(8)
+    for metric in ("cosine", "l2"):
+        store = VectorStore(33, str(tmp_path / f"{metric}.index"), str(tmp_path / f"{metric}.json"), metric=metric)
+        for trial in range(50):
+            v = (rng.standard_normal(33) * 10.0 ** rng.integers(-3, 4)).tolist()
+            if trial == 0:
+                v = [0.0] * 33
+            want = np.array([store._normalize_vector(v)], dtype="float32")
+            got = store._query_row(v)
+            assert got.dtype == np.float32 and got.shape == (1, 33)
+            assert got.tobytes() == want.tobytes()
