@@ -178,7 +178,7 @@ def run_reference(args):
     del probe
     by_ram = max(1 << 17, (mem_available_bytes() - (6 << 30)) // (d * 4))
     by_time = int(150.0 / max(per_row * (args.steps + max(args.warmup, 1) + 3), 1e-12))
-    sample_rows = int(max(1 << 17, min(rows, by_ram, by_time)))
+    sample_rows = int(min(rows, max(1 << 17, min(by_ram, by_time))))
     x = c_oracle.fill_unit_rows(sample_rows, d, CORPUS_SEED)
     scale = rows / sample_rows
     for i in range(args.warmup):
