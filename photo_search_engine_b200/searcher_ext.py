@@ -292,6 +292,35 @@ class _LazyCombined(Sequence):
         return self.item(i)
 
 
+class _LazyFused(Sequence):
+    """``_hybrid_search`` under ``FusedRecallMixin``: fused entries ``(score, vector_score, keyword_score, photo_path,
+    metadata)`` in result order; the reference's dicts are built on demand."""
+
+    def __init__(self, owner: Any, entries: List[tuple]) -> None:
+        self.owner, self.entries = owner, entries
+
+    def __len__(self) -> int:
+        return len(self.entries)
+
+    def item(self, i: int) -> Dict[str, Any]:
+        score, v_score, k_score, photo_path, metadata = self.entries[i]
+        return {
+            "photo_path": photo_path,
+            "description": metadata.get("description", ""),
+            "score": score,
+            "vector_score": v_score,
+            "keyword_score": k_score,
+            "rank": 0,
+            "metadata": metadata,
+            "match_summary": self.owner._psx_match_summary(metadata),
+        }
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [self.item(j) for j in range(*i.indices(len(self)))]
+        return self.item(i)
+
+
 class FusedRecallMixin:
     """Opt-in: once the scan takes a few milliseconds, a search round is dominated by
     O(candidate_k) Python -- one dict, one ``normalize_local_path``, one ``build_match_summary`` and (under a time
@@ -348,7 +377,7 @@ class FusedRecallMixin:
 
     # -- the three hooks --------------------------------------------------------------------------------------------
     def _run_single_search_round(self, **kwargs: Any):
-        fast = (self.keyword_store is None and not kwargs.get("media_terms") and not kwargs.get("identity_terms")
+        fast = (not kwargs.get("media_terms") and not kwargs.get("identity_terms")
                 and not getattr(self, "validate_file_exists", False) and hasattr(self.vector_store._store, "search_batch")
                 and not getattr(self._psx_local, "constraints", None))
         self._psx_local.lazy = bool(fast)
@@ -357,6 +386,75 @@ class FusedRecallMixin:
             return super()._run_single_search_round(**kwargs)
         finally:
             self._psx_local.lazy = False
+
+    def _hybrid_search(self, query, query_embedding, candidate_k, filters=None, allow_keyword_only_results=False, media_terms=None,
+                       identity_terms=None, strict_identity_filter=False):
+        """The Elasticsearch branch (core/searcher.py:855-988) with the per-candidate dicts deferred: the same dict / set
+        operations on the same path strings (so that even the iteration order of ``all_paths``, which breaks score ties, is
+        the reference's), the same Python-float arithmetic, the same stable sort -- but ``build_match_summary`` and the
+        result dict are produced only for the entries somebody looks at."""
+        if not getattr(self._psx_local, "lazy", False) or media_terms or identity_terms or self.keyword_store is None:
+            return super()._hybrid_search(query, query_embedding, candidate_k, filters=filters,
+                                          allow_keyword_only_results=allow_keyword_only_results, media_terms=media_terms,
+                                          identity_terms=identity_terms, strict_identity_filter=strict_identity_filter)
+        vector_results = self.vector_store.search(query_embedding, candidate_k)
+        vector_scores: Dict[str, float] = {}
+        if isinstance(vector_results, _LazyHits):
+            records = vector_results.records
+            for row, distance in zip(vector_results.ids.tolist(), vector_results.distances.tolist()):
+                metadata = records[row] or {}
+                vector_scores[metadata.get("photo_path", "")] = self._distance_to_score(float(distance))
+        else:
+            for item in vector_results:
+                metadata = item.get("metadata") or {}
+                vector_scores[metadata.get("photo_path", "")] = self._distance_to_score(float(item.get("distance", 0.0)))
+        keyword_scores: Dict[str, float] = {}
+        es_filtered_paths = None
+        keyword_candidate_k = max(1, min(candidate_k, max(self.top_k * 3, 15)))
+        es_filters = self._build_es_filters(filters) if filters else {}
+        if es_filters:
+            keyword_results = self.keyword_store.search_with_filters(query, es_filters, keyword_candidate_k)
+            es_filtered_paths = set()
+            for item in keyword_results:
+                keyword_scores[item["photo_path"]] = item["score"]
+                es_filtered_paths.add(item["photo_path"])
+        else:
+            for item in self.keyword_store.search(query, keyword_candidate_k):
+                keyword_scores[item["photo_path"]] = item["score"]
+        all_paths = set(vector_scores.keys())
+        if allow_keyword_only_results:
+            all_paths |= set(keyword_scores.keys())
+        strict = bool(filters) and self._has_strict_filters(filters)
+        entries = []  # (combined, v_score, k_score, photo_path, metadata) in the iteration order of all_paths
+        for photo_path in all_paths:
+            if es_filtered_paths is not None and photo_path not in es_filtered_paths and strict:
+                continue
+            has_vector = photo_path in vector_scores
+            has_keyword = photo_path in keyword_scores
+            v_score = vector_scores.get(photo_path, 0.0)
+            k_score = keyword_scores.get(photo_path, 0.0)
+            metadata = self._get_metadata_by_path(photo_path)
+            if metadata is None:
+                continue
+            available_weight = 0.0
+            weighted_score = 0.0
+            if has_vector:
+                available_weight += self.vector_weight
+                weighted_score += self.vector_weight * v_score
+            if has_keyword:
+                available_weight += self.keyword_weight
+                weighted_score += self.keyword_weight * k_score
+            if available_weight <= 0:
+                continue
+            combined_score = weighted_score / available_weight
+            combined_score *= 1.0  # _compute_metadata_boost without media / identity terms
+            if has_keyword and not has_vector:
+                combined_score *= 0.65
+            if has_keyword and not has_vector and es_filtered_paths is None and k_score < 0.45:
+                continue
+            entries.append((round(combined_score, 6), round(v_score, 6), round(k_score, 6), photo_path, metadata))
+        entries.sort(key=lambda e: e[0], reverse=True)  # stable, as list.sort in the reference
+        return _LazyFused(self, entries)
 
     def _vector_results_to_combined(self, raw_results):
         if not isinstance(raw_results, _LazyHits):
@@ -379,8 +477,10 @@ class FusedRecallMixin:
 
     def _finalize_results(self, combined_results, normalized_top_k, has_filter, constraints, search_text="", media_terms=None,
                           identity_terms=None, strict_identity_filter=False, relaxation_level=0, strip_internal=True):
+        if isinstance(combined_results, _LazyFused) and not media_terms and not identity_terms and self.keyword_store is not None:
+            return self._psx_finalize_fused(combined_results, normalized_top_k, relaxation_level, strip_internal)
         if not isinstance(combined_results, _LazyCombined) or media_terms or identity_terms or self.keyword_store is not None:
-            if isinstance(combined_results, _LazyCombined):
+            if isinstance(combined_results, (_LazyCombined, _LazyFused)):
                 combined_results = list(combined_results)
             return super()._finalize_results(combined_results=combined_results, normalized_top_k=normalized_top_k, has_filter=has_filter,
                                              constraints=constraints, search_text=search_text, media_terms=media_terms,
@@ -444,6 +544,75 @@ class FusedRecallMixin:
         final_results = []
         for rank, i in enumerate(chosen, start=1):
             item = view.item(i)
+            item["_confidence_bucket"] = buckets[i]
+            item["_relaxation_level"] = level
+            item["rank"] = rank
+            final_results.append(item)
+        return self._sanitize_results(final_results) if strip_internal else final_results
+
+    def _psx_path_keys(self, paths: Sequence[Any]) -> List[str]:
+        """``_path_key`` per path string, cached (path strings are few and repeat from query to query)."""
+        cache = self.__dict__.setdefault("_psx_pathkey_cache", {})
+        if len(cache) > 2_000_000:
+            cache.clear()
+        out = []
+        for path in paths:
+            key = cache.get(path)
+            if key is None:
+                key = self._path_key(path)
+                cache[path] = key
+            out.append(key)
+        return out
+
+    def _psx_finalize_fused(self, fused: "_LazyFused", normalized_top_k: int, relaxation_level: int, strip_internal: bool):
+        """``_finalize_results`` for the Elasticsearch branch (no post-filter there, core/searcher.py:1474-1481): de-duplicate
+        by path key (first occurrence stays; the list is sorted by score, so a later duplicate is never strictly better),
+        thresholds, buckets, fill -- dicts for the returned photos only."""
+        entries = fused.entries
+        keys = self._psx_path_keys([e[3] for e in entries])
+        keep, seen = [], set()
+        for i, key in enumerate(keys):
+            if not key or key in seen:
+                continue
+            seen.add(key)
+            keep.append(i)
+        scores = [entries[i][0] for i in keep]
+        strict_floor, broad_floor = self._get_round_score_floors(relaxation_level)
+        if scores:
+            dynamic_threshold = self._calculate_dynamic_threshold(scores, normalized_top_k)
+            strict_threshold = max(dynamic_threshold, strict_floor)
+            broad_threshold = min(strict_threshold - 0.05, max(broad_floor, strict_threshold * 0.84))
+            broad_threshold = round(max(broad_floor, broad_threshold), 6)
+        else:
+            strict_threshold, broad_threshold = strict_floor, broad_floor
+        buckets = [3 if s >= strict_threshold else 2 if s >= broad_threshold else 1 for s in scores]
+        reliable = [i for i, b in enumerate(buckets) if b >= 3]
+        generalized = [i for i, b in enumerate(buckets) if b == 2]
+        prioritized = reliable + generalized
+        chosen = prioritized[:normalized_top_k]
+        if len(chosen) < normalized_top_k:
+            taken = set(chosen)
+            for i in range(len(keep)):
+                if i not in taken:
+                    chosen.append(i)
+                    if len(chosen) >= normalized_top_k:
+                        break
+        prioritized_set = set(prioritized)
+        level = max(0, int(relaxation_level))
+        self._last_round_quality = {
+            "raw_count": len(keep),
+            "returned_count": len(chosen),
+            "reliable_count": len(reliable),
+            "generalized_count": len(prioritized),
+            "fallback_used_count": sum(1 for i in chosen if i not in prioritized_set),
+            "strict_threshold": round(strict_threshold, 6),
+            "broad_threshold": round(broad_threshold, 6),
+            "relaxation_level": level,
+            "top_score": round(float(scores[0]), 6) if scores else 0.0,
+        }
+        final_results = []
+        for rank, i in enumerate(chosen, start=1):
+            item = fused.item(keep[i])
             item["_confidence_bucket"] = buckets[i]
             item["_relaxation_level"] = level
             item["rank"] = rank

@@ -173,6 +173,68 @@ def prefilter_case(tmp):
     return out
 
 
+class FakeKeywordStore:
+    """What Searcher needs of utils/keyword_store.py: BM25-like hits as [{"photo_path", "score"}], scores in (0, 1]."""
+
+    def __init__(self, metas):
+        self.paths = [m["photo_path"] for m in metas if m.get("photo_path")]
+        self.by_year = {}
+        for m in metas:
+            year = (m.get("time_info") or {}).get("year")
+            if m.get("photo_path"):
+                self.by_year.setdefault(year, []).append(m["photo_path"])
+
+    def _hits(self, pool, query, k):
+        rng = np.random.default_rng(abs(hash(("kw", len(pool), k))) % (2 ** 32) if False else len(query) * 7919 + k)
+        picks = rng.permutation(len(pool))[: min(k, len(pool))]
+        scores = np.sort(rng.random(len(picks)))[::-1]
+        if len(scores):
+            scores = scores / scores[0]
+        return [{"photo_path": pool[int(i)], "score": float(round(s, 4))} for i, s in zip(picks, scores)] + \
+               [{"photo_path": "/gone/stale.jpg", "score": 0.9}]  # a stale ES document: no metadata in the local index
+
+    def search(self, query, k):
+        return self._hits(self.paths, query, k)
+
+    def search_with_filters(self, query, filters, k):
+        pool = self.by_year.get(filters.get("year"), self.paths) if isinstance(filters, dict) else self.paths
+        return self._hits(pool, query, k)
+
+
+def hybrid_case(tmp):
+    """FusedRecallMixin on the Elasticsearch branch (_hybrid_search + _finalize_results): identical rounds, fewer dicts."""
+    rng = np.random.default_rng(33)
+    n = 2500
+    rows = rng.standard_normal((n, D)).astype(np.float32)
+    metas = [{"photo_path": f"/photos/y{2010 + i % 6}/IMG_{i}.jpg" if i % 53 else f"/photos/y{2010 + (i + 1) % 6}/IMG_{i + 1}.jpg",
+              "description": f"photo {i}", "exif_data": {"datetime": f"{2010 + i % 6}-03-0{1 + i % 9}T10:00:00"},
+              "time_info": {"year": 2010 + i % 6, "month": 3, "season": "春天", "time_period": "上午",
+                            "datetime_str": f"{2010 + i % 6}-03-0{1 + i % 9}T10:00:00"}} for i in range(n)]
+    rounds = [dict(constraints={}, has_filter=False, normalized_top_k=10, relaxation_level=0),
+              dict(constraints={"year": 2013}, has_filter=True, normalized_top_k=10, relaxation_level=1),
+              dict(constraints={}, has_filter=False, normalized_top_k=40, relaxation_level=2),
+              dict(constraints={"year": 2011}, has_filter=True, normalized_top_k=3, relaxation_level=0)]
+    out = {}
+    for tag, cls in (("plain", Searcher), ("recall", RecallSearcher)):
+        store = CountingStore(D, os.path.join(tmp, tag + "_hy.index"), os.path.join(tmp, tag + "_hy.json"))
+        store.add_batch(rows, metas)
+        emb = CountingEmbedding()
+        s = cls(embedding=emb, time_parser=FakeTimeParser(), vector_store=store, keyword_store=FakeKeywordStore(metas), query_formatter=None)
+        s.index_loaded = True
+        qs = np.random.default_rng(6).standard_normal((len(rounds), D)).astype(np.float32)
+        res = []
+        for qi, kw in enumerate(rounds):
+            emb._vec = lambda text, _q=qs[qi]: _q.tolist()
+            r = s._run_single_search_round(query="海边 日落 photo", intent={"search_text": "q"}, embedding_query="q", media_terms=[],
+                                           identity_terms=[], strict_identity_filter=False, **kw)
+            res.append({"results": [[x.get("photo_path"), x.get("score"), x.get("vector_score"), x.get("keyword_score"), x.get("rank"),
+                                     x.get("_confidence_bucket"), x.get("match_summary"), x.get("description")] for x in r],
+                        "quality": s._get_last_round_quality()})
+        out[tag] = res
+        out[tag + "_stats"] = getattr(s, "psx_recall_stats", None)
+    return out
+
+
 def alt(text, terms=()):
     return {"search_text": text, "media_terms": list(terms), "identity_terms": [], "strict_identity_filter": False,
             "intent_mode": "open", "time_hint": None, "season": None, "time_period": None, "original_query": QUERY,
@@ -220,6 +282,7 @@ def main():
                         "expansion_triggered_full": bool(s._last_search_debug.get("expansion_triggered"))}
         out["prefilter_case"] = prefilter_case(tmp)
         out["recall_case"] = recall_case(tmp)
+        out["hybrid_case"] = hybrid_case(tmp)
     print("RESULT " + json.dumps(out))
 
 

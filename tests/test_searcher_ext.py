@@ -57,6 +57,15 @@ def _check(out):
     assert any(len(r["results"]) > 0 for r in rc["plain"][2:7])            # the filtered rounds do return photos
     assert rc["recall_stats"]["array_rounds"] == 24 and rc["recall_stats"]["reference_rounds"] == 1
     assert rc["ms_per_round"]["recall"] < rc["ms_per_round"]["plain"]        # and the Python tail got shorter
+    # the same on the Elasticsearch branch: vector hits + keyword hits fused (core/searcher.py:855-988), stale ES documents
+    # dropped, duplicate paths collapsed, ES filters applied -- identical results and round quality
+    hy = out["hybrid_case"]
+    assert len(hy["plain"]) == len(hy["recall"]) == 4
+    for i, (a, b) in enumerate(zip(hy["plain"], hy["recall"])):
+        assert a["results"] == b["results"] and len(a["results"]) > 0, i
+        assert a["quality"] == b["quality"], i
+    assert any(r[3] > 0 for rnd in hy["plain"] for r in rnd["results"])        # keyword scores really took part
+    assert hy["recall_stats"]["array_rounds"] == 4
 
 
 @pytest.mark.skipif(not os.path.isdir(os.path.join(REFERENCE, "core")), reason="reference checkout not present")
