@@ -257,8 +257,9 @@ int psx_storage_device(psx_index* h, const void** rows_dev, int64_t* ld_elems, i
 /* key: "warps" (consumer warps per CTA), "stages" (ring slots per warp), "ctas_per_sm"
  * (values <= 0 restore the default), "batch_min" (smallest nq routed to the tensor-core path
  * by psx_search; 0 disables it, < 0 restores the default of 4), "batch_pair" (CTA-pair GEMM kernel
- * for 129..256 queries, default 1), "filter_mode" (0 = default, 1 = EXIF predicate evaluated inside
- * the scan, 2 = predicate compacted into a row list that the scan then streams), "deal" (1 = rows
+ * for 129..256 queries, default 1), "filter_mode" (0 = default (= 3), 1 = EXIF predicate evaluated inside
+ * the scan group by group, 2 = predicate compacted into a row list by a kernel ahead of the scan, 3 = compacted into
+ * the row list by the first phase of the scan launch itself -- one launch per filtered query), "deal" (1 = rows
  * dealt to the warps as units with a dynamically scheduled tail, the default; 0 = static groups),
  * "dyn_tail" (0 = deal everything statically), "static_batch" (units per dealt batch, default 8), "pdl"
  * (programmatic dependent launch: the next scan starts streaming while the previous one sorts and merges.  0 = plain
@@ -270,8 +271,10 @@ int psx_set_tunable(psx_index* h, const char* key, int value);
 /* Diagnostics: while `trace_dev` is non-NULL every scan launch writes, per CTA, 8 uint64 into
  * trace_dev[cta*8 ..]: %globaltimer (ns) at kernel entry, prologue done, stream drained, list
  * published, lists merged (last CTA only), results emitted (last CTA only), then the number of
- * candidate-buffer compactions.  The buffer (>= 8 * SM count * ctas_per_sm words, device memory)
- * stays owned by the caller; NULL switches tracing off. */
+ * candidate-buffer compactions; a filtered launch that compacts its own row list adds a second block at
+ * trace_dev[(grid + cta)*8 ..]: first ticket known, words evaluated, list space reserved, entries written, every ticket
+ * finished.  The buffer (>= 16 * SM count * ctas_per_sm words, device memory) stays owned by the caller; NULL switches
+ * tracing off. */
 int psx_set_trace_device(psx_index* h, uint64_t* trace_dev);
 /* Number of kernels launched by this library in the calling process so far. */
 int64_t psx_launch_count(void);

@@ -90,7 +90,8 @@ struct psx_index {
 
     uint64_t* lists = nullptr;  // [grid][kpad]
     size_t lists_cap = 0;
-    unsigned int* counter = nullptr;  // [0] merge tickets, [1] / [3] dynamic-tail tickets of even / odd launches, [2] / [4] entries of the even / odd rowlist
+    unsigned int* counter = nullptr;  // [0] merge tickets, [1] / [3] dynamic-tail tickets of even / odd launches, [2] / [4] entries of the even / odd rowlist,
+                                      // [32 + slot * PSX_FUSE_WORDS ..] tickets, finished tickets, arrived CTAs of a scan that compacts the even / odd rowlist itself
     unsigned long long list_seq = 0;  // row lists written so far (alternates the two lists)
     unsigned long long scan_seq = 0;  // launches so far (alternates the dynamic-tail ticket word)
     // Programmatic dependent launch of the scans: 0 = never; 1 = the 2nd, 3rd ... scan of ONE API call overlaps its
@@ -105,7 +106,8 @@ struct psx_index {
     bool deal = true;        // unfiltered scans: dealt units with a dynamic tail (false: static predicate groups)
     bool dyn_tail = true;
     int static_batch = 8;
-    int filter_mode = 0;     // 0 = auto, 1 = predicate fused into the scan, 2 = predicate compacted into a row list first
+    int filter_mode = 0;     // 0 = auto, 1 = predicate evaluated group by group inside the scan, 2 = compacted into a row list by a kernel
+                             // before the scan, 3 = compacted into a row list by the scan's own first phase (auto)
     // device + pinned staging for the host-buffer API
     float* dq = nullptr;
     size_t dq_cap = 0;
@@ -336,8 +338,8 @@ extern "C" int psx_create(int d, int metric, int store_dtype, int device, psx_in
     auto init = [&]() -> int {
         CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
         CU(cudaEventCreateWithFlags(&h->last_ev, cudaEventDisableTiming));
-        CU(cudaMalloc(&h->counter, 8 * sizeof(unsigned int)));
-        CU(cudaMemset(h->counter, 0, 8 * sizeof(unsigned int)));
+        CU(cudaMalloc(&h->counter, (32 + 2 * PSX_FUSE_WORDS) * sizeof(unsigned int)));
+        CU(cudaMemset(h->counter, 0, (32 + 2 * PSX_FUSE_WORDS) * sizeof(unsigned int)));
         CU(cudaMalloc(&h->dmax_sumsq, sizeof(float)));
         CU(cudaMemset(h->dmax_sumsq, 0, sizeof(float)));
         return set_max_smem(merge_keys_kernel);
@@ -859,6 +861,9 @@ static int launch_scan(psx_index* h, const float* q_dev, int k, const psx_filter
     const bool overlap_ok = !cond_flag && !ceil_ptr && !h->trace;
     const bool overlap_prev = (h->pdl >= 2 || (h->pdl == 1 && !h->call_first)) && overlap_ok;
     p.list_count = h->counter + 2;
+    // the list is compacted by the scan's own first phase (one launch per query, and the whole of it may overlap the
+    // merge of the query before), or by a kernel of its own ahead of the scan
+    const bool self_listed = listed && h->filter_mode != 2;
     if (listed) {
         if (h->rowlist_cap < h->cap) {
             CU(cudaStreamSynchronize(st));
@@ -872,16 +877,24 @@ static int launch_scan(psx_index* h, const float* q_dev, int k, const psx_filter
         const int slot = (int)(h->list_seq++ & 1ull);
         uint32_t* list = h->rowlist + (size_t)slot * h->rowlist_cap;
         p.list_count = h->counter + (slot ? 4 : 2);
-        const long long chunks = (h->n + 2047) / 2048;  // 256 threads x 8 rows per trip
-        const unsigned blocks = (unsigned)std::max<long long>(1, std::min<long long>(chunks, (long long)h->sm_count * 8));
-        CU(launch_ex(filter_list_kernel, blocks, 256u, 0, st, overlap_prev, (const uint64_t*)h->attrs, (long long)h->n, *f, list, p.list_count,
-                     cond_flag));
-        g_launches++;
+        if (self_listed) {
+            p.fuse = h->counter + 32 + slot * PSX_FUSE_WORDS;
+            // about one ticket per CTA (one CTA may be late: see the kernel) while a ticket stays within 4 blocks
+            const long long blk = (long long)(plan.block / 32) * 256;
+            const long long share = (h->n + std::max(plan.grid - 1, 1) - 1) / std::max(plan.grid - 1, 1);
+            p.fuse_sub = (int)std::max<long long>(1, std::min<long long>(4, (share + blk - 1) / blk));
+        } else {
+            const long long chunks = (h->n + 2047) / 2048;  // 256 threads x 8 rows per trip
+            const unsigned blocks = (unsigned)std::max<long long>(1, std::min<long long>(chunks, (long long)h->sm_count * 8));
+            CU(launch_ex(filter_list_kernel, blocks, 256u, 0, st, overlap_prev, (const uint64_t*)h->attrs, (long long)h->n, *f, list,
+                         p.list_count, cond_flag));
+            g_launches++;
+        }
         p.rowlist = list;
     }
     p.work = h->counter + ((h->scan_seq++ & 1ull) ? 3 : 1);
     // a row-list scan always overlaps the kernel that writes its list (it waits for it before reading the list)
-    plan.pdl = listed ? (h->pdl >= 1 && overlap_ok) : overlap_prev;
+    plan.pdl = listed && !self_listed ? (h->pdl >= 1 && overlap_ok) : overlap_prev;
     h->call_first = false;
     const size_t need_lists = (size_t)plan.grid * p.kpad;
     if (need_lists > h->lists_cap) {
@@ -908,6 +921,9 @@ static int launch_scan(psx_index* h, const float* q_dev, int k, const psx_filter
     p.attrs = nullptr;
     if (filtered && !listed) {
         p.has_filter = 1;
+        p.attrs = h->attrs;
+        p.f = *f;
+    } else if (self_listed) {  // phase 1 of the launch reads the words; the streaming phase only sees the list
         p.attrs = h->attrs;
         p.f = *f;
     }
@@ -1863,8 +1879,8 @@ extern "C" int psx_set_tunable(psx_index* h, const char* key, int value) {
         h->dyn_tail = value != 0;
     } else if (!strcmp(key, "static_batch")) {
         h->static_batch = value <= 0 ? 8 : std::min(value, 32);
-    } else if (!strcmp(key, "filter_mode")) {  // 0 auto, 1 predicate inside the scan, 2 row list
-        h->filter_mode = value < 0 || value > 2 ? 0 : value;
+    } else if (!strcmp(key, "filter_mode")) {  // 0 auto (= 3), 1 predicate inside the scan, 2 row list by a kernel, 3 row list by the scan
+        h->filter_mode = value < 0 || value > 3 ? 0 : value;
     } else if (!strcmp(key, "batch_pair")) {
         h->batch_pair = value > 0;
     } else if (!strcmp(key, "batch_fold")) {  // 1 = threshold sample folded into the filter kernel where possible (default), 0 = separate passes

@@ -525,11 +525,6 @@ __device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap*
         : "memory");
 }
 
-__device__ __forceinline__ unsigned int ld_acquire_gpu_u32(const unsigned int* p) {
-    unsigned int v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
 __device__ __forceinline__ float ld_cg_f32(const float* p) {
     float v;
     asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(v) : "l"(p));

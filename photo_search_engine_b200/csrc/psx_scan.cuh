@@ -27,6 +27,8 @@
 
 namespace psx {
 
+constexpr int PSX_FUSE_TICKET = 0, PSX_FUSE_DONE = 32, PSX_FUSE_ARRIVED = 64, PSX_FUSE_WORDS = 96;
+
 struct ScanParams {
     const unsigned char* x;   // [n][row_bytes]
     const uint64_t* attrs;    // [n] or nullptr
@@ -62,6 +64,14 @@ struct ScanParams {
     unsigned int* work;         // ticket counter of the dynamically dealt tail (0 at launch, reset by the last CTA)
     int static_batch;           // units per statically dealt batch (and cap of a dynamic one)
     int dyn_tail;               // 0 = deal everything statically
+    // Row list compacted by THIS launch (no filter_list_kernel before it): phase 1 evaluates the predicate over `attrs`
+    // in 256-row chunks dealt by ticket and appends to rowlist / list_count, a counter of finished chunks is the barrier,
+    // phase 2 scans the list.  fuse[PSX_FUSE_TICKET] = tickets handed out, [PSX_FUSE_DONE] = a 64-bit word: list entries
+    // reserved (low half) and tickets finished (high half), [PSX_FUSE_ARRIVED] = CTAs arrived (all 0 at launch, reset by
+    // the last CTA; 32 words apart: one cache line each).
+    // nullptr = the list was written by the kernel before this one.
+    unsigned int* fuse;
+    int fuse_sub;               // blocks of (warps x 256) rows per ticket, 1..4
     int xchg_world, xchg_rank;
     int xchg_targets;      // receive buffers this shard publishes to: xchg_recv[0 .. xchg_targets) (all ranks when one
                            // process per GPU; only the merging device when one process drives every GPU)
@@ -100,6 +110,12 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
 // diagnostics: phase `i` of this CTA reached (entry, prologue done, stream done, list published, merged, emitted)
 __device__ __forceinline__ void trace_stamp(unsigned long long* trace, int i) {
     if (trace && threadIdx.x == 0) trace[(size_t)blockIdx.x * 8 + i] = globaltimer_ns();
+}
+
+// second block of stamps (phase 1 of a launch that compacts its own row list): ticket known, words evaluated, list space
+// reserved, entries written and fenced, every ticket finished
+__device__ __forceinline__ void trace_stamp2(unsigned long long* trace, int i) {
+    if (trace && threadIdx.x == 0) trace[(size_t)(gridDim.x + blockIdx.x) * 8 + i] = globaltimer_ns();
 }
 
 // Programmatic dependent launch.  A scan launched with programmaticStreamSerialization may become resident
@@ -325,6 +341,15 @@ __global__ void __launch_bounds__(PSX_MAX_THREADS, 1) scan_topk_kernel(const Sca
     const int W = blockDim.x >> 5;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int S = p.stages;
+    // a launch that compacts its own row list: this CTA's arrival number and first ticket, asked for now so that their
+    // round trips run under the prologue
+    uint32_t fuse_arrival = 0, fuse_ticket = 0;
+    if constexpr (MODE == PSX_SCAN_DEAL) {
+        if (p.fuse && threadIdx.x == 0) {
+            fuse_arrival = atomicAdd(p.fuse + PSX_FUSE_ARRIVED, 1u);
+            fuse_ticket = atomicAdd(p.fuse + PSX_FUSE_TICKET, 1u);
+        }
+    }
 
     unsigned char* ring = smem_raw;
     float* sq = reinterpret_cast<float*>(ring + (size_t)W * S * PSX_SLOT_BYTES);
@@ -357,8 +382,8 @@ __global__ void __launch_bounds__(PSX_MAX_THREADS, 1) scan_topk_kernel(const Sca
 
     const uint64_t ceil_key = p.ceil_ptr ? *p.ceil_ptr : ~0ull;
     const int R = p.rps, cpr = p.cpr, row_bytes = p.row_bytes;
-    const uint32_t Wt = gridDim.x * (uint32_t)W;
-    const uint32_t gw = blockIdx.x * (uint32_t)W + warp;
+    uint32_t Wt = gridDim.x * (uint32_t)W;             // warps the work is dealt to ...
+    uint32_t gw = blockIdx.x * (uint32_t)W + warp;     // ... and this warp's number among them
 
     const uint32_t ring_base = smem_u32(ring) + (uint32_t)(warp * S) * PSX_SLOT_BYTES;
     const uint32_t bar_base = smem_u32(bars + warp * S);
@@ -370,8 +395,125 @@ __global__ void __launch_bounds__(PSX_MAX_THREADS, 1) scan_topk_kernel(const Sca
     dot.load_query(q4, lane);
 
     const bool listed = MODE == PSX_SCAN_DEAL && p.rowlist != nullptr;
+    const bool self_listed = listed && p.fuse != nullptr;
     // a row-list launch follows the kernel that wrote the list: everything above overlapped it, the list is read below
-    if (listed) pdl_wait();
+    if (listed && !self_listed) pdl_wait();
+    bool late_warp = false;
+    uint32_t self_rows = 0;  // length of the list this launch compacted itself
+    if constexpr (MODE == PSX_SCAN_DEAL) {
+        if (self_listed) {
+            // ---- phase 1: the predicate as a stream compaction, by the scan's own CTAs -------------------------
+            // Tickets of W x 256 rows go to whichever CTA asks next, so the barrier below waits for RUNNING CTAs only: one
+            // that becomes resident late (its SM still merges the previous query) finds no ticket left and holds nobody up.
+            // One atomic per ticket for the ticket, one for the list space (every counter on a cache line of its own).
+            uint32_t* list = const_cast<uint32_t*>(p.rowlist);
+            uint32_t* s_f = reinterpret_cast<uint32_t*>(cand);  // [0] ticket, [1] list base, [2 + w] offset of warp w (cand is idle until the stream starts)
+            // ONE 64-bit word carries both counters: entries reserved in the list (low half) and tickets finished (high
+            // half) -- the poll that sees the last ticket finished has the length of the list in the same load
+            unsigned long long* fuse_word = reinterpret_cast<unsigned long long*>(p.fuse + PSX_FUSE_DONE);
+            // a ticket = `sub` (1..4) consecutive blocks of W x 256 rows, sized by the host so that a corpus of a few
+            // million rows is about one ticket per CTA (one round of the latency chain load -> count -> reserve -> write)
+            const uint32_t sub = (uint32_t)p.fuse_sub;
+            const uint32_t blk = (uint32_t)W << 8;
+            const uint32_t per = blk * sub;
+            const uint32_t tickets = (uint32_t)((p.n + per - 1) / per);
+            if (threadIdx.x == 0) {
+                s_f[0] = fuse_ticket;
+                s_f[1] = fuse_arrival;
+            }
+            __syncthreads();
+            uint32_t t = s_f[0];
+            const uint32_t cta_arrival = s_f[1];
+            uint32_t finished = 0;
+            __syncthreads();
+            trace_stamp2(p.trace, 0);
+            while (t < tickets) {
+                uint32_t next = 0;
+                if (threadIdx.x == 0) next = atomicAdd(p.fuse + PSX_FUSE_TICKET, 1u);
+                // lane l of warp w, block b of the ticket: row pairs t*per + b*blk + w*256 + 64 h + 2 l, h = 0..3
+                const long long t0 = (long long)t * per + ((long long)warp << 8) + 2 * lane;
+                uint32_t bits = 0;  // byte b = the 8 rows of block b
+#pragma unroll
+                for (int b2 = 0; b2 < 4; b2 += 2) {  // two blocks (8 loads of 16 bytes per lane) in flight at a time
+                    uint64_t a[16];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const int b = b2 + (j >> 2), h = j & 3;
+                        const long long r = t0 + (long long)b * blk + h * 64;
+                        a[2 * j] = a[2 * j + 1] = 0ull;
+                        if ((uint32_t)b < sub) {
+                            if (r + 1 < p.n) {
+                                const ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2*>(p.attrs + r));
+                                a[2 * j] = v.x;
+                                a[2 * j + 1] = v.y;
+                            } else if (r < p.n) {
+                                a[2 * j] = __ldg(p.attrs + r);
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const int b = b2 + (j >> 2), h = j & 3;
+                        const long long r = t0 + (long long)b * blk + h * 64;
+                        if ((uint32_t)b < sub) {
+                            if (r < p.n && attr_pass(a[2 * j], p.f)) bits |= 1u << (8 * b + 2 * h);
+                            if (r + 1 < p.n && attr_pass(a[2 * j + 1], p.f)) bits |= 2u << (8 * b + 2 * h);
+                        }
+                    }
+                }
+                const uint32_t mine = __popc(bits);
+                uint32_t incl = mine;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += v;
+                }
+                if (lane == 31) s_f[2 + warp] = incl;
+                __syncthreads();
+                if (finished == 0) trace_stamp2(p.trace, 1);
+                if (threadIdx.x == 0) {
+                    uint32_t tot = 0;
+                    for (int w = 0; w < W; ++w) {
+                        const uint32_t c = s_f[2 + w];
+                        s_f[2 + w] = tot;
+                        tot += c;
+                    }
+                    s_f[1] = tot ? (uint32_t)atomicAdd(fuse_word, (unsigned long long)tot) : 0u;
+                    s_f[0] = next;
+                }
+                __syncthreads();
+                if (finished == 0) trace_stamp2(p.trace, 2);
+                uint32_t pos = s_f[1] + s_f[2 + warp] + incl - mine;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const uint32_t r = (uint32_t)(t0 + (long long)(j >> 2) * blk + (j & 3) * 64);
+                    if (bits & (1u << (2 * j))) list[pos++] = r;
+                    if (bits & (2u << (2 * j))) list[pos++] = r + 1;
+                }
+                ++finished;
+                t = s_f[0];
+                __syncthreads();  // s_f is rewritten by the next trip
+            }
+            __threadfence();  // this thread's list entries, before the CTA reports its tickets
+            __syncthreads();
+            trace_stamp2(p.trace, 3);
+            if (threadIdx.x == 0) {
+                if (finished) atomicAdd(fuse_word, (unsigned long long)finished << 32);
+                unsigned long long v;
+                while ((uint32_t)((v = ld_acquire_gpu_u64(fuse_word)) >> 32) < tickets) __nanosleep(20);
+                s_f[0] = (uint32_t)v;
+            }
+            __syncthreads();
+            self_rows = s_f[0];
+            __syncthreads();  // (cand is handed to the stream phase)
+            trace_stamp2(p.trace, 4);
+            // ---- phase 2 deals the list to the CTAs in order of ARRIVAL, the last one excepted: that CTA (a late one, or
+            // simply the last to get going) takes no fixed share and only helps with the dynamically dealt tail
+            if (gridDim.x > 1) Wt -= (uint32_t)W;
+            gw = cta_arrival * (uint32_t)W + warp;
+            late_warp = gw >= Wt;
+        }
+    }
     bool p_exhausted = false;
     int p_chunk = 0;         // long rows: next chunk of the current row
     int in_flight = 0;
@@ -402,7 +544,7 @@ __global__ void __launch_bounds__(PSX_MAX_THREADS, 1) scan_topk_kernel(const Sca
     uint64_t attr_a = 0, attr_b = 0;  // attribute words of the next two groups (prefetched)
 
     if constexpr (MODE == PSX_SCAN_DEAL) {
-        n_rows = listed ? *p.list_count : (uint32_t)p.n;
+        n_rows = self_listed ? self_rows : listed ? __ldcg(p.list_count) : (uint32_t)p.n;
         n_units = (n_rows + (uint32_t)R - 1u) / (uint32_t)R;
         // the dynamically dealt tail: an eighth of the launch, at least 16 and at most 48 units per warp;
         // launches too small for that are dealt statically (their warps finish within one unit of each other)
@@ -416,6 +558,7 @@ __global__ void __launch_bounds__(PSX_MAX_THREADS, 1) scan_topk_kernel(const Sca
         bs = (uint32_t)p.static_batch;
         while (bs > 1 && n_static / (Wt * bs) < 8) bs >>= 1;
         s_next = gw;
+        if (late_warp) s_next = n_static;  // (bs >= 1: beyond every statically dealt batch)
     }
     auto request_grab = [&](uint32_t remaining) {  // ask for the next dynamic batch; the reply is read later
         uint32_t c = remaining / Wt;
@@ -453,13 +596,13 @@ __global__ void __launch_bounds__(PSX_MAX_THREADS, 1) scan_topk_kernel(const Sca
                     const uint64_t b = (uint64_t)pf_first + (uint64_t)j * Wt;
                     const uint64_t idx = b * per + o;
                     pf_ids = (j < pf_batches && b * bs < n_static && idx < n_rows && (b * bs + o / (uint32_t)R) < n_static)
-                                 ? __ldg(p.rowlist + idx) : 0u;
+                                 ? __ldcg(p.rowlist + idx) : 0u;
                 }
                 rid_batch = __shfl_sync(0xffffffffu, pf_ids, (pf_used * per + (uint32_t)lane) & 31u);
                 ++pf_used;
             } else {
                 const uint32_t idx = u_cur * (uint32_t)R + lane;
-                rid_batch = (lane < (u_end - u_cur) * (uint32_t)R && idx < n_rows) ? __ldg(p.rowlist + idx) : 0u;
+                rid_batch = (lane < (u_end - u_cur) * (uint32_t)R && idx < n_rows) ? __ldcg(p.rowlist + idx) : 0u;
             }
         }
         return true;
@@ -489,6 +632,7 @@ __global__ void __launch_bounds__(PSX_MAX_THREADS, 1) scan_topk_kernel(const Sca
         return true;
     };
 
+    const uint64_t row_policy = l2_policy_evict_first();
     // Fill `slot` with the next window (or the next chunk of a long row).  false = stream exhausted.
     auto produce = [&](int slot) -> bool {
         uint32_t rid = 0;  // list launches: the row this lane copies
@@ -542,7 +686,8 @@ __global__ void __launch_bounds__(PSX_MAX_THREADS, 1) scan_topk_kernel(const Sca
             if (lane == 0) mbar_arrive_expect_tx(bar, __popc(mask) * row_bytes);
             if ((mask >> lane) & 1u) my_rowids[slot * 32 + lane] = rid;
             __syncwarp();
-            if ((mask >> lane) & 1u) bulk_g2s(dst + lane * row_bytes, p.x + (size_t)rid * row_bytes, row_bytes, bar);
+            // (evict-first: the listed rows pass through L2 once, the attribute words of the next query's predicate stay)
+            if ((mask >> lane) & 1u) bulk_g2s_hint(dst + lane * row_bytes, p.x + (size_t)rid * row_bytes, row_bytes, bar, row_policy);
         } else {
             const int hi = 32 - __clz(mask);  // rows [0, hi) of the window, all passing <=> one copy
             if (mask == (hi >= 32 ? 0xffffffffu : ((1u << hi) - 1u))) {
@@ -713,6 +858,7 @@ __global__ void __launch_bounds__(PSX_MAX_THREADS, 1) scan_topk_kernel(const Sca
         if (MODE == PSX_SCAN_DEAL) {
             *p.work = 0u;
             if (listed) *p.list_count = 0u;
+            if (p.fuse) p.fuse[PSX_FUSE_TICKET] = p.fuse[PSX_FUSE_DONE] = p.fuse[PSX_FUSE_DONE + 1] = p.fuse[PSX_FUSE_ARRIVED] = 0u;
         }
     }
     if (p.xchg_world > 0) {

@@ -68,7 +68,7 @@ def test_random_case_against_oracle(seed):
     oracle = make_oracle(stored, metric=metric)
     for key, val in (("warps", int(rng.choice([2, 4, 8, 16]))), ("stages", int(rng.choice([0, 2, 3]))),
                      ("deal", int(rng.random() < 0.8)), ("dyn_tail", int(rng.random() < 0.8)),
-                     ("static_batch", int(rng.choice([0, 1, 3, 8, 32]))), ("filter_mode", int(rng.choice([0, 1, 2])))):
+                     ("static_batch", int(rng.choice([0, 1, 3, 8, 32]))), ("filter_mode", int(rng.choice([0, 1, 2, 3])))):
         ix.set_tunable(key, val)
     mask = flt = None
     if rng.random() < 0.6:

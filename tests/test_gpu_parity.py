@@ -334,7 +334,7 @@ def _random_meta(rng, n):
     return meta
 
 
-@pytest.mark.parametrize("filter_mode", [1, 2])
+@pytest.mark.parametrize("filter_mode", [1, 2, 3])
 @pytest.mark.parametrize("n,d", [(6000, 1024), (5000, 8), (3000, 4096), (4000, 200)])
 def test_fused_predicate(n, d, filter_mode):
     """Scan restricted by the packed EXIF word == oracle restricted to rows passing the restated
@@ -430,7 +430,7 @@ def test_scores_do_not_depend_on_window_shape(d, dtype):
     score_of = [dict(zip(I0[qi].tolist(), D0[qi].tolist())) for qi in range(2)]
     flt = PsxFilter(flags=F_NEED_DT | F_START | F_END, start=1, end=600)  # ~60 % pass: most windows are partial
     npass = int((words <= 600).sum())
-    for mode in (1, 2):
+    for mode in (1, 2, 3):
         ix.set_tunable("filter_mode", mode)
         D1, I1 = ix.search(q, npass, flt)
         for qi in range(2):
@@ -505,6 +505,52 @@ def test_back_to_back_scans_overlap_safely():
             for a, b in zip(res[0], res[level]):
                 assert np.array_equal(a, b), (n, d, k, level)
         assert np.array_equal(res[2][3][0], res[2][1][nq - 1])
+        ix.close()
+
+
+@pytest.mark.parametrize("filter_mode", [2, 3])
+def test_back_to_back_filtered_scans_overlap_safely(filter_mode):
+    """The same for scans under an EXIF predicate: the row list of query i+1 is compacted (by a kernel of its own, or by
+    the first phase of the scan launch) while query i still sorts and merges; predicates of very different selectivity
+    and unfiltered scans alternate launch by launch.  Results equal plain stream order bit for bit, and the oracle."""
+    import torch
+
+    from photo_search_engine_b200._native import F_END, F_NEED_DT, F_START, PsxFilter
+
+    rng = np.random.default_rng(78)
+    # (the last two cases run 4 warps per CTA: their compaction tickets span two and three 1024-row blocks)
+    for n, d, k, warps in ((40_000, 256, 50, 0), (150_000, 128, 100, 0), (5000, 1024, 100, 0), (700, 64, 10, 0), (300_000, 64, 20, 4),
+                           (400_001, 32, 20, 4)):
+        x = unit_rows(rng, n, d)
+        nq = 36
+        qh = unit_rows(rng, nq, d)
+        q = torch.from_numpy(qh).cuda()
+        ix, oracle = make_index(x), make_oracle(x)
+        ix.set_tunable("filter_mode", filter_mode)
+        ix.set_tunable("warps", warps)
+        words = rng.integers(1, 1001, n).astype(np.uint64)
+        words[rng.random(n) < 0.1] = 0  # rows without EXIF
+        ix.set_attrs(0, words)
+        ends = [800, 30, None, 200, 3, 1000]  # fraction / 1000 of the rows pass; None = no predicate
+        flts = [None if e is None else PsxFilter(flags=F_NEED_DT | F_START | F_END, start=1, end=e) for e in ends]
+        kk = min(k, n)
+        st = torch.cuda.current_stream().cuda_stream
+        res = {}
+        for pdl in (0, 2):
+            ix.set_tunable("pdl", pdl)
+            sc = torch.zeros((nq, kk), device="cuda")
+            ids = torch.zeros((nq, kk), dtype=torch.int64, device="cuda")
+            for rep in range(3):
+                for qi in range(nq):
+                    ix.search_device(q[qi: qi + 1].data_ptr(), 1, kk, sc[qi: qi + 1].data_ptr(), ids[qi: qi + 1].data_ptr(), 0,
+                                     flt=flts[qi % len(flts)], stream=st)
+            torch.cuda.synchronize()
+            res[pdl] = (sc.cpu().numpy(), ids.cpu().numpy())
+        assert np.array_equal(res[0][0], res[2][0]) and np.array_equal(res[0][1], res[2][1]), (n, d, k)
+        for qi in range(nq):
+            e = ends[qi % len(ends)]
+            mask = None if e is None else (words >= 1) & (words <= e)
+            check_against_oracle(res[2][0][qi: qi + 1], res[2][1][qi: qi + 1], oracle, qh[qi: qi + 1], kk, mask=mask)
         ix.close()
 
 

@@ -55,7 +55,9 @@ def trace_once(ix, q, k, flt=None):
     ix.search_device(q.data_ptr(), 1, k, sc.data_ptr(), ids.data_ptr(), 0, flt=flt, stream=st.cuda_stream)
     torch.cuda.synchronize()
     ix.set_trace_device(0)
-    t = buf.cpu().numpy().reshape(-1, 8)
+    both = buf.cpu().numpy().reshape(-1, 8)
+    t, ph = both[:148], both[148:296]  # the kernel's stamps; phase 1 of a launch that compacts its own row list
+    ph = ph[t[:, 0] != 0]
     t = t[t[:, 0] != 0]
     t0 = t[:, 0].min()
     rel = (t[:, :6] - t0) / 1e3
@@ -70,6 +72,9 @@ def trace_once(ix, q, k, flt=None):
         "last_cta_merged_us": round(float(rel[last, 4]), 1),
         "last_cta_emitted_us": round(float(rel[last, 5]), 1),
         "compactions[min,med,max]": pct(t[:, 6]),
+        **({"phase1_us[ticket,evaluated,reserved,written,all_done] med/max": [[round(float(np.median((ph[:, j][ph[:, j] != 0] - t0) / 1e3)), 1),
+                                                                                 round(float(((ph[:, j][ph[:, j] != 0] - t0) / 1e3).max()), 1)]
+                                                                                for j in range(5)]} if (ph[:, 4] != 0).any() else {}),
     }
 
 
@@ -107,11 +112,11 @@ def main():
                 passing = int((words <= sel).sum())
                 algo = passing * a.dim * 4 + rows * 8
                 res = {"rows": rows, "pass_frac": sel / 1000}
-                for mode in (1, 2, 1, 2):
+                for mode in (1, 2, 3, 1, 2, 3):
                     ix.set_tunable("filter_mode", mode)
                     us = timed(ix, qs, a.k, a.steps, flt)
                     res.setdefault(f"filter_mode={mode}", []).append([round(us, 1), round(algo / us / 1e3)])
-                ix.set_tunable("filter_mode", 2)
+                ix.set_tunable("filter_mode", 3)
                 res["trace_row_list_scan"] = trace_once(ix, qs[0], a.k, flt)   # phase times of the listed scan (no overlap while traced)
                 print(json.dumps(res), flush=True)
         ix.close()
