@@ -257,7 +257,7 @@ int psx_storage_device(psx_index* h, const void** rows_dev, int64_t* ld_elems, i
 /* key: "warps" (consumer warps per CTA), "stages" (ring slots per warp), "ctas_per_sm"
  * (values <= 0 restore the default), "batch_min" (smallest nq routed to the tensor-core path
  * by psx_search; 0 disables it, < 0 restores the default of 4), "batch_pair" (CTA-pair GEMM kernel
- * for 129..256 queries, default 1), "filter_mode" (0 = default (= 3), 1 = EXIF predicate evaluated inside
+ * for 129..256 queries, default 1), "filter_mode" (0 = default (3 up to 4M rows, 2 beyond), 1 = EXIF predicate evaluated inside
  * the scan group by group, 2 = predicate compacted into a row list by a kernel ahead of the scan, 3 = compacted into
  * the row list by the first phase of the scan launch itself -- one launch per filtered query), "deal" (1 = rows
  * dealt to the warps as units with a dynamically scheduled tail, the default; 0 = static groups),

@@ -107,7 +107,7 @@ struct psx_index {
     bool dyn_tail = true;
     int static_batch = 8;
     int filter_mode = 0;     // 0 = auto, 1 = predicate evaluated group by group inside the scan, 2 = compacted into a row list by a kernel
-                             // before the scan, 3 = compacted into a row list by the scan's own first phase (auto)
+                             // before the scan, 3 = compacted into a row list by the scan's own first phase (auto: 3 up to 4M rows, else 2)
     // device + pinned staging for the host-buffer API
     float* dq = nullptr;
     size_t dq_cap = 0;
@@ -863,7 +863,9 @@ static int launch_scan(psx_index* h, const float* q_dev, int k, const psx_filter
     p.list_count = h->counter + 2;
     // the list is compacted by the scan's own first phase (one launch per query, and the whole of it may overlap the
     // merge of the query before), or by a kernel of its own ahead of the scan
-    const bool self_listed = listed && h->filter_mode != 2;
+    // (auto: by the scan itself up to 4M rows -- 5-13 % faster at 1M rows, level at 10M, where the words are 80 MB and the
+    // compaction kernel's overlap with the previous query's tail is worth as much as the saved launch)
+    const bool self_listed = listed && (h->filter_mode == 3 || (h->filter_mode != 2 && h->n <= (1ll << 22)));
     if (listed) {
         if (h->rowlist_cap < h->cap) {
             CU(cudaStreamSynchronize(st));
@@ -1879,7 +1881,7 @@ extern "C" int psx_set_tunable(psx_index* h, const char* key, int value) {
         h->dyn_tail = value != 0;
     } else if (!strcmp(key, "static_batch")) {
         h->static_batch = value <= 0 ? 8 : std::min(value, 32);
-    } else if (!strcmp(key, "filter_mode")) {  // 0 auto (= 3), 1 predicate inside the scan, 2 row list by a kernel, 3 row list by the scan
+    } else if (!strcmp(key, "filter_mode")) {  // 0 auto (3 up to 4M rows, else 2), 1 predicate inside the scan, 2 row list by a kernel, 3 row list by the scan
         h->filter_mode = value < 0 || value > 3 ? 0 : value;
     } else if (!strcmp(key, "batch_pair")) {
         h->batch_pair = value > 0;

@@ -145,6 +145,46 @@ __device__ __forceinline__ bool attr_pass(uint64_t a, const psx_filter& f) {
     return true;
 }
 
+// The same predicate without data-dependent branches, for the compaction phase (16 words per lane and trip): the
+// equality constraints as one masked compare, the datetime window as one unsigned range test.  Built once per thread
+// from the (launch-uniform) filter.
+struct AttrTest {
+    uint64_t mask, want;  // ((a ^ want) & mask) == 0
+    uint64_t lo, span;    // (dt - lo) <= span  (unsigned)
+    bool none;            // the constraints contradict the encoding: nothing passes (folded into the two tests)
+};
+__device__ __forceinline__ AttrTest make_attr_test(const psx_filter& f) {
+    constexpr uint64_t DT = (1ull << 39) - 1;
+    AttrTest t{0ull, 0ull, 0ull, DT, false};
+    const uint32_t fl = f.flags;
+    if (fl & (PSX_F_SEASON | PSX_F_PERIOD | PSX_F_YEAR | PSX_F_MONTH)) {
+        t.mask |= 1ull << 63;
+        t.want |= 1ull << 63;
+        if (fl & PSX_F_SEASON) t.mask |= 7ull << 60, t.want |= (uint64_t)(f.season & 7u) << 60, t.none |= f.season > 7u;
+        if (fl & PSX_F_PERIOD) t.mask |= 7ull << 57, t.want |= (uint64_t)(f.period & 7u) << 57, t.none |= f.period > 7u;
+        if (fl & PSX_F_YEAR) t.mask |= 0x3fffull << 43, t.want |= (uint64_t)(f.year & 0x3fffu) << 43, t.none |= f.year > 0x3fffu;
+        if (fl & PSX_F_MONTH) t.mask |= 0xfull << 39, t.want |= (uint64_t)(f.month & 0xfu) << 39, t.none |= f.month > 0xfu;
+    }
+    if (fl & PSX_F_NEED_DT) {
+        uint64_t lo = 1ull, hi = DT;
+        if ((fl & PSX_F_START) && f.start > lo) lo = f.start;
+        if ((fl & PSX_F_END) && f.end < hi) hi = f.end;
+        if (lo > hi) t.none = true;
+        t.lo = lo;
+        t.span = hi - lo;
+    }
+    if (t.none) {  // an unsatisfiable pair of tests: the word would need dt = 2^39 - 1 and dt = 1 at once
+        t.mask = ~0ull;
+        t.want = ~0ull >> 1;
+        t.lo = 1ull;
+        t.span = 0ull;
+    }
+    return t;
+}
+__device__ __forceinline__ bool attr_pass_fast(uint64_t a, const AttrTest& t) {
+    return (((a ^ t.want) & t.mask) == 0ull) & (((a & ((1ull << 39) - 1)) - t.lo) <= t.span);
+}
+
 // 16 bytes of a stored row against the matching query elements, accumulated into a[0..3].
 template <typename T, int METRIC>
 __device__ __forceinline__ void piece_fma(const uint4& raw, const float4* __restrict__ q4, int piece, float (&a)[4]);
@@ -422,6 +462,7 @@ __global__ void __launch_bounds__(PSX_MAX_THREADS, 1) scan_topk_kernel(const Sca
                 s_f[1] = fuse_arrival;
             }
             __syncthreads();
+            const AttrTest at = make_attr_test(p.f);
             uint32_t t = s_f[0];
             const uint32_t cta_arrival = s_f[1];
             uint32_t finished = 0;
@@ -456,8 +497,9 @@ __global__ void __launch_bounds__(PSX_MAX_THREADS, 1) scan_topk_kernel(const Sca
                         const int b = b2 + (j >> 2), h = j & 3;
                         const long long r = t0 + (long long)b * blk + h * 64;
                         if ((uint32_t)b < sub) {
-                            if (r < p.n && attr_pass(a[2 * j], p.f)) bits |= 1u << (8 * b + 2 * h);
-                            if (r + 1 < p.n && attr_pass(a[2 * j + 1], p.f)) bits |= 2u << (8 * b + 2 * h);
+                            // (words past the end of the corpus were loaded as 0 = "no EXIF"; an unconstrained filter never gets here)
+                            bits |= (uint32_t)(r < p.n && attr_pass_fast(a[2 * j], at)) << (8 * b + 2 * h);
+                            bits |= (uint32_t)(r + 1 < p.n && attr_pass_fast(a[2 * j + 1], at)) << (8 * b + 2 * h + 1);
                         }
                     }
                 }
@@ -509,7 +551,9 @@ __global__ void __launch_bounds__(PSX_MAX_THREADS, 1) scan_topk_kernel(const Sca
             trace_stamp2(p.trace, 4);
             // ---- phase 2 deals the list to the CTAs in order of ARRIVAL, the last one excepted: that CTA (a late one, or
             // simply the last to get going) takes no fixed share and only helps with the dynamically dealt tail
-            if (gridDim.x > 1) Wt -= (uint32_t)W;
+            // (a list long enough for the dynamically dealt tail absorbs a late CTA by itself: everybody gets a share)
+            const uint32_t units = (self_rows + (uint32_t)R - 1u) / (uint32_t)R;
+            if (gridDim.x > 1 && !(p.dyn_tail && units >= 64u * Wt)) Wt -= (uint32_t)W;
             gw = cta_arrival * (uint32_t)W + warp;
             late_warp = gw >= Wt;
         }

@@ -508,6 +508,71 @@ def test_back_to_back_scans_overlap_safely():
         ix.close()
 
 
+def test_predicate_edge_encodings():
+    """The predicate has two implementations (the branching form inside the scan / the list kernel, the masked-compare
+    form of the scan's own compaction phase): every filter shape -- fields beyond their bit width, empty and open
+    windows, window flags without the datetime flag, a window past the 39-bit datetime -- selects exactly the rows a
+    numpy restatement of include/psx.h's rule selects, in every filter mode."""
+    from photo_search_engine_b200 import _native as nat
+
+    rng = np.random.default_rng(91)
+    n, d = 9000, 64
+    x = unit_rows(rng, n, d)
+    q = unit_rows(rng, 1, d)
+    ix = make_index(x)
+    dt = rng.integers(0, 5000, n).astype(np.uint64)
+    dt[rng.random(n) < 0.05] = (1 << 39) - 1
+    season, period = rng.integers(0, 8, n).astype(np.uint64), rng.integers(0, 8, n).astype(np.uint64)
+    year, month = rng.integers(2015, 2019, n).astype(np.uint64), rng.integers(0, 16, n).astype(np.uint64)
+    has = rng.random(n) < 0.8
+    words = np.where(has, (np.uint64(1) << np.uint64(63)) | (season << np.uint64(60)) | (period << np.uint64(57)) | (year << np.uint64(43))
+                     | (month << np.uint64(39)) | dt, dt * (rng.random(n) < 0.5)).astype(np.uint64)  # rows without the EXIF bit may still carry a dt
+    ix.set_attrs(0, words)
+
+    def rule(f):
+        a = words
+        ok = np.ones(n, bool)
+        if f.flags & (nat.F_SEASON | nat.F_PERIOD | nat.F_YEAR | nat.F_MONTH):
+            ok &= (a >> np.uint64(63)) == 1
+            if f.flags & nat.F_SEASON:
+                ok &= ((a >> np.uint64(60)) & np.uint64(7)) == np.uint64(f.season)
+            if f.flags & nat.F_PERIOD:
+                ok &= ((a >> np.uint64(57)) & np.uint64(7)) == np.uint64(f.period)
+            if f.flags & nat.F_YEAR:
+                ok &= ((a >> np.uint64(43)) & np.uint64(0x3FFF)) == np.uint64(f.year)
+            if f.flags & nat.F_MONTH:
+                ok &= ((a >> np.uint64(39)) & np.uint64(0xF)) == np.uint64(f.month)
+        if f.flags & nat.F_NEED_DT:
+            t = a & np.uint64((1 << 39) - 1)
+            ok &= t != 0
+            if f.flags & nat.F_START:
+                ok &= t >= np.uint64(f.start)
+            if f.flags & nat.F_END:
+                ok &= t <= np.uint64(f.end)
+        return ok
+
+    P = nat.PsxFilter
+    W = nat.F_NEED_DT | nat.F_START | nat.F_END
+    cases = [
+        P(flags=nat.F_SEASON, season=3), P(flags=nat.F_SEASON, season=9), P(flags=nat.F_PERIOD, period=8),
+        P(flags=nat.F_YEAR, year=2016), P(flags=nat.F_YEAR, year=0x4000 + 2016), P(flags=nat.F_MONTH, month=16),
+        P(flags=nat.F_MONTH | nat.F_SEASON, month=0, season=0), P(flags=nat.F_NEED_DT),
+        P(flags=W, start=0, end=100), P(flags=W, start=200, end=100), P(flags=W, start=1, end=(1 << 39) - 1),
+        P(flags=W, start=1 << 39, end=(1 << 40)), P(flags=W, start=4000, end=(1 << 45)),
+        P(flags=nat.F_NEED_DT | nat.F_START, start=4990), P(flags=nat.F_NEED_DT | nat.F_END, end=3),
+        P(flags=nat.F_START | nat.F_END, start=10, end=20),  # no datetime flag: the window is not applied
+        P(flags=nat.F_SEASON | W, season=2, start=100, end=3000), P(flags=nat.F_YEAR | nat.F_MONTH | nat.F_PERIOD, year=2017, month=5, period=2),
+    ]
+    for ci, f in enumerate(cases):
+        want = np.nonzero(rule(f))[0]
+        for mode in (1, 2, 3):
+            ix.set_tunable("filter_mode", mode)
+            D, I = ix.search(q, n, f)
+            got = I[0][I[0] >= 0]
+            assert np.array_equal(np.sort(got), want), (ci, mode, len(got), len(want))
+    ix.close()
+
+
 @pytest.mark.parametrize("filter_mode", [2, 3])
 def test_back_to_back_filtered_scans_overlap_safely(filter_mode):
     """The same for scans under an EXIF predicate: the row list of query i+1 is compacted (by a kernel of its own, or by
