@@ -339,7 +339,8 @@ def _random_meta(rng, n):
 def test_fused_predicate(n, d, filter_mode):
     """Scan restricted by the packed EXIF word == oracle restricted to rows passing the restated
     ``_check_time_match_v2`` (core/searcher.py:1884-1950).  filter_mode 1 evaluates the predicate inside
-    the scan, 2 (the default) compacts the passing rows into a list that the scan then streams."""
+    the scan, 2 compacts the passing rows into a list with a kernel ahead of the scan, 3 (the default at these sizes) lets
+    the scan launch compact the list itself."""
     from photo_search_engine_b200.exif_attrs import attr_words, build_filter
 
     rng = np.random.default_rng(n + d)
