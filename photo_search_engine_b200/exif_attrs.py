@@ -17,6 +17,7 @@ are ignored.
 from __future__ import annotations
 
 from datetime import datetime
+import re
 from typing import Any, Dict, Iterable, Optional, Tuple
 
 import numpy as np
@@ -33,6 +34,7 @@ _DT_BITS, _MONTH_SHIFT, _YEAR_SHIFT, _PERIOD_SHIFT, _SEASON_SHIFT, _EXIF_SHIFT =
 
 _WITH_TIME = ("%Y-%m-%dT%H:%M:%S", "%Y-%m-%d %H:%M:%S", "%Y:%m:%d %H:%M:%S", "%Y/%m/%d %H:%M:%S")
 _DATE_ONLY = ("%Y-%m-%d", "%Y/%m/%d", "%Y%m%d")
+_ISO_SECONDS = re.compile(r"[0-9]{4}-[0-9]{2}-[0-9]{2}T[0-9]{2}:[0-9]{2}:[0-9]{2}")
 
 
 def parse_date(value: Any, is_end_date: bool = False) -> Optional[datetime]:
@@ -41,6 +43,13 @@ def parse_date(value: Any, is_end_date: bool = False) -> Optional[datetime]:
     if not isinstance(value, str) or not value:
         return None
     text = value.strip().rstrip("\x00")
+    # what the indexer writes (datetime.isoformat(), core/indexer.py:535-582) without going through strptime: for a string
+    # of exactly this shape the first format below that can match is "%Y-%m-%dT%H:%M:%S", with these very fields
+    if len(text) == 19 and _ISO_SECONDS.fullmatch(text):
+        try:
+            return datetime(int(text[0:4]), int(text[5:7]), int(text[8:10]), int(text[11:13]), int(text[14:16]), int(text[17:19]))
+        except ValueError:
+            pass  # a field out of range: let the formats below decide (they all refuse it)
     # the reference tries its formats in a fixed order; the sets are disjoint except that the
     # order decides nothing for well-formed input, so date-only and date-time are tried apart
     for fmt in ("%Y-%m-%d",) + _WITH_TIME + _DATE_ONLY[1:]:

@@ -475,6 +475,18 @@ class FusedRecallMixin:
             kept_scores.append(self._distance_to_score(float(distance)))
         return _LazyCombined(self, raw_results.records, kept_rows, kept_scores)
 
+    def _psx_candidate_words(self, records, rows, attr_words):
+        """Packed EXIF words of the candidate rows when the store has not built its sidecar: packed once per row and
+        remembered for as long as the store keeps the same metadata list (rows are only ever appended to it)."""
+        memo = self.__dict__.get("_psx_word_memo")
+        if memo is None or memo[0] is not records:
+            memo = self._psx_word_memo = (records, {})
+        known = memo[1]
+        missing = [r for r in rows if r not in known]
+        if missing:
+            known.update(zip(missing, attr_words([records[r] or {} for r in missing]).tolist()))
+        return np.fromiter((known[r] for r in rows), dtype=np.uint64, count=len(rows))
+
     def _finalize_results(self, combined_results, normalized_top_k, has_filter, constraints, search_text="", media_terms=None,
                           identity_terms=None, strict_identity_filter=False, relaxation_level=0, strip_internal=True):
         if isinstance(combined_results, _LazyFused) and not media_terms and not identity_terms and self.keyword_store is not None:
@@ -501,7 +513,7 @@ class FusedRecallMixin:
                 if words is not None and getattr(store, "_attrs_built", 0) == len(records) and len(words) == len(records):
                     cand_words = np.asarray(words)[np.asarray(rows, dtype=np.int64)] if rows else np.zeros(0, np.uint64)
                 else:
-                    cand_words = attr_words([records[r] or {} for r in rows])
+                    cand_words = self._psx_candidate_words(records, rows, attr_words)
                 keep = words_pass(cand_words, flt).tolist()
             rows = [r for r, ok in zip(rows, keep) if ok]
             scores = [s for s, ok in zip(scores, keep) if ok]

@@ -260,6 +260,22 @@ def test_attr_words_reproduce_reference_predicate():
         assert never and not any(O.check_time_match_v2(m, c) for m in meta)
 
 
+def test_parse_date_fast_path_equals_the_format_loop():
+    """exif_attrs.parse_date short-cuts the shape the indexer writes (YYYY-MM-DDTHH:MM:SS); it must accept, refuse and
+    return exactly what the oracle's restatement of Searcher._parse_date (core/searcher.py:1963-2001) does."""
+    from photo_search_engine_b200.exif_attrs import parse_date
+
+    texts = ["2023-07-01T14:00:00", "0001-01-01T00:00:00", "9999-12-31T23:59:59", "2024-02-29T23:59:59", "2023-02-29T00:00:00",
+             "2023-13-01T00:00:00", "2023-00-10T00:00:00", "2023-06-31T12:00:00", "2023-06-15T24:00:00", "2023-06-15T23:60:00",
+             "2023-06-15T23:59:60", "2023-06-15T23:59:61", "0000-01-01T00:00:00", " 2023-07-01T14:00:00 ", "2023-07-01T14:00:00\x00\x00",
+             "2023-07-01 14:00:00", "2023:07:01 14:00:00", "2023/07/01 14:00:00", "2023-07-01", "2023/07/01", "20230701",
+             "2023-7-1T4:5:6", "2023-07-01T14:00", "2023-07-01T14:00:00.250", "2023-07-01T14:00:00+08:00", "２０２３-07-01T14:00:00",
+             "2023-07-01t14:00:00", "2023-07-01T14-00-00", "", "garbage", None, 20230701]
+    for text in texts:
+        for is_end in (False, True):
+            assert parse_date(text, is_end) == O.parse_date(text, is_end), (text, is_end)
+
+
 def test_filtered_search_equals_reference_post_filter_superset(VS, tmp_path):
     ix, _ = O.read_index(os.path.join(GOLDEN, "real77.index"))
     x = ix._matrix()
