@@ -373,6 +373,132 @@ struct RowDot {
 #define PSX_SCAN_DEAL 0
 #define PSX_SCAN_GROUPS 1
 
+// Phase 1 of a launch that compacts its own row list (ScanParams::fuse).  Kept out of line: the streaming loop of
+// scan_topk_kernel is compiled exactly as it is without this phase.  Block-wide; returns the length of the list, and the
+// order in which this CTA arrived (high half of the result).  `scratch` = a few words of shared memory that are idle until the stream starts.
+struct CompactArgs {  // the few launch parameters the phase reads (by value: the kernel's parameter block stays in the constant bank)
+    const uint64_t* attrs;
+    long long n;
+    psx_filter f;
+    const uint32_t* rowlist;
+    unsigned int* fuse;
+    int fuse_sub;
+    unsigned long long* trace;
+};
+static __device__ __noinline__ unsigned long long compact_own_list(const CompactArgs p, uint32_t* scratch, uint32_t fuse_ticket,
+                                                                   uint32_t fuse_arrival) {
+    const int W = blockDim.x >> 5;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // ---- phase 1: the predicate as a stream compaction, by the scan's own CTAs -------------------------
+    // Tickets of W x 256 rows go to whichever CTA asks next, so the barrier below waits for RUNNING CTAs only: one
+    // that becomes resident late (its SM still merges the previous query) finds no ticket left and holds nobody up.
+    // One atomic per ticket for the ticket, one for the list space (every counter on a cache line of its own).
+    uint32_t* list = const_cast<uint32_t*>(p.rowlist);
+    uint32_t* s_f = scratch;  // [0] ticket, [1] list base, [2 + w] offset of warp w (cand is idle until the stream starts)
+    // ONE 64-bit word carries both counters: entries reserved in the list (low half) and tickets finished (high
+    // half) -- the poll that sees the last ticket finished has the length of the list in the same load
+    unsigned long long* fuse_word = reinterpret_cast<unsigned long long*>(p.fuse + PSX_FUSE_DONE);
+    // a ticket = `sub` (1..4) consecutive blocks of W x 256 rows, sized by the host so that a corpus of a few
+    // million rows is about one ticket per CTA (one round of the latency chain load -> count -> reserve -> write)
+    const uint32_t sub = (uint32_t)p.fuse_sub;
+    const uint32_t blk = (uint32_t)W << 8;
+    const uint32_t per = blk * sub;
+    const uint32_t tickets = (uint32_t)((p.n + per - 1) / per);
+    if (threadIdx.x == 0) {
+        s_f[0] = fuse_ticket;
+        s_f[1] = fuse_arrival;
+    }
+    __syncthreads();
+    const AttrTest at = make_attr_test(p.f);
+    uint32_t t = s_f[0];
+    const uint32_t cta_arrival = s_f[1];
+    uint32_t finished = 0;
+    __syncthreads();
+    trace_stamp2(p.trace, 0);
+    while (t < tickets) {
+        uint32_t next = 0;
+        if (threadIdx.x == 0) next = atomicAdd(p.fuse + PSX_FUSE_TICKET, 1u);
+        // lane l of warp w, block b of the ticket: row pairs t*per + b*blk + w*256 + 64 h + 2 l, h = 0..3
+        const long long t0 = (long long)t * per + ((long long)warp << 8) + 2 * lane;
+        uint32_t bits = 0;  // byte b = the 8 rows of block b
+#pragma unroll
+        for (int b2 = 0; b2 < 4; b2 += 2) {  // two blocks (8 loads of 16 bytes per lane) in flight at a time
+            uint64_t a[16];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int b = b2 + (j >> 2), h = j & 3;
+                const long long r = t0 + (long long)b * blk + h * 64;
+                a[2 * j] = a[2 * j + 1] = 0ull;
+                if ((uint32_t)b < sub) {
+                    if (r + 1 < p.n) {
+                        const ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2*>(p.attrs + r));
+                        a[2 * j] = v.x;
+                        a[2 * j + 1] = v.y;
+                    } else if (r < p.n) {
+                        a[2 * j] = __ldg(p.attrs + r);
+                    }
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int b = b2 + (j >> 2), h = j & 3;
+                const long long r = t0 + (long long)b * blk + h * 64;
+                if ((uint32_t)b < sub) {
+                    // (words past the end of the corpus were loaded as 0 = "no EXIF"; an unconstrained filter never gets here)
+                    bits |= (uint32_t)(r < p.n && attr_pass_fast(a[2 * j], at)) << (8 * b + 2 * h);
+                    bits |= (uint32_t)(r + 1 < p.n && attr_pass_fast(a[2 * j + 1], at)) << (8 * b + 2 * h + 1);
+                }
+            }
+        }
+        const uint32_t mine = __popc(bits);
+        uint32_t incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        if (lane == 31) s_f[2 + warp] = incl;
+        __syncthreads();
+        if (finished == 0) trace_stamp2(p.trace, 1);
+        if (threadIdx.x == 0) {
+            uint32_t tot = 0;
+            for (int w = 0; w < W; ++w) {
+                const uint32_t c = s_f[2 + w];
+                s_f[2 + w] = tot;
+                tot += c;
+            }
+            s_f[1] = tot ? (uint32_t)atomicAdd(fuse_word, (unsigned long long)tot) : 0u;
+            s_f[0] = next;
+        }
+        __syncthreads();
+        if (finished == 0) trace_stamp2(p.trace, 2);
+        uint32_t pos = s_f[1] + s_f[2 + warp] + incl - mine;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const uint32_t r = (uint32_t)(t0 + (long long)(j >> 2) * blk + (j & 3) * 64);
+            if (bits & (1u << (2 * j))) list[pos++] = r;
+            if (bits & (2u << (2 * j))) list[pos++] = r + 1;
+        }
+        ++finished;
+        t = s_f[0];
+        __syncthreads();  // s_f is rewritten by the next trip
+    }
+    __threadfence();  // this thread's list entries, before the CTA reports its tickets
+    __syncthreads();
+    trace_stamp2(p.trace, 3);
+    if (threadIdx.x == 0) {
+        if (finished) atomicAdd(fuse_word, (unsigned long long)finished << 32);
+        unsigned long long v;
+        while ((uint32_t)((v = ld_acquire_gpu_u64(fuse_word)) >> 32) < tickets) __nanosleep(20);
+        s_f[0] = (uint32_t)v;
+    }
+    __syncthreads();
+    const uint32_t self_rows = s_f[0];
+    __syncthreads();  // (cand is handed to the stream phase)
+    trace_stamp2(p.trace, 4);
+    return ((unsigned long long)cta_arrival << 32) | self_rows;
+}
+
 template <typename T, int METRIC, int PPL, bool QREG, int MODE>
 __global__ void __launch_bounds__(PSX_MAX_THREADS, 1) scan_topk_kernel(const ScanParams p) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -432,123 +558,19 @@ __global__ void __launch_bounds__(PSX_MAX_THREADS, 1) scan_topk_kernel(const Sca
     uint32_t* my_rowids = rowids + (size_t)warp * S * 32;
     const float4* q4 = reinterpret_cast<const float4*>(sq);
     RowDot<T, METRIC, PPL, QREG> dot;
-    dot.load_query(q4, lane);
 
     const bool listed = MODE == PSX_SCAN_DEAL && p.rowlist != nullptr;
     const bool self_listed = listed && p.fuse != nullptr;
     // a row-list launch follows the kernel that wrote the list: everything above overlapped it, the list is read below
     if (listed && !self_listed) pdl_wait();
     bool late_warp = false;
-    uint32_t self_rows = 0;  // length of the list this launch compacted itself
+    uint32_t self_rows = 0, cta_arrival = 0;  // length of the list this launch compacted itself; this CTA's arrival number
     if constexpr (MODE == PSX_SCAN_DEAL) {
         if (self_listed) {
-            // ---- phase 1: the predicate as a stream compaction, by the scan's own CTAs -------------------------
-            // Tickets of W x 256 rows go to whichever CTA asks next, so the barrier below waits for RUNNING CTAs only: one
-            // that becomes resident late (its SM still merges the previous query) finds no ticket left and holds nobody up.
-            // One atomic per ticket for the ticket, one for the list space (every counter on a cache line of its own).
-            uint32_t* list = const_cast<uint32_t*>(p.rowlist);
-            uint32_t* s_f = reinterpret_cast<uint32_t*>(cand);  // [0] ticket, [1] list base, [2 + w] offset of warp w (cand is idle until the stream starts)
-            // ONE 64-bit word carries both counters: entries reserved in the list (low half) and tickets finished (high
-            // half) -- the poll that sees the last ticket finished has the length of the list in the same load
-            unsigned long long* fuse_word = reinterpret_cast<unsigned long long*>(p.fuse + PSX_FUSE_DONE);
-            // a ticket = `sub` (1..4) consecutive blocks of W x 256 rows, sized by the host so that a corpus of a few
-            // million rows is about one ticket per CTA (one round of the latency chain load -> count -> reserve -> write)
-            const uint32_t sub = (uint32_t)p.fuse_sub;
-            const uint32_t blk = (uint32_t)W << 8;
-            const uint32_t per = blk * sub;
-            const uint32_t tickets = (uint32_t)((p.n + per - 1) / per);
-            if (threadIdx.x == 0) {
-                s_f[0] = fuse_ticket;
-                s_f[1] = fuse_arrival;
-            }
-            __syncthreads();
-            const AttrTest at = make_attr_test(p.f);
-            uint32_t t = s_f[0];
-            const uint32_t cta_arrival = s_f[1];
-            uint32_t finished = 0;
-            __syncthreads();
-            trace_stamp2(p.trace, 0);
-            while (t < tickets) {
-                uint32_t next = 0;
-                if (threadIdx.x == 0) next = atomicAdd(p.fuse + PSX_FUSE_TICKET, 1u);
-                // lane l of warp w, block b of the ticket: row pairs t*per + b*blk + w*256 + 64 h + 2 l, h = 0..3
-                const long long t0 = (long long)t * per + ((long long)warp << 8) + 2 * lane;
-                uint32_t bits = 0;  // byte b = the 8 rows of block b
-#pragma unroll
-                for (int b2 = 0; b2 < 4; b2 += 2) {  // two blocks (8 loads of 16 bytes per lane) in flight at a time
-                    uint64_t a[16];
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const int b = b2 + (j >> 2), h = j & 3;
-                        const long long r = t0 + (long long)b * blk + h * 64;
-                        a[2 * j] = a[2 * j + 1] = 0ull;
-                        if ((uint32_t)b < sub) {
-                            if (r + 1 < p.n) {
-                                const ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2*>(p.attrs + r));
-                                a[2 * j] = v.x;
-                                a[2 * j + 1] = v.y;
-                            } else if (r < p.n) {
-                                a[2 * j] = __ldg(p.attrs + r);
-                            }
-                        }
-                    }
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const int b = b2 + (j >> 2), h = j & 3;
-                        const long long r = t0 + (long long)b * blk + h * 64;
-                        if ((uint32_t)b < sub) {
-                            // (words past the end of the corpus were loaded as 0 = "no EXIF"; an unconstrained filter never gets here)
-                            bits |= (uint32_t)(r < p.n && attr_pass_fast(a[2 * j], at)) << (8 * b + 2 * h);
-                            bits |= (uint32_t)(r + 1 < p.n && attr_pass_fast(a[2 * j + 1], at)) << (8 * b + 2 * h + 1);
-                        }
-                    }
-                }
-                const uint32_t mine = __popc(bits);
-                uint32_t incl = mine;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
-                    if (lane >= o) incl += v;
-                }
-                if (lane == 31) s_f[2 + warp] = incl;
-                __syncthreads();
-                if (finished == 0) trace_stamp2(p.trace, 1);
-                if (threadIdx.x == 0) {
-                    uint32_t tot = 0;
-                    for (int w = 0; w < W; ++w) {
-                        const uint32_t c = s_f[2 + w];
-                        s_f[2 + w] = tot;
-                        tot += c;
-                    }
-                    s_f[1] = tot ? (uint32_t)atomicAdd(fuse_word, (unsigned long long)tot) : 0u;
-                    s_f[0] = next;
-                }
-                __syncthreads();
-                if (finished == 0) trace_stamp2(p.trace, 2);
-                uint32_t pos = s_f[1] + s_f[2 + warp] + incl - mine;
-#pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const uint32_t r = (uint32_t)(t0 + (long long)(j >> 2) * blk + (j & 3) * 64);
-                    if (bits & (1u << (2 * j))) list[pos++] = r;
-                    if (bits & (2u << (2 * j))) list[pos++] = r + 1;
-                }
-                ++finished;
-                t = s_f[0];
-                __syncthreads();  // s_f is rewritten by the next trip
-            }
-            __threadfence();  // this thread's list entries, before the CTA reports its tickets
-            __syncthreads();
-            trace_stamp2(p.trace, 3);
-            if (threadIdx.x == 0) {
-                if (finished) atomicAdd(fuse_word, (unsigned long long)finished << 32);
-                unsigned long long v;
-                while ((uint32_t)((v = ld_acquire_gpu_u64(fuse_word)) >> 32) < tickets) __nanosleep(20);
-                s_f[0] = (uint32_t)v;
-            }
-            __syncthreads();
-            self_rows = s_f[0];
-            __syncthreads();  // (cand is handed to the stream phase)
-            trace_stamp2(p.trace, 4);
+            const CompactArgs ca{p.attrs, p.n, p.f, p.rowlist, p.fuse, p.fuse_sub, p.trace};
+            const unsigned long long packed = compact_own_list(ca, reinterpret_cast<uint32_t*>(cand), fuse_ticket, fuse_arrival);
+            self_rows = (uint32_t)packed;
+            cta_arrival = (uint32_t)(packed >> 32);
             // ---- phase 2 deals the list to the CTAs in order of ARRIVAL, the last one excepted: that CTA (a late one, or
             // simply the last to get going) takes no fixed share and only helps with the dynamically dealt tail
             // (a list long enough for the dynamically dealt tail absorbs a late CTA by itself: everybody gets a share)
@@ -558,6 +580,7 @@ __global__ void __launch_bounds__(PSX_MAX_THREADS, 1) scan_topk_kernel(const Sca
             late_warp = gw >= Wt;
         }
     }
+    dot.load_query(q4, lane);
     bool p_exhausted = false;
     int p_chunk = 0;         // long rows: next chunk of the current row
     int in_flight = 0;
@@ -676,7 +699,6 @@ __global__ void __launch_bounds__(PSX_MAX_THREADS, 1) scan_topk_kernel(const Sca
         return true;
     };
 
-    const uint64_t row_policy = l2_policy_evict_first();
     // Fill `slot` with the next window (or the next chunk of a long row).  false = stream exhausted.
     auto produce = [&](int slot) -> bool {
         uint32_t rid = 0;  // list launches: the row this lane copies
@@ -731,7 +753,7 @@ __global__ void __launch_bounds__(PSX_MAX_THREADS, 1) scan_topk_kernel(const Sca
             if ((mask >> lane) & 1u) my_rowids[slot * 32 + lane] = rid;
             __syncwarp();
             // (evict-first: the listed rows pass through L2 once, the attribute words of the next query's predicate stay)
-            if ((mask >> lane) & 1u) bulk_g2s_hint(dst + lane * row_bytes, p.x + (size_t)rid * row_bytes, row_bytes, bar, row_policy);
+            if ((mask >> lane) & 1u) bulk_g2s_hint(dst + lane * row_bytes, p.x + (size_t)rid * row_bytes, row_bytes, bar, l2_policy_evict_first());
         } else {
             const int hi = 32 - __clz(mask);  // rows [0, hi) of the window, all passing <=> one copy
             if (mask == (hi >= 32 ? 0xffffffffu : ((1u << hi) - 1u))) {
