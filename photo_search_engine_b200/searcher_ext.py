@@ -333,10 +333,10 @@ class FusedRecallMixin:
     Results are identical to the unmodified Searcher: scores come from its own ``_distance_to_score``, the thresholds
     from its own ``_calculate_dynamic_threshold`` / ``_get_round_score_floors``, path keys from its own ``_path_key``
     (cached per row), the time filter from the packed EXIF words the fused predicate uses (same conjunction as
-    ``_check_time_match_v2``; constraints that cannot be packed go through the reference function).  Only the pure
-    vector branch without media / identity terms takes the array path; every other case (Elasticsearch hybrid rounds,
-    term matching, file-existence validation) runs the reference code on lazily materialised dicts.  Combine with the
-    other mixins by listing this one first.
+    ``_check_time_match_v2``; constraints that cannot be packed go through the reference function).  Rounds without
+    media / identity terms take the array path (with a keyword store: ``_hybrid_search`` below joins on tuples); every
+    other case (term matching, file-existence validation) runs the reference code on lazily materialised dicts.
+    Combine with the other mixins by listing this one first.
     """
 
     def __init__(self, *args: Any, **kwargs: Any) -> None:
@@ -347,6 +347,7 @@ class FusedRecallMixin:
             self.vector_store = _PrefetchingStore(self.vector_store, self._psx_local)
         self._psx_key_cache: Dict[int, str] = {}
         self._psx_key_owner: Any = None
+        self._psx_vector_scores_ok: Optional[bool] = None  # None = not probed yet
         self.psx_recall_stats = {"array_rounds": 0, "reference_rounds": 0}
 
     # -- helpers ---------------------------------------------------------------------------------------------------
@@ -375,6 +376,38 @@ class FusedRecallMixin:
             out.append(key)
         return out
 
+    @staticmethod
+    def _psx_cosine_scores(distances: np.ndarray) -> List[float]:
+        """``_distance_to_score`` of the cosine metric (core/searcher.py:611-620) over an array: the same IEEE double
+        operations in the same order (``min`` / ``max`` as Python evaluates them, NaN included), Python's own ``round``."""
+        d = distances.astype(np.float64)
+        sim = np.where(d < 1.0, d, 1.0)            # min(1.0, distance)
+        sim = np.where(sim > -1.0, sim, -1.0)      # max(-1.0, .)
+        score = (sim + 1.0) / 2.0
+        score = np.where(score > 0.7, 0.7 + (score - 0.7) * 1.3, np.where(score < 0.3, score * 0.8, score))
+        score = np.where(score < 1.0, score, 1.0)  # min(1.0, score)
+        score = np.where(score > 0.0, score, 0.0)  # max(0.0, .)
+        return [round(v, 6) for v in score.tolist()]
+
+    def _psx_scores(self, distances: np.ndarray) -> List[float]:
+        """Scores of a whole candidate list.  The array form is used only while it reproduces THIS Searcher's own
+        ``_distance_to_score`` bit for bit on a probe of 4k distances (checked once per instance: an overridden or changed
+        method simply keeps being called candidate by candidate)."""
+        ok = self._psx_vector_scores_ok
+        if ok is None:
+            ok = False
+            if getattr(self, "metric", None) == "cosine":
+                probe = np.concatenate([np.linspace(-1.25, 1.25, 4001), np.array([0.4, -0.4, 1.0, -1.0, 0.0, np.nan, np.inf, -np.inf]),
+                                        np.nextafter(np.float32(0.4), np.float32(1), dtype=np.float32).reshape(1)]).astype(np.float32)
+                try:
+                    ok = self._psx_cosine_scores(probe) == [self._distance_to_score(float(v)) for v in probe.tolist()]
+                except Exception:
+                    ok = False
+            self._psx_vector_scores_ok = ok
+        if ok:
+            return self._psx_cosine_scores(distances)
+        return [self._distance_to_score(float(v)) for v in distances.tolist()]
+
     # -- the three hooks --------------------------------------------------------------------------------------------
     def _run_single_search_round(self, **kwargs: Any):
         fast = (not kwargs.get("media_terms") and not kwargs.get("identity_terms")
@@ -401,9 +434,9 @@ class FusedRecallMixin:
         vector_scores: Dict[str, float] = {}
         if isinstance(vector_results, _LazyHits):
             records = vector_results.records
-            for row, distance in zip(vector_results.ids.tolist(), vector_results.distances.tolist()):
+            for row, score in zip(vector_results.ids.tolist(), self._psx_scores(vector_results.distances)):
                 metadata = records[row] or {}
-                vector_scores[metadata.get("photo_path", "")] = self._distance_to_score(float(distance))
+                vector_scores[metadata.get("photo_path", "")] = score
         else:
             for item in vector_results:
                 metadata = item.get("metadata") or {}
@@ -462,17 +495,18 @@ class FusedRecallMixin:
         store = self.vector_store._store
         rows = raw_results.ids.tolist()
         keys = self._psx_row_keys(store, rows)
+        scores = self._psx_scores(raw_results.distances)
         kept_rows: List[int] = []
         kept_scores: List[float] = []
         seen = set()
-        for row, distance, key in zip(rows, raw_results.distances.tolist(), keys):
+        for row, score, key in zip(rows, scores, keys):
             # the reference drops hits without a usable path, then keeps the first hit per path key: hits arrive best
             # first and _distance_to_score is monotone, so a later duplicate never has a strictly higher score
             if not key or key in seen:
                 continue
             seen.add(key)
             kept_rows.append(row)
-            kept_scores.append(self._distance_to_score(float(distance)))
+            kept_scores.append(score)
         return _LazyCombined(self, raw_results.records, kept_rows, kept_scores)
 
     def _psx_candidate_words(self, records, rows, attr_words):

@@ -134,6 +134,29 @@ def recall_case(tmp):
         out[tag] = res
         out[tag + "_stats"] = getattr(s, "psx_recall_stats", None)
     out["ms_per_round"] = timing
+    out["vector_scores"] = s._psx_vector_scores_ok  # the array form of _distance_to_score passed its probe
+
+    # a Searcher whose _distance_to_score is not the reference's: the probe fails, the method keeps being called, results agree
+    class OddScore(Searcher):
+        def _distance_to_score(self, distance):
+            return round(max(0.0, min(1.0, 0.5 + 0.25 * distance)), 6)
+
+    class OddRecall(FusedRecallMixin, OddScore):
+        pass
+
+    odd = {}
+    for tag, cls in (("plain", OddScore), ("recall", OddRecall)):
+        store = CountingStore(D, os.path.join(tmp, tag + "_odd.index"), os.path.join(tmp, tag + "_odd.json"))
+        store.add_batch(rows, metas)
+        emb = CountingEmbedding()
+        emb._vec = lambda text, _q=qs[1]: _q.tolist()
+        s = cls(embedding=emb, time_parser=FakeTimeParser(), vector_store=store, keyword_store=None, query_formatter=None)
+        s.index_loaded = True
+        r = s._run_single_search_round(query="q", intent={"search_text": "q"}, embedding_query="q", media_terms=[], identity_terms=[],
+                                       strict_identity_filter=False, constraints={}, has_filter=False, normalized_top_k=10)
+        odd[tag] = [[x.get("photo_path"), x.get("score"), x.get("rank"), x.get("_confidence_bucket")] for x in r]
+        odd[tag + "_vector_scores"] = getattr(s, "_psx_vector_scores_ok", None)
+    out["odd"] = odd
     return out
 
 

@@ -57,6 +57,8 @@ def _check(out):
     assert any(len(r["results"]) > 0 for r in rc["plain"][2:7])            # the filtered rounds do return photos
     assert rc["recall_stats"]["array_rounds"] == 24 and rc["recall_stats"]["reference_rounds"] == 1
     assert rc["ms_per_round"]["recall"] < rc["ms_per_round"]["plain"]        # and the Python tail got shorter
+    assert rc["vector_scores"] is True                                       # scores computed as one array, bit-identical (probe)
+    assert rc["odd"]["recall_vector_scores"] is False and rc["odd"]["plain"] == rc["odd"]["recall"] and len(rc["odd"]["plain"]) > 0
     # the same on the Elasticsearch branch: vector hits + keyword hits fused (core/searcher.py:855-988), stale ES documents
     # dropped, duplicate paths collapsed, ES filters applied -- identical results and round quality
     hy = out["hybrid_case"]

@@ -260,6 +260,19 @@ def test_attr_words_reproduce_reference_predicate():
         assert never and not any(O.check_time_match_v2(m, c) for m in meta)
 
 
+def test_array_form_of_distance_to_score_is_bit_identical():
+    """FusedRecallMixin computes a candidate list's scores as one array; every value equals the oracle's restatement of
+    Searcher._distance_to_score (core/searcher.py:605-625) on 200k fp32 distances, the kinks, the clamps and NaN / inf."""
+    from photo_search_engine_b200.searcher_ext import FusedRecallMixin
+
+    rng = np.random.default_rng(17)
+    d = np.concatenate([rng.uniform(-1.3, 1.3, 200_000), [0.4, -0.4, 1.0, -1.0, 0.0, -0.0, np.nan, np.inf, -np.inf],
+                        np.nextafter(np.float32([0.4, 0.4, -0.4, -0.4]), np.float32([1, -1, 1, -1]))]).astype(np.float32)
+    got = FusedRecallMixin._psx_cosine_scores(d)
+    want = [O.distance_to_score(float(v), "cosine") for v in d.tolist()]
+    assert got == want
+
+
 def test_parse_date_fast_path_equals_the_format_loop():
     """exif_attrs.parse_date short-cuts the shape the indexer writes (YYYY-MM-DDTHH:MM:SS); it must accept, refuse and
     return exactly what the oracle's restatement of Searcher._parse_date (core/searcher.py:1963-2001) does."""
