@@ -153,3 +153,101 @@ def test_oracle_thresholds_equal_the_reference_searcher():
         want = [s._assign_confidence_bucket(item={"score": v}, strict_threshold=strict, broad_threshold=broad, media_terms=[],
                                             identity_terms=[], strict_identity_filter=False) for v in scores]
         assert buckets == want
+
+
+def _reference_searcher_class():
+    import sys
+    import types
+
+    from oracle import stage_reference
+
+    ref = stage_reference.locate()
+    if ref is None:
+        pytest.skip("reference Searcher neither checked out nor staged")
+    saved = list(sys.path)
+    sys.path.insert(0, ref)
+    try:
+        if "utils.vector_store" not in sys.modules:
+            shim = types.ModuleType("utils.vector_store")
+            shim.VectorStore = object
+            sys.modules["utils.vector_store"] = shim
+        from core.searcher import Searcher
+    finally:
+        sys.path[:] = saved
+    return Searcher
+
+
+def test_oracle_call_site_numerics_equal_the_reference_searcher():
+    """oracle.distance_to_score / calculate_candidate_k / hybrid_fuse restate core/searcher.py:605-625, :771-820, :855-988:
+    pinned against the reference's own methods on swept and random inputs (fakes stand in for the stores)."""
+    Searcher = _reference_searcher_class()
+
+    class Store:
+        metric, index_path, metadata_path = "cosine", "/tmp/_o.index", "/tmp/_o.json"
+
+        def __init__(self, n):
+            self.metadata = [{"photo_path": f"/p/{i}.jpg", "description": f"d{i}"} for i in range(n)]
+            self.hits = []
+
+        def get_total_items(self):
+            return len(self.metadata)
+
+        def search(self, q, k):
+            return self.hits[:k]
+
+        def load(self):
+            return True
+
+    class Keywords:
+        hits = []
+
+        def search(self, query, k):
+            return self.hits[:k]
+
+        def search_with_filters(self, query, filters, k):
+            return self.hits[:k]
+
+    class Emb:
+        def generate_embedding(self, text):
+            return [0.0]
+
+    class NoTime:
+        def extract_time_constraints(self, query):
+            return {}
+
+    rng = np.random.default_rng(8)
+    vs, ks = Store(400), Keywords()
+    s = Searcher(embedding=Emb(), time_parser=NoTime(), vector_store=vs, keyword_store=ks, query_formatter=None)
+    s.index_loaded = True
+    # _distance_to_score, both metrics, the knees, the clamps, NaN
+    sweep = np.concatenate([rng.uniform(-1.3, 1.3, 20_000), [0.4, -0.4, 1.0, -1.0, 0.0, np.nan, np.inf, -np.inf]]).astype(np.float32)
+    for metric, values in (("cosine", sweep), ("l2", np.abs(sweep) * 6 - 0.5)):
+        s.metric = metric
+        for v in values.tolist():
+            a, b = O.distance_to_score(v, metric), s._distance_to_score(v)
+            assert a == b or (a != a and b != b), (metric, v, a, b)
+    s.metric = "cosine"
+    # _calculate_candidate_k over every corpus-size regime
+    for n in (0, 1, 50, 51, 500, 501, 5000, 5001, 49_999, 60_000, 1_000_000):
+        vs.metadata = [None] * n
+        for top_k in (1, 5, 12, 50):
+            for has_filter in (False, True):
+                for level in range(6):
+                    assert s._calculate_candidate_k(top_k, has_filter, level) == O.calculate_candidate_k(n, top_k, has_filter, level)
+    # _hybrid_search fusion: random overlaps of vector candidates and keyword hits, keyword-only hits allowed or not
+    vs.metadata = [{"photo_path": f"/p/{i}.jpg", "description": f"d{i}"} for i in range(400)]
+    for trial in range(40):
+        nv, nk = int(rng.integers(1, 200)), int(rng.integers(0, 60))
+        ids = rng.permutation(400)[:nv]
+        dist = np.sort(rng.uniform(-0.3, 1.0, nv).astype(np.float32))[::-1]
+        vs.hits = [{"metadata": vs.metadata[i], "distance": float(x)} for i, x in zip(ids, dist)]
+        kid = rng.permutation(400)[:nk]
+        ks.hits = [{"photo_path": f"/p/{i}.jpg", "score": float(x)} for i, x in zip(kid, np.sort(rng.uniform(0, 1, nk))[::-1])]
+        allow = bool(trial % 2)
+        out = s._hybrid_search("q", [0.0], nv, filters=None, allow_keyword_only_results=allow)
+        got = [(int(r["photo_path"][3:-4]), r["score"], r["vector_score"], r["keyword_score"]) for r in out]
+        kk = max(1, min(nv, max(s.top_k * 3, 15)))  # core/searcher.py:905
+        want = O.hybrid_fuse([(int(i), float(x)) for i, x in zip(ids, dist)], [(int(i), h["score"]) for i, h in zip(kid, ks.hits)][:kk],
+                             vector_weight=s.vector_weight, keyword_weight=s.keyword_weight, allow_keyword_only=allow)
+        assert sorted(got) == sorted(want), trial                       # same entries, same three scores each
+        assert [g[1] for g in got] == [w[1] for w in want], trial       # same descending order of fused scores
