@@ -89,7 +89,7 @@ def _reference_searcher():
     return Searcher.__new__(Searcher)
 
 
-@settings(max_examples=400, deadline=None, suppress_health_check=[HealthCheck.too_slow])
+@settings(max_examples=400, deadline=None, derandomize=True, database=None, suppress_health_check=[HealthCheck.too_slow])
 @given(st.lists(records, min_size=1, max_size=12), constraints)
 def test_packed_predicate_equals_reference_rule(metas, cons):
     want = [O.check_time_match_v2(m, cons) for m in metas]
